@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE: regenerates tests/golden/ from the UNMODIFIED reference built in oracle/_ref
+(make -f oracle/Makefile.ref).  Run in the build container (needs /root/reference):
+
+    python oracle/gen_golden.py
+
+ * tests/golden/ref_vectors.json  per-function vectors printed by oracle/ref_probe.cc linked against the
+                                  reference's libscene.so (XorShift, TriRayIntersect, BoxRayIntersect,
+                                  make_transform_matrix/MatInverse, Camera::GetRay, FixedGridSampler,
+                                  Gaussian filter, SlFresnel/SlReflect/SlRefract, Mesh::ComputeNormals)
+ * tests/golden/ref_images.npz    whole frames rendered by the reference binary, thread_count 1
+                                  (float32 arrays parsed from its .fb text output), for tests/golden_scenes.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "tests"))
+import scenekit as sk  # noqa: E402
+import golden_scenes  # noqa: E402
+
+
+def main():
+    subprocess.check_call(["make", "-f", "oracle/Makefile.ref", "-j8"], cwd=REPO, stdout=subprocess.DEVNULL)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(sk.REF_DIR, "lib"))
+    txt = subprocess.check_output([os.path.join(sk.REF_DIR, "bin", "ref_probe"), "vectors"], env=env)
+    gold = os.path.join(REPO, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+    with open(os.path.join(gold, "ref_vectors.json"), "wb") as f:
+        f.write(txt)
+    imgs = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, make in golden_scenes.SCENES.items():
+            img, secs = sk.reference_render(make(), os.path.join(tmp, name), threads=1)
+            imgs[name] = img
+            print("%-16s %s  %.3fs  mean %.6f" % (name, img.shape, secs, img.mean()))
+    np.savez_compressed(os.path.join(gold, "ref_images.npz"), **imgs)
+
+
+if __name__ == "__main__":
+    main()
