@@ -15,7 +15,7 @@ LIBFJSCENE = os.path.join(HERE, "host", "libfjscene.so")
 FJGPU_MAX_SHADING_GROUPS = 8
 SHADER_NONE, SHADER_CONSTANT, SHADER_PLASTIC, SHADER_PATHTRACING = 0, 1, 2, 3
 LIGHT_POINT, LIGHT_GRID, LIGHT_SPHERE, LIGHT_DOME = 0, 1, 2, 3
-FLAG_FP32_BOXES, FLAG_NO_SMEM_TOP = 1, 2
+FLAG_FP64_BOXES = 1
 
 
 class Instance(C.Structure):

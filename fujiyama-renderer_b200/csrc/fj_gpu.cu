@@ -1,0 +1,669 @@
+// fj_gpu.cu — libfjgpu.so: the extern "C" ABI of include/fjgpu.h over the sm_100a kernels.
+//
+// Host side of the device path: keeps the scene description the caller hands over (meshes, instances,
+// object groups, shaders, lights, camera), builds the two BVH levels (fj_bvh.cc), lays everything out in
+// HBM (DESIGN.md "Data layout"), and runs the frame: batches of tiles -> k_render_samples ->
+// k_resolve_tiles -> packed tile blocks -> host frame / device frame / caller's device buffer.
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
+#include "fjgpu.h"
+#include "fj_bvh.h"
+#include "fj_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string g_last_error;
+
+struct DevBuf {
+  void *p = nullptr; size_t bytes = 0;
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct MeshRec {
+  DevBuf nodes, tri, N, idx, group;
+  fj::DMesh d;
+  double bmin[3], bmax[3];      // exact FP64 bounds of the mesh (Mesh::ComputeBounds, fj_mesh.cc:235-244)
+  int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0;
+  void release() { nodes.release(); tri.release(); N.release(); idx.release(); group.release(); }
+};
+
+}  // namespace
+
+struct fjgpu_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  int sm_count = 148;
+
+  std::map<int, MeshRec> meshes;
+  std::vector<fjgpu_instance> inst;
+  std::vector<int32_t> group_off, group_ids;
+  std::vector<fjgpu_shader> shaders;
+  std::vector<fjgpu_light> lights;
+  std::vector<std::vector<double>> dome_dirs;
+  std::vector<std::vector<float>> dome_cols;
+  fjgpu_camera cam;
+  bool have_cam = false, dirty = true;
+
+  // device scene
+  DevBuf d_meshes, d_inst, d_groups, d_shaders, d_lights;
+  std::vector<DevBuf> d_group_nodes, d_group_order, d_dome;
+  fj::DScene sc;
+  std::vector<int> mesh_slot_of_id;   // dense slot per mesh id (map order)
+  uint64_t tlas_nodes = 0;
+  double build_seconds = 0;
+
+  // frame resources
+  DevBuf d_samples, d_tiles, d_blocks, d_jitter, d_counters, d_frame;
+  size_t jitter_count = 0;
+  float *h_blocks = nullptr; size_t h_blocks_bytes = 0;
+};
+
+namespace {
+
+int fail(fjgpu_context *c, int code, const std::string &msg) {
+  g_last_error = msg;
+  if (c) c->err = msg;
+  return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, FJGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+int dev_alloc(fjgpu_context *ctx, DevBuf &b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return 0;
+  b.release();
+  if (bytes == 0) bytes = 16;
+  CK(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return 0;
+}
+int dev_upload(fjgpu_context *ctx, DevBuf &b, const void *src, size_t bytes) {
+  if (int rc = dev_alloc(ctx, b, bytes)) return rc;
+  if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+inline void rows12(const double *m16, double *m12) { memcpy(m12, m16, 12 * sizeof(double)); }
+
+// FP32 box of a set of FP64 points, rounded outward and padded by a few ulps so that culling never rejects
+// a box whose content the reference's FP64 tests would reach (fj_bvh.h).
+void pad_box(const double lo[3], const double hi[3], fjb::Aabb *b) {
+  for (int a = 0; a < 3; a++) {
+    const double m = std::max(std::fabs(lo[a]), std::fabs(hi[a]));
+    const double pad = 4e-7 * m + 1e-30;
+    b->lo[a] = fjb::round_down(lo[a] - pad);
+    b->hi[a] = fjb::round_up(hi[a] + pad);
+  }
+}
+
+// matrix * point with the reference's operation order (MatTransformPoint, src/fj_matrix.cc:209-215)
+inline void xpoint(const double *m, const double p[3], double out[3]) {
+  for (int r = 0; r < 3; r++) out[r] = m[4 * r] * p[0] + m[4 * r + 1] * p[1] + m[4 * r + 2] * p[2] + m[4 * r + 3];
+}
+
+int env_int(const char *name, int def) { const char *s = getenv(name); return s && *s ? atoi(s) : def; }
+
+// ---- scene commit: instances, TLAS per object group, shader/light tables ------------------------
+int commit_scene(fjgpu_context *ctx) {
+  if (!ctx->dirty) return 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  // dense mesh table
+  std::map<int, int> slot;
+  std::vector<fj::DMesh> dm;
+  for (auto &kv : ctx->meshes) { slot[kv.first] = (int)dm.size(); dm.push_back(kv.second.d); }
+  if (int rc = dev_upload(ctx, ctx->d_meshes, dm.data(), dm.size() * sizeof(fj::DMesh))) return rc;
+
+  const int ninst = (int)ctx->inst.size();
+  std::vector<fj::DInstance> di(ninst);
+  std::vector<fjb::Aabb> ibox(ninst);
+  for (int i = 0; i < ninst; i++) {
+    const fjgpu_instance &s = ctx->inst[i];
+    auto it = ctx->meshes.find(s.mesh_id);
+    if (it == ctx->meshes.end()) return fail(ctx, FJGPU_ERR_INVALID, "instance refers to an unknown mesh_id");
+    fj::DInstance &d = di[i];
+    memset(&d, 0, sizeof d);
+    rows12(s.inv, d.inv); rows12(s.fwd, d.fwd);
+    d.mesh = slot[s.mesh_id];
+    for (int g = 0; g < FJGPU_MAX_SHADING_GROUPS; g++) {
+      d.shader_of_group[g] = s.shader_of_group[g];
+      if (d.shader_of_group[g] >= (int)ctx->shaders.size()) return fail(ctx, FJGPU_ERR_INVALID, "instance refers to an unknown shader slot");
+    }
+    const int ng = (int)ctx->group_off.size() - 1;
+    if (s.reflect_target < 0 || s.reflect_target >= ng || s.refract_target < 0 || s.refract_target >= ng ||
+        s.shadow_target < 0 || s.shadow_target >= ng)
+      return fail(ctx, FJGPU_ERR_INVALID, "instance target group out of range (call fjgpu_groups_set first)");
+    d.reflect_target = s.reflect_target; d.refract_target = s.refract_target; d.shadow_target = s.shadow_target;
+    // world bounds: the mesh accelerator's padded bounds through the forward matrix
+    // (ObjectInstance::update_bounds, src/fj_object_instance.cc:299-360; MatTransformBounds, src/fj_matrix.cc:225-252)
+    const MeshRec &m = it->second;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    if (m.nfaces > 0) {
+      for (int c = 0; c < 8; c++) {
+        double p[3], q[3];
+        for (int a = 0; a < 3; a++) p[a] = ((c >> a) & 1) ? m.bmax[a] + 1e-4 : m.bmin[a] - 1e-4;
+        xpoint(s.fwd, p, q);
+        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[a]); }
+      }
+      pad_box(lo, hi, &ibox[i]);
+    } else {
+      for (int a = 0; a < 3; a++) { ibox[i].lo[a] = 3e38f; ibox[i].hi[a] = -3e38f; }
+    }
+  }
+  if (int rc = dev_upload(ctx, ctx->d_inst, di.data(), di.size() * sizeof(fj::DInstance))) return rc;
+
+  const int ngroups = (int)ctx->group_off.size() - 1;
+  for (auto &b : ctx->d_group_nodes) b.release();
+  for (auto &b : ctx->d_group_order) b.release();
+  ctx->d_group_nodes.assign(std::max(ngroups, 0), DevBuf());
+  ctx->d_group_order.assign(std::max(ngroups, 0), DevBuf());
+  std::vector<fj::DGroup> dg(std::max(ngroups, 0));
+  ctx->tlas_nodes = 0;
+  for (int g = 0; g < ngroups; g++) {
+    const int b = ctx->group_off[g], e = ctx->group_off[g + 1];
+    std::vector<fjb::Aabb> boxes; std::vector<int32_t> ids;
+    for (int k = b; k < e; k++) {
+      const int id = ctx->group_ids[k];
+      if (id < 0 || id >= ninst) return fail(ctx, FJGPU_ERR_INVALID, "object group refers to an unknown instance");
+      if (ibox[id].lo[0] > ibox[id].hi[0]) continue;      // empty mesh: can never be hit
+      boxes.push_back(ibox[id]); ids.push_back(id);
+    }
+    fjb::BuildResult br;
+    fjb::build_bvh(boxes.data(), (int32_t)boxes.size(), 1, 1.f, 0, &br);
+    std::vector<int32_t> order(std::max<size_t>(br.order.size(), 1), 0);
+    for (size_t k = 0; k < br.order.size(); k++) order[k] = ids[br.order[k]];
+    if (int rc = dev_upload(ctx, ctx->d_group_nodes[g], br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64))) return rc;
+    if (int rc = dev_upload(ctx, ctx->d_group_order[g], order.data(), order.size() * sizeof(int32_t))) return rc;
+    dg[g].nodes = (const float4 *)ctx->d_group_nodes[g].p;
+    dg[g].order = (const int32_t *)ctx->d_group_order[g].p;
+    dg[g].ninst = (int32_t)ids.size(); dg[g].pad = 0;
+    ctx->tlas_nodes += br.nodes.size();
+  }
+  if (int rc = dev_upload(ctx, ctx->d_groups, dg.data(), dg.size() * sizeof(fj::DGroup))) return rc;
+
+  std::vector<fj::DShader> ds(ctx->shaders.size());
+  for (size_t i = 0; i < ds.size(); i++) {
+    const fjgpu_shader &s = ctx->shaders[i]; fj::DShader &d = ds[i];
+    d.kind = s.kind; d.do_reflect = s.do_reflect; d.do_color_filter = s.do_color_filter; d.pad = 0;
+    memcpy(d.diffuse, s.diffuse, 12); memcpy(d.reflect, s.reflect, 12); memcpy(d.refract, s.refract, 12);
+    memcpy(d.emission, s.emission, 12); memcpy(d.transmit, s.transmit, 12);
+    d.ior = s.ior; d.opacity = s.opacity;
+  }
+  if (int rc = dev_upload(ctx, ctx->d_shaders, ds.data(), ds.size() * sizeof(fj::DShader))) return rc;
+
+  for (auto &b : ctx->d_dome) b.release();
+  ctx->d_dome.assign(2 * ctx->lights.size(), DevBuf());
+  std::vector<fj::DLight> dl(ctx->lights.size());
+  for (size_t i = 0; i < dl.size(); i++) {
+    const fjgpu_light &s = ctx->lights[i]; fj::DLight &d = dl[i];
+    memset(&d, 0, sizeof d);
+    d.kind = s.kind; d.sample_count = s.sample_count; d.double_sided = s.double_sided;
+    d.dome_count = (int32_t)(ctx->dome_dirs[i].size() / 3);
+    memcpy(d.color, s.color, 12); d.intensity = s.intensity;
+    memcpy(d.translate, s.translate, 24); rows12(s.fwd, d.fwd);
+    if (d.dome_count > 0) {
+      if (int rc = dev_upload(ctx, ctx->d_dome[2 * i], ctx->dome_dirs[i].data(), ctx->dome_dirs[i].size() * 8)) return rc;
+      if (int rc = dev_upload(ctx, ctx->d_dome[2 * i + 1], ctx->dome_cols[i].data(), ctx->dome_cols[i].size() * 4)) return rc;
+      d.dome_dirs = (const double *)ctx->d_dome[2 * i].p; d.dome_colors = (const float *)ctx->d_dome[2 * i + 1].p;
+    }
+  }
+  if (int rc = dev_upload(ctx, ctx->d_lights, dl.data(), dl.size() * sizeof(fj::DLight))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+
+  fj::DScene &sc = ctx->sc;
+  sc.meshes = (const fj::DMesh *)ctx->d_meshes.p; sc.inst = (const fj::DInstance *)ctx->d_inst.p;
+  sc.groups = (const fj::DGroup *)ctx->d_groups.p; sc.shaders = (const fj::DShader *)ctx->d_shaders.p;
+  sc.lights = (const fj::DLight *)ctx->d_lights.p;
+  sc.nmeshes = (int)dm.size(); sc.ninst = ninst; sc.ngroups = ngroups; sc.nshaders = (int)ds.size(); sc.nlights = (int)dl.size(); sc.pad = 0;
+  ctx->dirty = false;
+  ctx->build_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+// ---- frame set-up ---------------------------------------------------------------------------------
+struct FramePlan {
+  fj::DFrame fr; fj::DCamera cam;
+  uint32_t wstride = 0; int bw = 0, bh = 0;
+  int tiles_per_batch = 0;
+};
+
+int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_tile *tiles, int ntiles, FramePlan *pl) {
+  if (!p || (!tiles && ntiles > 0) || ntiles < 0) return fail(ctx, FJGPU_ERR_INVALID, "null params/tiles");
+  if (p->xres <= 0 || p->yres <= 0 || p->xrate <= 0 || p->yrate <= 0 || !(p->xfwidth > 0) || !(p->yfwidth > 0))
+    return fail(ctx, FJGPU_ERR_INVALID, "resolution, pixelsamples and filterwidth must be positive");
+  if (!ctx->have_cam) return fail(ctx, FJGPU_ERR_INVALID, "no camera set");
+  if (int rc = commit_scene(ctx)) return rc;
+  if (p->target_group < 0 || p->target_group >= ctx->sc.ngroups) return fail(ctx, FJGPU_ERR_INVALID, "target_group out of range");
+  if (p->max_diffuse_depth < 0 || p->max_reflect_depth < 0 || p->max_refract_depth < 0 ||
+      2 * (p->max_diffuse_depth + p->max_reflect_depth + p->max_refract_depth) + 1 > FJ_PENDING)
+    return fail(ctx, FJGPU_ERR_UNSUPPORTED, "max_*_depth: 2*(diffuse+reflect+refract)+1 exceeds the per-path ray stack");
+  fj::DFrame &fr = pl->fr;
+  memset(&fr, 0, sizeof fr);
+  fr.xres = p->xres; fr.yres = p->yres; fr.xrate = p->xrate; fr.yrate = p->yrate;
+  // count_samples_in_margin, src/fj_fixed_grid_sampler.cc:131-136
+  fr.mx = (int)std::ceil(((p->xfwidth - 1) * p->xrate) * .5);
+  fr.my = (int)std::ceil(((p->yfwidth - 1) * p->yrate) * .5);
+  if (fr.mx < 0) fr.mx = 0; if (fr.my < 0) fr.my = 0;
+  fr.xfw = p->xfwidth; fr.yfw = p->yfwidth; fr.jitter = p->jitter;
+  fr.udelta = 1. / (p->xrate * p->xres); fr.vdelta = 1. / (p->yrate * p->yres);       // :45-46
+  fr.max_diffuse = p->max_diffuse_depth; fr.max_reflect = p->max_reflect_depth; fr.max_refract = p->max_refract_depth;
+  fr.cast_shadow = p->cast_shadow; fr.target_group = p->target_group; fr.seed = p->seed; fr.flags = p->flags;
+  int tw = 1, th = 1;
+  for (int i = 0; i < ntiles; i++) {
+    const fjgpu_tile &t = tiles[i];
+    if (t.xmax <= t.xmin || t.ymax <= t.ymin) return fail(ctx, FJGPU_ERR_INVALID, "empty tile");
+    if (t.xmin < 0 || t.ymin < 0 || t.xmax > p->xres || t.ymax > p->yres) return fail(ctx, FJGPU_ERR_INVALID, "tile outside the frame");
+    tw = std::max(tw, t.xmax - t.xmin); th = std::max(th, t.ymax - t.ymin);
+  }
+  pl->bw = tw; pl->bh = th;
+  const long nsx = (long)p->xrate * tw + 2 * fr.mx, nsy = (long)p->yrate * th + 2 * fr.my;
+  const long slots = ((nsx + 7) / 8) * ((nsy + 3) / 4) * 32;
+  if (slots > (1l << 30)) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "tile sample grid too large");
+  pl->wstride = (uint32_t)slots;
+  fr.max_ns = (int32_t)(nsx * nsy);
+  // jitter table: the first 2*max_ns draws of a default-seeded XorShift (src/fj_random.cc:10-43) —
+  // every tile restarts the same stream (src/fj_fixed_grid_sampler.cc:41-42)
+  const size_t need = 2 * (size_t)fr.max_ns;
+  if (ctx->jitter_count < need) {
+    std::vector<uint32_t> tab(need);
+    uint32_t s[4] = {123456789u, 362436069u, 521288629u, 88675123u};
+    for (size_t i = 0; i < need; i++) {
+      const uint32_t t = s[0] ^ (s[0] << 11);
+      s[0] = s[1]; s[1] = s[2]; s[2] = s[3];
+      s[3] = (s[3] ^ (s[3] >> 19)) ^ (t ^ (t >> 8));
+      tab[i] = s[3];
+    }
+    if (int rc = dev_upload(ctx, ctx->d_jitter, tab.data(), need * 4)) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->jitter_count = need;
+  }
+  fr.jitter_tab = (const uint32_t *)ctx->d_jitter.p;
+  // Camera: uv_size_ (src/fj_camera.cc:97-101 via update_uv_size) — aspect = xres / (double) yres
+  const double PI = 3.14159265358979323846;
+  const double aspect = p->xres / (double)p->yres;
+  pl->cam.uvy = 2 * std::tan((ctx->cam.fov / 2.) * PI / 180.);
+  pl->cam.uvx = pl->cam.uvy * aspect;
+  rows12(ctx->cam.fwd, pl->cam.fwd); pl->cam.znear = ctx->cam.znear; pl->cam.zfar = ctx->cam.zfar;
+  // batch so the sample buffer stays bounded (default 1 GiB)
+  const size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 1024) << 20;
+  long per = (long)(cap / ((size_t)pl->wstride * sizeof(float4)));
+  pl->tiles_per_batch = (int)std::max(1l, std::min<long>(per, std::max(ntiles, 1)));
+  return 0;
+}
+
+enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
+
+template <typename T>
+void launch_samples(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
+  fj::k_render_samples<T><<<blocks, 128, 0, ctx->stream>>>(a);
+}
+
+int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_tile *tiles, int ntiles, int mode,
+                float *rgba_frame, void *d_out_blocks, int out_bw, int out_bh, fjgpu_stats *stats) {
+  if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
+  CK(cudaSetDevice(ctx->device));
+  FramePlan pl;
+  if (int rc = plan_frame(ctx, p, tiles, ntiles, &pl)) return rc;
+  if (mode == OUT_DEVICE_BLOCKS) {
+    if (out_bw < pl.bw || out_bh < pl.bh) return fail(ctx, FJGPU_ERR_INVALID, "tile_w_max/tile_h_max smaller than a tile");
+    pl.bw = out_bw; pl.bh = out_bh;
+  }
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (ntiles == 0) return 0;
+  const size_t block_floats = (size_t)pl.bw * pl.bh * 4;
+
+  if (int rc = dev_upload(ctx, ctx->d_tiles, tiles, (size_t)ntiles * sizeof(fjgpu_tile))) return rc;
+  if (int rc = dev_alloc(ctx, ctx->d_samples, (size_t)pl.tiles_per_batch * pl.wstride * sizeof(float4))) return rc;
+  if (int rc = dev_alloc(ctx, ctx->d_counters, sizeof(fj::DCounters) + 64)) return rc;
+  float4 *blocks = nullptr;
+  if (mode == OUT_DEVICE_BLOCKS) {
+    blocks = (float4 *)d_out_blocks;
+    CK(cudaMemsetAsync(blocks, 0, (size_t)ntiles * block_floats * 4, ctx->stream));
+  } else if (mode != OUT_SAMPLES_ONLY) {
+    if (int rc = dev_alloc(ctx, ctx->d_blocks, (size_t)ntiles * block_floats * 4)) return rc;
+    blocks = (float4 *)ctx->d_blocks.p;
+  }
+  if (mode == OUT_RESIDENT)
+    if (int rc = dev_alloc(ctx, ctx->d_frame, (size_t)p->xres * p->yres * sizeof(float4))) return rc;
+  if (mode == OUT_HOST && ctx->h_blocks_bytes < (size_t)ntiles * block_floats * 4) {
+    if (ctx->h_blocks) cudaFreeHost(ctx->h_blocks);
+    ctx->h_blocks = nullptr; ctx->h_blocks_bytes = 0;
+    CK(cudaMallocHost((void **)&ctx->h_blocks, (size_t)ntiles * block_floats * 4));
+    ctx->h_blocks_bytes = (size_t)ntiles * block_floats * 4;
+  }
+  CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(fj::DCounters) + 64, ctx->stream));
+
+  const int blocks_per_sm = env_int("FJGPU_BLOCKS_PER_SM", 4);
+  const int grid = ctx->sm_count * blocks_per_sm;
+  uint64_t launches = 0;
+  float ms_trace = 0, ms_resolve = 0;
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  for (int b0 = 0; b0 < ntiles; b0 += pl.tiles_per_batch) {
+    const int nb = std::min(pl.tiles_per_batch, ntiles - b0);
+    fj::RenderArgs a;
+    a.sc = ctx->sc; a.cam = pl.cam; a.fr = pl.fr;
+    a.tiles = (const fj::DTile *)ctx->d_tiles.p + b0; a.ntiles = nb; a.wstride = pl.wstride;
+    a.samples = (float4 *)ctx->d_samples.p;
+    a.counters = (fj::DCounters *)ctx->d_counters.p;
+    a.work = (unsigned long long *)((char *)ctx->d_counters.p + sizeof(fj::DCounters));
+    CK(cudaMemsetAsync(a.work, 0, 8, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (p->flags & FJGPU_FLAG_FP64_BOXES) launch_samples<double>(ctx, a, grid);
+    else launch_samples<float>(ctx, a, grid);
+    launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (mode != OUT_SAMPLES_ONLY) {
+      fj::k_resolve_tiles<<<nb, 256, 0, ctx->stream>>>(pl.fr, a.tiles, pl.wstride, a.samples, blocks + (size_t)b0 * pl.bw * pl.bh, pl.bw, pl.bh);
+      launches++;
+      CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (ntiles > pl.tiles_per_batch || stats) {     // per-batch timing needs the events read before reuse
+      CK(cudaEventSynchronize(ctx->ev[3]));
+      float t1 = 0, t2 = 0;
+      cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]); cudaEventElapsedTime(&t2, ctx->ev[2], ctx->ev[3]);
+      ms_trace += t1; ms_resolve += t2;
+    }
+  }
+  if (mode == OUT_RESIDENT) {
+    fj::k_blocks_to_frame<<<ntiles, 256, 0, ctx->stream>>>((const fj::DTile *)ctx->d_tiles.p, ntiles, blocks, pl.bw, pl.bh, (float4 *)ctx->d_frame.p, p->xres);
+    launches++;
+    CK(cudaGetLastError());
+  }
+  if (mode == OUT_HOST) CK(cudaMemcpyAsync(ctx->h_blocks, blocks, (size_t)ntiles * block_floats * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  fj::DCounters hc; memset(&hc, 0, sizeof hc);
+  if (stats) CK(cudaMemcpyAsync(&hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (mode == OUT_HOST) {
+    if (!rgba_frame) return fail(ctx, FJGPU_ERR_INVALID, "null framebuffer");
+    for (int i = 0; i < ntiles; i++) {
+      const fjgpu_tile &t = tiles[i];
+      const int w = t.xmax - t.xmin;
+      for (int y = t.ymin; y < t.ymax; y++)
+        memcpy(rgba_frame + ((size_t)y * p->xres + t.xmin) * 4, ctx->h_blocks + (size_t)i * block_floats + (size_t)(y - t.ymin) * pl.bw * 4, (size_t)w * 16);
+    }
+  }
+  if (stats) {
+    float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[3]);
+    stats->rays_camera = hc.rays[0]; stats->rays_shadow = hc.rays[1]; stats->rays_diffuse = hc.rays[2];
+    stats->rays_reflect = hc.rays[3]; stats->rays_refract = hc.rays[4]; stats->camera_samples = hc.samples;
+    stats->kernel_launches = launches; stats->ms_trace = ms_trace; stats->ms_resolve = ms_resolve; stats->ms_total = tot;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================== extern "C"
+extern "C" {
+
+int fjgpu_api_version(void) { return FJGPU_API_VERSION; }
+
+const char *fjgpu_last_error(const fjgpu_context *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int fjgpu_create(int device_ordinal, fjgpu_context **out_ctx) {
+  if (!out_ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null out_ctx");
+  *out_ctx = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) return fail(nullptr, FJGPU_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libfjgpu has no CPU fallback)");
+  if (device_ordinal < 0 || device_ordinal >= n) return fail(nullptr, FJGPU_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess || prop.major < 10)
+    return fail(nullptr, FJGPU_ERR_NO_DEVICE, "device is not sm_100 class (this library carries sm_100a code only)");
+  fjgpu_context *ctx = new fjgpu_context();
+  ctx->device = device_ordinal; ctx->sm_count = prop.multiProcessorCount;
+  memset(&ctx->sc, 0, sizeof ctx->sc); memset(&ctx->cam, 0, sizeof ctx->cam);
+  ctx->group_off.assign(1, 0);
+  if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx; return fail(nullptr, FJGPU_ERR_CUDA, "cannot create a stream");
+  }
+  for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+  cudaDeviceSetLimit(cudaLimitStackSize, 8192);
+  *out_ctx = ctx;
+  return FJGPU_OK;
+}
+
+void fjgpu_destroy(fjgpu_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->meshes) kv.second.release();
+  for (auto &b : ctx->d_group_nodes) b.release();
+  for (auto &b : ctx->d_group_order) b.release();
+  for (auto &b : ctx->d_dome) b.release();
+  DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
+                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame};
+  for (DevBuf *b : all) b->release();
+  if (ctx->h_blocks) cudaFreeHost(ctx->h_blocks);
+  for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, const double *N, int32_t nverts,
+                      const int32_t *idx3, const int32_t *face_group_id, int32_t nfaces) {
+  if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
+  if (nverts < 0 || nfaces < 0 || (nverts > 0 && !P) || (nfaces > 0 && !idx3)) return fail(ctx, FJGPU_ERR_INVALID, "bad mesh arrays");
+  if (nfaces >= (1 << 28)) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "more than 2^28 faces in one mesh");
+  for (size_t i = 0; i < 3 * (size_t)nfaces; i++)
+    if (idx3[i] < 0 || idx3[i] >= nverts) return fail(ctx, FJGPU_ERR_INVALID, "face index out of range");
+  CK(cudaSetDevice(ctx->device));
+  const auto t0 = std::chrono::steady_clock::now();
+  MeshRec &m = ctx->meshes[mesh_id];
+  m.release();
+  m.nfaces = nfaces; m.nverts = nverts;
+  bool f32ok = true;
+  for (size_t i = 0; i < 3 * (size_t)nverts && f32ok; i++) f32ok = ((double)(float)P[i] == P[i]);
+  if (env_int("FJGPU_FORCE_TRI64", 0)) f32ok = false;
+  std::vector<fjb::Aabb> boxes(nfaces);
+  for (int a = 0; a < 3; a++) { m.bmin[a] = 1.7976931348623157e308; m.bmax[a] = -1.7976931348623157e308; }
+  for (int f = 0; f < nfaces; f++) {
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+      const double x = P[3 * (size_t)idx3[3 * f] + a], y = P[3 * (size_t)idx3[3 * f + 1] + a], z = P[3 * (size_t)idx3[3 * f + 2] + a];
+      lo[a] = std::min(x, std::min(y, z)); hi[a] = std::max(x, std::max(y, z));
+      m.bmin[a] = std::min(m.bmin[a], lo[a]); m.bmax[a] = std::max(m.bmax[a], hi[a]);
+    }
+    pad_box(lo, hi, &boxes[f]);
+  }
+  fjb::BuildResult br;
+  fjb::build_bvh(boxes.data(), nfaces, env_int("FJGPU_MAX_LEAF", 4), (float)env_int("FJGPU_LEAF_COST_X10", 15) / 10.f, 0, &br);
+  m.nnodes = (int32_t)br.nodes.size(); m.max_depth = br.max_depth;
+  if (br.max_depth + 8 > FJ_STACK) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+  if (int rc = dev_upload(ctx, m.nodes, br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64))) return rc;
+  memset(&m.d, 0, sizeof m.d);
+  m.d.nodes = (const float4 *)m.nodes.p;
+  const size_t nt = br.order.size();
+  if (f32ok) {
+    std::vector<float> tri(std::max<size_t>(nt, 1) * 12, 0.f);
+    for (size_t k = 0; k < nt; k++) {
+      const int f = br.order[k];
+      for (int v = 0; v < 3; v++) {
+        for (int a = 0; a < 3; a++) tri[12 * k + 4 * v + a] = (float)P[3 * (size_t)idx3[3 * f + v] + a];
+      }
+      memcpy(&tri[12 * k + 3], &f, 4);
+    }
+    if (int rc = dev_upload(ctx, m.tri, tri.data(), tri.size() * 4)) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    m.d.tri32 = (const float4 *)m.tri.p;
+  } else {
+    std::vector<double> tri(std::max<size_t>(nt, 1) * 10, 0.);
+    for (size_t k = 0; k < nt; k++) {
+      const int f = br.order[k];
+      for (int v = 0; v < 3; v++) for (int a = 0; a < 3; a++) tri[10 * k + 3 * v + a] = P[3 * (size_t)idx3[3 * f + v] + a];
+      const long long fl = f; memcpy(&tri[10 * k + 9], &fl, 8);
+    }
+    if (int rc = dev_upload(ctx, m.tri, tri.data(), tri.size() * 8)) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    m.d.tri64 = (const double *)m.tri.p;
+  }
+  if (N) { if (int rc = dev_upload(ctx, m.N, N, (size_t)nverts * 24)) return rc; m.d.N = (const double *)m.N.p; }
+  if (int rc = dev_upload(ctx, m.idx, idx3, (size_t)nfaces * 12)) return rc;
+  m.d.idx = (const int32_t *)m.idx.p;
+  if (face_group_id) { if (int rc = dev_upload(ctx, m.group, face_group_id, (size_t)nfaces * 4)) return rc; m.d.group = (const int32_t *)m.group.p; }
+  m.d.top_count = br.top_count;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->dirty = true;
+  ctx->build_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return FJGPU_OK;
+}
+
+int fjgpu_instances_set(fjgpu_context *ctx, int32_t n, const fjgpu_instance *inst) {
+  if (!ctx || n < 0 || (n > 0 && !inst)) return fail(ctx, FJGPU_ERR_INVALID, "bad instance array");
+  ctx->inst.assign(inst, inst + n); ctx->dirty = true;
+  return FJGPU_OK;
+}
+
+int fjgpu_groups_set(fjgpu_context *ctx, int32_t ngroups, const int32_t *group_offsets, const int32_t *instance_ids) {
+  if (!ctx || ngroups < 0 || (ngroups > 0 && !group_offsets)) return fail(ctx, FJGPU_ERR_INVALID, "bad group arrays");
+  ctx->group_off.assign(1, 0); ctx->group_ids.clear();
+  if (ngroups > 0) {
+    if (group_offsets[0] != 0) return fail(ctx, FJGPU_ERR_INVALID, "group_offsets[0] must be 0");
+    for (int g = 0; g < ngroups; g++) if (group_offsets[g + 1] < group_offsets[g]) return fail(ctx, FJGPU_ERR_INVALID, "group_offsets must be non-decreasing");
+    ctx->group_off.assign(group_offsets, group_offsets + ngroups + 1);
+    if (group_offsets[ngroups] > 0 && !instance_ids) return fail(ctx, FJGPU_ERR_INVALID, "null instance_ids");
+    ctx->group_ids.assign(instance_ids, instance_ids + group_offsets[ngroups]);
+  }
+  ctx->dirty = true;
+  return FJGPU_OK;
+}
+
+int fjgpu_shaders_set(fjgpu_context *ctx, int32_t n, const fjgpu_shader *shaders) {
+  if (!ctx || n < 0 || (n > 0 && !shaders)) return fail(ctx, FJGPU_ERR_INVALID, "bad shader array");
+  for (int i = 0; i < n; i++) if (shaders[i].kind < FJGPU_SHADER_NONE || shaders[i].kind > FJGPU_SHADER_PATHTRACING)
+    return fail(ctx, FJGPU_ERR_UNSUPPORTED, "shader kind has no device implementation");
+  ctx->shaders.assign(shaders, shaders + n); ctx->dirty = true;
+  return FJGPU_OK;
+}
+
+int fjgpu_lights_set(fjgpu_context *ctx, int32_t n, const fjgpu_light *lights) {
+  if (!ctx || n < 0 || (n > 0 && !lights)) return fail(ctx, FJGPU_ERR_INVALID, "bad light array");
+  ctx->lights.assign(lights, lights + n);
+  ctx->dome_dirs.assign(n, std::vector<double>()); ctx->dome_cols.assign(n, std::vector<float>());
+  for (int i = 0; i < n; i++) {
+    fjgpu_light &l = ctx->lights[i];
+    if (l.kind < FJGPU_LIGHT_POINT || l.kind > FJGPU_LIGHT_DOME) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "unknown light kind");
+    if (l.kind == FJGPU_LIGHT_DOME && l.dome_sample_count > 0) {
+      if (!l.dome_dirs || !l.dome_colors) return fail(ctx, FJGPU_ERR_INVALID, "dome light without sample tables");
+      ctx->dome_dirs[i].assign(l.dome_dirs, l.dome_dirs + 3 * (size_t)l.dome_sample_count);
+      ctx->dome_cols[i].assign(l.dome_colors, l.dome_colors + 3 * (size_t)l.dome_sample_count);
+    }
+    l.dome_dirs = nullptr; l.dome_colors = nullptr;    // the caller's buffers are not kept
+  }
+  ctx->dirty = true;
+  return FJGPU_OK;
+}
+
+int fjgpu_camera_set(fjgpu_context *ctx, const fjgpu_camera *cam) {
+  if (!ctx || !cam) return fail(ctx, FJGPU_ERR_INVALID, "null camera");
+  ctx->cam = *cam; ctx->have_cam = true;
+  return FJGPU_OK;
+}
+
+int fjgpu_render_tiles(fjgpu_context *ctx, const fjgpu_render_params *params, const fjgpu_tile *tiles, int32_t ntiles,
+                       float *rgba_frame, fjgpu_stats *stats) {
+  if (!rgba_frame && ntiles > 0) return fail(ctx, FJGPU_ERR_INVALID, "null framebuffer");
+  return render_impl(ctx, params, tiles, ntiles, OUT_HOST, rgba_frame, nullptr, 0, 0, stats);
+}
+
+int fjgpu_render_tiles_device(fjgpu_context *ctx, const fjgpu_render_params *params, const fjgpu_tile *tiles, int32_t ntiles,
+                              int32_t tile_w_max, int32_t tile_h_max, void *d_tile_blocks, fjgpu_stats *stats) {
+  if (!d_tile_blocks && ntiles > 0) return fail(ctx, FJGPU_ERR_INVALID, "null device buffer");
+  return render_impl(ctx, params, tiles, ntiles, OUT_DEVICE_BLOCKS, nullptr, d_tile_blocks, tile_w_max, tile_h_max, stats);
+}
+
+int fjgpu_render_tiles_resident(fjgpu_context *ctx, const fjgpu_render_params *params, const fjgpu_tile *tiles, int32_t ntiles,
+                                fjgpu_stats *stats) {
+  return render_impl(ctx, params, tiles, ntiles, OUT_RESIDENT, nullptr, nullptr, 0, 0, stats);
+}
+
+int fjgpu_trace_closest(fjgpu_context *ctx, int32_t group, int32_t n, const double *orig3, const double *dir3,
+                        const double *tmin, const double *tmax, int32_t flags,
+                        double *out_t, double *out_u, double *out_v, int32_t *out_prim, int32_t *out_inst) {
+  if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
+  if (n < 0 || (n > 0 && (!orig3 || !dir3 || !tmin || !tmax || !out_t || !out_u || !out_v || !out_prim || !out_inst)))
+    return fail(ctx, FJGPU_ERR_INVALID, "null ray arrays");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = commit_scene(ctx)) return rc;
+  if (group < 0 || group >= ctx->sc.ngroups) return fail(ctx, FJGPU_ERR_INVALID, "group out of range");
+  if (n == 0) return FJGPU_OK;
+  DevBuf o, d, t0, t1, rt, ru, rv, rp, ri;
+  int rc = 0;
+  const size_t N = (size_t)n;
+  if ((rc = dev_upload(ctx, o, orig3, N * 24)) || (rc = dev_upload(ctx, d, dir3, N * 24)) || (rc = dev_upload(ctx, t0, tmin, N * 8)) ||
+      (rc = dev_upload(ctx, t1, tmax, N * 8)) || (rc = dev_alloc(ctx, rt, N * 8)) || (rc = dev_alloc(ctx, ru, N * 8)) ||
+      (rc = dev_alloc(ctx, rv, N * 8)) || (rc = dev_alloc(ctx, rp, N * 4)) || (rc = dev_alloc(ctx, ri, N * 4))) {
+    DevBuf *all[] = {&o, &d, &t0, &t1, &rt, &ru, &rv, &rp, &ri}; for (DevBuf *b : all) b->release();
+    return rc;
+  }
+  const int grid = (n + 127) / 128;
+  if (flags & FJGPU_FLAG_FP64_BOXES)
+    fj::k_trace_closest<double><<<grid, 128, 0, ctx->stream>>>(ctx->sc, group, n, (const double *)o.p, (const double *)d.p, (const double *)t0.p, (const double *)t1.p,
+                                                               (double *)rt.p, (double *)ru.p, (double *)rv.p, (int32_t *)rp.p, (int32_t *)ri.p);
+  else
+    fj::k_trace_closest<float><<<grid, 128, 0, ctx->stream>>>(ctx->sc, group, n, (const double *)o.p, (const double *)d.p, (const double *)t0.p, (const double *)t1.p,
+                                                              (double *)rt.p, (double *)ru.p, (double *)rv.p, (int32_t *)rp.p, (int32_t *)ri.p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_t, rt.p, N * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_u, ru.p, N * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_v, rv.p, N * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_prim, rp.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_inst, ri.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  DevBuf *all[] = {&o, &d, &t0, &t1, &rt, &ru, &rv, &rp, &ri}; for (DevBuf *b : all) b->release();
+  if (e != cudaSuccess) return fail(ctx, FJGPU_ERR_CUDA, std::string("trace_closest: ") + cudaGetErrorString(e));
+  return FJGPU_OK;
+}
+
+int fjgpu_render_tile_samples(fjgpu_context *ctx, const fjgpu_render_params *params, const fjgpu_tile *tile, int32_t max_samples,
+                              double *out_uv, float *out_rgba, int32_t *out_nsamples) {
+  if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
+  if (!tile || !out_nsamples) return fail(ctx, FJGPU_ERR_INVALID, "null tile");
+  int rc = render_impl(ctx, params, tile, 1, OUT_SAMPLES_ONLY, nullptr, nullptr, 0, 0, nullptr);
+  if (rc) return rc;
+  FramePlan pl;
+  if ((rc = plan_frame(ctx, params, tile, 1, &pl))) return rc;
+  const int n = pl.fr.max_ns;
+  *out_nsamples = n;
+  if (max_samples < n || !out_uv || !out_rgba) return FJGPU_OK;    // size query
+  DevBuf duv, drgba;
+  if ((rc = dev_alloc(ctx, duv, (size_t)n * 16)) || (rc = dev_alloc(ctx, drgba, (size_t)n * 16))) { duv.release(); drgba.release(); return rc; }
+  fj::DTile t; t.id = tile->id; t.xmin = tile->xmin; t.ymin = tile->ymin; t.xmax = tile->xmax; t.ymax = tile->ymax;
+  fj::k_dump_tile_samples<<<std::min((n + 255) / 256, 1024), 256, 0, ctx->stream>>>(pl.fr, t, (const float4 *)ctx->d_samples.p, (double *)duv.p, (float4 *)drgba.p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_uv, duv.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgba, drgba.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  duv.release(); drgba.release();
+  if (e != cudaSuccess) return fail(ctx, FJGPU_ERR_CUDA, std::string("render_tile_samples: ") + cudaGetErrorString(e));
+  return FJGPU_OK;
+}
+
+int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info) {
+  if (!ctx || !info) return fail(ctx, FJGPU_ERR_INVALID, "null argument");
+  memset(info, 0, sizeof *info);
+  for (auto &kv : ctx->meshes) {
+    const MeshRec &m = kv.second;
+    info->hbm_bytes += m.nodes.bytes + m.tri.bytes + m.N.bytes + m.idx.bytes + m.group.bytes;
+    info->blas_nodes += m.nnodes; info->blas_tris += m.nfaces;
+    info->blas_max_depth = std::max<uint32_t>(info->blas_max_depth, (uint32_t)m.max_depth);
+  }
+  info->hbm_bytes += ctx->d_inst.bytes + ctx->d_shaders.bytes + ctx->d_lights.bytes;
+  for (auto &b : ctx->d_group_nodes) info->hbm_bytes += b.bytes;
+  info->tlas_nodes = ctx->tlas_nodes; info->instances = ctx->inst.size();
+  info->build_seconds = ctx->build_seconds;
+  return FJGPU_OK;
+}
+
+}  // extern "C"

@@ -157,8 +157,8 @@ typedef struct fjgpu_render_params {
   int32_t _pad;
 } fjgpu_render_params;
 
-enum { FJGPU_FLAG_FP32_BOXES = 1,   /* cull BVH boxes in FP32 (conservative) instead of FP64 */
-       FJGPU_FLAG_NO_SMEM_TOP = 2   /* do not stage the top of the BVH in shared memory     */ };
+enum { FJGPU_FLAG_FP64_BOXES = 1    /* cull BVH boxes with FP64 slab arithmetic instead of the default
+                                       conservative FP32 (same hits; a cross-check for the parity tests) */ };
 
 typedef struct fjgpu_tile {         /* Tile of src/fj_tiler.h; [xmin,xmax) x [ymin,ymax) pixels */
   int32_t id;                       /* global tile id in the frame's tile list (keys the RNG) */
