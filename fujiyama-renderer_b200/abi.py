@@ -66,6 +66,7 @@ class Stats(C.Structure):
     _fields_ = [("rays_camera", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("rays_diffuse", C.c_uint64), ("rays_reflect", C.c_uint64),
                 ("rays_refract", C.c_uint64), ("camera_samples", C.c_uint64),
+                ("rays_hit", C.c_uint64), ("hit_mesh_levels", C.c_uint64),
                 ("kernel_launches", C.c_uint64),
                 ("ms_trace", C.c_float), ("ms_resolve", C.c_float),
                 ("ms_total", C.c_float), ("_pad", C.c_float)]
@@ -89,7 +90,7 @@ FJGPU_SYMBOLS = [
     "fjgpu_mesh_upload", "fjgpu_instances_set", "fjgpu_groups_set", "fjgpu_shaders_set",
     "fjgpu_lights_set", "fjgpu_camera_set", "fjgpu_render_tiles", "fjgpu_render_tiles_device",
     "fjgpu_render_tiles_resident", "fjgpu_trace_closest", "fjgpu_render_tile_samples",
-    "fjgpu_scene_info_get",
+    "fjgpu_scene_info_get", "fjgpu_scene_resend",
 ]
 
 _P = C.POINTER
@@ -114,6 +115,7 @@ def _proto(lib):
     lib.fjgpu_trace_closest.argtypes = [vp, i32, i32, f64p, f64p, f64p, f64p, i32, f64p, f64p, f64p, i32p, i32p]
     lib.fjgpu_render_tile_samples.argtypes = [vp, _P(RenderParams), _P(Tile), i32, f64p, _P(C.c_float), i32p]
     lib.fjgpu_scene_info_get.argtypes = [vp, _P(SceneInfo)]
+    lib.fjgpu_scene_resend.argtypes = [vp, _P(C.c_uint64)]
     return lib
 
 

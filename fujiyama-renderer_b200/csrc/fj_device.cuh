@@ -63,8 +63,8 @@ struct DMesh {
   const double *N;          // vertex normals, 3 doubles per vertex (may be null)
   const int32_t *idx;       // 3 vertex indices per face (original order)
   const int32_t *group;     // shading group per face (may be null -> 0)
-  int32_t top_count;        // leading BFS-ordered nodes eligible for shared-memory staging
-  int32_t pad;
+  int32_t top_count;        // leading BFS-ordered nodes (reserved for shared-memory staging)
+  int32_t log2_tris;        // ceil(log2(triangle count)): root-to-leaf path length of the algorithmic-bytes model
 };
 struct DInstance {
   double inv[12];           // rows 0..2 of MatInverse(matrix): world -> object (fj_object_instance.cc:222-225)
@@ -100,7 +100,7 @@ struct DFrame {
   const uint32_t *jitter_tab;     // first 2*max_ns draws of a default-seeded XorShift (fj_random.cc:10-43)
 };
 struct DTile { int32_t id, xmin, ymin, xmax, ymax; };
-struct DCounters { unsigned long long rays[5]; unsigned long long samples; };
+struct DCounters { unsigned long long rays[5]; unsigned long long samples; unsigned long long hits; unsigned long long levels; };
 
 struct Hit { double t, u, v; int32_t prim, inst; };
 

@@ -25,7 +25,8 @@ std::string g_last_error;
 
 struct DevBuf {
   void *p = nullptr; size_t bytes = 0;
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void *h = nullptr; size_t used = 0;     // retained pinned host copy of a scene array (fjgpu_scene_resend)
+  void release() { if (p) cudaFree(p); if (h) cudaFreeHost(h); p = nullptr; h = nullptr; bytes = 0; used = 0; }
 };
 
 struct MeshRec {
@@ -86,8 +87,15 @@ int dev_alloc(fjgpu_context *ctx, DevBuf &b, size_t bytes) {
   b.bytes = bytes;
   return 0;
 }
-int dev_upload(fjgpu_context *ctx, DevBuf &b, const void *src, size_t bytes) {
+int dev_upload(fjgpu_context *ctx, DevBuf &b, const void *src, size_t bytes, bool keep = false) {
   if (int rc = dev_alloc(ctx, b, bytes)) return rc;
+  if (keep && bytes) {       // scene arrays go through a retained pinned staging copy
+    if (b.h) { cudaFreeHost(b.h); b.h = nullptr; }
+    CK(cudaMallocHost(&b.h, bytes));
+    memcpy(b.h, src, bytes);
+    b.used = bytes;
+    src = b.h;
+  }
   if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
@@ -120,7 +128,7 @@ int commit_scene(fjgpu_context *ctx) {
   std::map<int, int> slot;
   std::vector<fj::DMesh> dm;
   for (auto &kv : ctx->meshes) { slot[kv.first] = (int)dm.size(); dm.push_back(kv.second.d); }
-  if (int rc = dev_upload(ctx, ctx->d_meshes, dm.data(), dm.size() * sizeof(fj::DMesh))) return rc;
+  if (int rc = dev_upload(ctx, ctx->d_meshes, dm.data(), dm.size() * sizeof(fj::DMesh), true)) return rc;
 
   const int ninst = (int)ctx->inst.size();
   std::vector<fj::DInstance> di(ninst);
@@ -158,7 +166,7 @@ int commit_scene(fjgpu_context *ctx) {
       for (int a = 0; a < 3; a++) { ibox[i].lo[a] = 3e38f; ibox[i].hi[a] = -3e38f; }
     }
   }
-  if (int rc = dev_upload(ctx, ctx->d_inst, di.data(), di.size() * sizeof(fj::DInstance))) return rc;
+  if (int rc = dev_upload(ctx, ctx->d_inst, di.data(), di.size() * sizeof(fj::DInstance), true)) return rc;
 
   const int ngroups = (int)ctx->group_off.size() - 1;
   for (auto &b : ctx->d_group_nodes) b.release();
@@ -180,14 +188,14 @@ int commit_scene(fjgpu_context *ctx) {
     fjb::build_bvh(boxes.data(), (int32_t)boxes.size(), 1, 1.f, 0, &br);
     std::vector<int32_t> order(std::max<size_t>(br.order.size(), 1), 0);
     for (size_t k = 0; k < br.order.size(); k++) order[k] = ids[br.order[k]];
-    if (int rc = dev_upload(ctx, ctx->d_group_nodes[g], br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64))) return rc;
-    if (int rc = dev_upload(ctx, ctx->d_group_order[g], order.data(), order.size() * sizeof(int32_t))) return rc;
+    if (int rc = dev_upload(ctx, ctx->d_group_nodes[g], br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64), true)) return rc;
+    if (int rc = dev_upload(ctx, ctx->d_group_order[g], order.data(), order.size() * sizeof(int32_t), true)) return rc;
     dg[g].nodes = (const float4 *)ctx->d_group_nodes[g].p;
     dg[g].order = (const int32_t *)ctx->d_group_order[g].p;
     dg[g].ninst = (int32_t)ids.size(); dg[g].pad = 0;
     ctx->tlas_nodes += br.nodes.size();
   }
-  if (int rc = dev_upload(ctx, ctx->d_groups, dg.data(), dg.size() * sizeof(fj::DGroup))) return rc;
+  if (int rc = dev_upload(ctx, ctx->d_groups, dg.data(), dg.size() * sizeof(fj::DGroup), true)) return rc;
 
   std::vector<fj::DShader> ds(ctx->shaders.size());
   for (size_t i = 0; i < ds.size(); i++) {
@@ -197,7 +205,7 @@ int commit_scene(fjgpu_context *ctx) {
     memcpy(d.emission, s.emission, 12); memcpy(d.transmit, s.transmit, 12);
     d.ior = s.ior; d.opacity = s.opacity;
   }
-  if (int rc = dev_upload(ctx, ctx->d_shaders, ds.data(), ds.size() * sizeof(fj::DShader))) return rc;
+  if (int rc = dev_upload(ctx, ctx->d_shaders, ds.data(), ds.size() * sizeof(fj::DShader), true)) return rc;
 
   for (auto &b : ctx->d_dome) b.release();
   ctx->d_dome.assign(2 * ctx->lights.size(), DevBuf());
@@ -215,7 +223,7 @@ int commit_scene(fjgpu_context *ctx) {
       d.dome_dirs = (const double *)ctx->d_dome[2 * i].p; d.dome_colors = (const float *)ctx->d_dome[2 * i + 1].p;
     }
   }
-  if (int rc = dev_upload(ctx, ctx->d_lights, dl.data(), dl.size() * sizeof(fj::DLight))) return rc;
+  if (int rc = dev_upload(ctx, ctx->d_lights, dl.data(), dl.size() * sizeof(fj::DLight), true)) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
 
   fj::DScene &sc = ctx->sc;
@@ -397,6 +405,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
     float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[3]);
     stats->rays_camera = hc.rays[0]; stats->rays_shadow = hc.rays[1]; stats->rays_diffuse = hc.rays[2];
     stats->rays_reflect = hc.rays[3]; stats->rays_refract = hc.rays[4]; stats->camera_samples = hc.samples;
+    stats->rays_hit = hc.hits; stats->hit_mesh_levels = hc.levels;
     stats->kernel_launches = launches; stats->ms_trace = ms_trace; stats->ms_resolve = ms_resolve; stats->ms_total = tot;
   }
   return 0;
@@ -481,7 +490,7 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
   fjb::build_bvh(boxes.data(), nfaces, env_int("FJGPU_MAX_LEAF", 4), (float)env_int("FJGPU_LEAF_COST_X10", 15) / 10.f, 0, &br);
   m.nnodes = (int32_t)br.nodes.size(); m.max_depth = br.max_depth;
   if (br.max_depth + 8 > FJ_STACK) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
-  if (int rc = dev_upload(ctx, m.nodes, br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64))) return rc;
+  if (int rc = dev_upload(ctx, m.nodes, br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64), true)) return rc;
   memset(&m.d, 0, sizeof m.d);
   m.d.nodes = (const float4 *)m.nodes.p;
   const size_t nt = br.order.size();
@@ -494,7 +503,7 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
       }
       memcpy(&tri[12 * k + 3], &f, 4);
     }
-    if (int rc = dev_upload(ctx, m.tri, tri.data(), tri.size() * 4)) return rc;
+    if (int rc = dev_upload(ctx, m.tri, tri.data(), tri.size() * 4, true)) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     m.d.tri32 = (const float4 *)m.tri.p;
   } else {
@@ -504,15 +513,16 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
       for (int v = 0; v < 3; v++) for (int a = 0; a < 3; a++) tri[10 * k + 3 * v + a] = P[3 * (size_t)idx3[3 * f + v] + a];
       const long long fl = f; memcpy(&tri[10 * k + 9], &fl, 8);
     }
-    if (int rc = dev_upload(ctx, m.tri, tri.data(), tri.size() * 8)) return rc;
+    if (int rc = dev_upload(ctx, m.tri, tri.data(), tri.size() * 8, true)) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     m.d.tri64 = (const double *)m.tri.p;
   }
-  if (N) { if (int rc = dev_upload(ctx, m.N, N, (size_t)nverts * 24)) return rc; m.d.N = (const double *)m.N.p; }
-  if (int rc = dev_upload(ctx, m.idx, idx3, (size_t)nfaces * 12)) return rc;
+  if (N) { if (int rc = dev_upload(ctx, m.N, N, (size_t)nverts * 24, true)) return rc; m.d.N = (const double *)m.N.p; }
+  if (int rc = dev_upload(ctx, m.idx, idx3, (size_t)nfaces * 12, true)) return rc;
   m.d.idx = (const int32_t *)m.idx.p;
-  if (face_group_id) { if (int rc = dev_upload(ctx, m.group, face_group_id, (size_t)nfaces * 4)) return rc; m.d.group = (const int32_t *)m.group.p; }
+  if (face_group_id) { if (int rc = dev_upload(ctx, m.group, face_group_id, (size_t)nfaces * 4, true)) return rc; m.d.group = (const int32_t *)m.group.p; }
   m.d.top_count = br.top_count;
+  { int l = 0; while ((1ll << l) < (long long)std::max(nfaces, 1)) l++; m.d.log2_tris = l; }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->dirty = true;
   ctx->build_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -663,6 +673,25 @@ int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info) {
   for (auto &b : ctx->d_group_nodes) info->hbm_bytes += b.bytes;
   info->tlas_nodes = ctx->tlas_nodes; info->instances = ctx->inst.size();
   info->build_seconds = ctx->build_seconds;
+  return FJGPU_OK;
+}
+
+int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent) {
+  if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = commit_scene(ctx)) return rc;
+  std::vector<DevBuf *> all = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights};
+  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.tri, &m.N, &m.idx, &m.group}) all.push_back(b); }
+  for (auto &b : ctx->d_group_nodes) all.push_back(&b);
+  for (auto &b : ctx->d_group_order) all.push_back(&b);
+  uint64_t total = 0;
+  for (DevBuf *b : all) {
+    if (!b->h || !b->used) continue;
+    CK(cudaMemcpyAsync(b->p, b->h, b->used, cudaMemcpyHostToDevice, ctx->stream));
+    total += b->used;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bytes_sent) *bytes_sent = total;
   return FJGPU_OK;
 }
 

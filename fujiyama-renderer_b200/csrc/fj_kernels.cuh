@@ -85,12 +85,13 @@ template <typename T>
 struct PathTracer {
   const DScene &sc; const DFrame &fr; PathKey key;
   unsigned long long rays[5];
+  unsigned int hits, levels;
   C3 acc;
   Pending stack[FJ_PENDING];
   int sp;
 
   __device__ PathTracer(const DScene &s, const DFrame &f, PathKey k) : sc(s), fr(f), key(k), sp(0) {
-    rays[0] = rays[1] = rays[2] = rays[3] = rays[4] = 0; acc = c3(0, 0, 0);
+    rays[0] = rays[1] = rays[2] = rays[3] = rays[4] = 0; hits = levels = 0; acc = c3(0, 0, 0);
   }
   __device__ __forceinline__ double rnd(unsigned long long node, uint32_t dim) const { return ctr_rand(key.seed, key.tile, key.sample, node, dim); }
 
@@ -111,6 +112,7 @@ struct PathTracer {
       Hit h;
       rays[RAY_SHADOW]++;
       if (trace_closest<T>(sc, sc.inst[shaded_object].shadow_target, sr, &h)) {
+        hits++; levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
         const float ac = fadd(1.f, -occluder_opacity(sc, h));
         lc.r = fmul(lc.r, ac); lc.g = fmul(lc.g, ac); lc.b = fmul(lc.b, ac);
       }
@@ -181,6 +183,7 @@ struct PathTracer {
       rays[cur.type]++;
       Hit h;
       if (!trace_closest<T>(sc, cur.target, ray, &h)) continue;
+      hits++; levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
       C3 thr = cur.thr;
       if (cur.filter) {    // pathtracing_shader.cc:247-251: C *= pow(transmit, t_hit) of the refracted child
         thr.r = fmul(thr.r, (float)pow((double)cur.transmit.r, h.t));
@@ -281,7 +284,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) k_render_samples(const RenderArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned long long total = (unsigned long long)a.ntiles * a.wstride;
-  unsigned long long cnt[5] = {0, 0, 0, 0, 0}; unsigned long long nsamp = 0;
+  unsigned long long cnt[7] = {0, 0, 0, 0, 0, 0, 0}; unsigned long long nsamp = 0;
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(a.work, 32ull);
@@ -301,14 +304,15 @@ __global__ void __launch_bounds__(128) k_render_samples(const RenderArgs a) {
       PathTracer<T> pt(a.sc, a.fr, key);
       out = pt.run(ray);
       for (int k = 0; k < 5; k++) cnt[k] += pt.rays[k];
+      cnt[5] += pt.hits; cnt[6] += pt.levels;
       nsamp++;
     }
     a.samples[(size_t)ti * a.wstride + (blk << 5) + lane] = out;
   }
-  for (int k = 0; k < 5; k++) {
+  for (int k = 0; k < 7; k++) {
     unsigned long long v = cnt[k];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0 && v) atomicAdd(&a.counters->rays[k], v);
+    if (lane == 0 && v) atomicAdd(k < 5 ? &a.counters->rays[k] : (k == 5 ? &a.counters->hits : &a.counters->levels), v);
   }
   for (int o = 16; o > 0; o >>= 1) nsamp += __shfl_down_sync(0xffffffffu, nsamp, o);
   if (lane == 0 && nsamp) atomicAdd(&a.counters->samples, nsamp);

@@ -168,6 +168,9 @@ typedef struct fjgpu_tile {         /* Tile of src/fj_tiler.h; [xmin,xmax) x [ym
 typedef struct fjgpu_stats {
   uint64_t rays_camera, rays_shadow, rays_diffuse, rays_reflect, rays_refract;
   uint64_t camera_samples;          /* incl. filter-margin samples */
+  uint64_t rays_hit;                /* rays (any type) that found a surface */
+  uint64_t hit_mesh_levels;         /* sum over those rays of ceil(log2(triangles of the mesh hit)): the root-to-leaf
+                                       path lengths of the algorithmic-bytes model */
   uint64_t kernel_launches;         /* launches of this library's kernels in the call */
   float    ms_trace;                /* device time of the sample/trace/shade kernels (CUDA events) */
   float    ms_resolve;              /* device time of the pixel-filter kernels */
@@ -224,6 +227,13 @@ typedef struct fjgpu_scene_info {
   double   build_seconds;   /* host time spent in BVH construction since context creation */
 } fjgpu_scene_info;
 int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info);
+
+/* Re-sends the retained pinned host copy of every scene array (BVH nodes, triangle packets, normals, indices,
+ * instance / group / shader / light tables) host -> device and reports the bytes copied: what a host that
+ * edited or re-loaded the scene pays before a frame (the reference re-walks its host scene in prepare_render,
+ * src/fj_scene_interface.cc:1204-1222).  bench.py's end-to-end leg calls it every step so that each step carries
+ * its inputs over PCIe. */
+int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,166 @@
+"""libfjscene.so — the host mirror of fj_scene_interface: (CPU) its matrices and normals are bit-identical to
+the reference's (golden vectors dumped from the reference's libscene.so), the `.scn` grammar and error
+behaviour follow tools/scene_parser; (GPU) a `.scn` file written for the reference's bin/scene renders through
+it to the same frame as the reference's own .fb."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_scenes
+import scenekit as sk
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def fuji():
+    import __graft_entry__ as g
+    g.build_fjgpu()
+    g.build_host()
+    sk.pkg()
+    from fujiyama_renderer_b200 import fujiyama
+    fujiyama.load_fjscene()
+    return fujiyama
+
+
+@pytest.fixture(scope="module")
+def vec():
+    with open(os.path.join(GOLD, "ref_vectors.json")) as f:
+        return json.load(f)
+
+
+def test_transform_bit_exact_vs_reference(fuji, vec):
+    lib = fuji.load_fjscene()
+    for c in vec["xfm"]:
+        fwd, inv = np.zeros(16), np.zeros(16)
+        T, R, S = (np.asarray(c[k], np.float64) for k in "TRS")
+        lib.fjscene_make_transform(c["torder"], c["rorder"], sk.dptr(T), sk.dptr(R), sk.dptr(S), sk.dptr(fwd), sk.dptr(inv))
+        assert fwd.tolist() == c["fwd"] and inv.tolist() == c["inv"]
+
+
+def test_compute_normals_bit_exact_vs_reference(fuji, vec):
+    c = vec["normals"]
+    with fuji.Session() as s:
+        s.run("NewMesh m\n")
+        P = np.asarray(c["P"], np.float64)
+        s.set_mesh("m", P, np.asarray(c["idx"], np.int32))
+        N = np.zeros_like(P)
+        assert s.lib.fjscene_mesh_normals(s.id("m"), sk.dptr(N), len(P)) == 0
+    assert N.tolist() == c["N"]
+
+
+def test_ids_and_errors_follow_the_reference(fuji):
+    with fuji.Session() as s:
+        s.run("NewMesh mesh1\nNewObjectInstance obj1 mesh1\nNewRenderer ren1\nNewCamera cam1 PerspectiveCamera\n")
+        # ID = type * 10000000 + index with the reference's type numbering (src/fj_scene_interface.cc:42-62)
+        assert s.id("mesh1") == 16 * 10000000 and s.id("obj1") == 1 * 10000000 and s.id("ren1") == 8 * 10000000
+        assert s.id("cam1") == 10 * 10000000
+        for bad, msg in [("Frobnicate x", "unknown command"), ("NewMesh", "too few arguments"),
+                         ("NewMesh a b", "too many arguments"), ("NewMesh mesh1", "entry name already exists"),
+                         ("RenderScene nope", "entry name not found"), ("SetProperty1 ren1 cast_shadow abc", "bad number arguments"),
+                         ("NewLight l1 LaserLight", "bad enum arguments"),
+                         ("OpenPlugin p /x/GlassShader.so", "plugin not found"),
+                         ("NewVolume v", "new entry failed"),
+                         ("SetProperty1 ren1 no_such_property 1", "command failed")]:
+            with pytest.raises(fuji.SceneError, match=msg):
+                s.run(bad + "\n")
+        s.run("# a comment\n\nSetProperty3 obj1 rotate_order ORDER_XYZ 0 0\nSetProperty2 ren1 resolution 64 48\n")
+        # rendering without a camera / framebuffer fails like the reference's SI_FAIL paths
+        with pytest.raises(fuji.SceneError):
+            s.run("RenderScene ren1\n")
+
+
+def test_ply_reader_matches_python_reader(fuji, tmp_path):
+    from fujiyama_renderer_b200 import synth
+    P, idx = synth.blob(9)
+    path = str(tmp_path / "b.ply")
+    synth.write_ply(path, P, idx)
+    ascii_path = str(tmp_path / "quad.ply")
+    with open(ascii_path, "w") as f:      # ascii polygon (fan triangulation, ply2mesh.cc:129-136) with an extra property
+        f.write("ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\nproperty float q\n"
+                "element face 1\nproperty list uchar int vertex_indices\nend_header\n"
+                "0 0 0 9\n1 0 0 9\n1 1 0 9\n0 1 0 9\n4 0 1 2 3\n")
+    with fuji.Session() as s:
+        s.run("OpenPlugin ply /any/where/StanfordPlyProcedure\nNewMesh m\nNewProcedure p ply\nAssignMesh p mesh m\n"
+              "SetStringProperty p filepath %s\nSetStringProperty p io_mode r\nRunProcedure p\n" % path)
+        N = np.zeros((len(P), 3))
+        assert s.lib.fjscene_mesh_normals(s.id("m"), sk.dptr(N), len(P)) == 0
+        ref = np.zeros_like(N)
+        P64 = np.ascontiguousarray(P.astype(np.float64))
+        sk.oracle().fjo_compute_normals(sk.dptr(P64), len(P64), sk.iptr(np.ascontiguousarray(idx.reshape(-1))), len(idx), sk.dptr(ref))
+        assert np.array_equal(N, ref)
+        s.run("NewMesh q\nNewProcedure p2 ply\nAssignMesh p2 mesh q\nSetStringProperty p2 filepath %s\nRunProcedure p2\n" % ascii_path)
+        Nq = np.zeros((4, 3))
+        assert s.lib.fjscene_mesh_normals(s.id("q"), sk.dptr(Nq), 4) == 0
+        assert np.allclose(Nq, [[0, 0, 1]] * 4)
+        with pytest.raises(fuji.SceneError):
+            s.run("SetStringProperty p2 filepath /no/such/file.ply\nRunProcedure p2\n")
+
+
+def test_python_shim_emits_reference_grammar(fuji):
+    si = fuji.SceneInterface(argv=["-R", "64", "48"])
+    si.OpenPlugin("PlasticShader", "${FJ}/PlasticShader")
+    si.NewMesh("mesh1")
+    si.SetProperty3("obj1", "rotate", 0, 10, 0)
+    si.AssignShader("obj1", "DEFAULT_SHADING_GROUP", "sh1")
+    si.RenderScene("ren1")
+    assert si.commands == ["OpenPlugin PlasticShader ${FJ}/PlasticShader.so", "NewMesh mesh1",
+                           "SetProperty3 obj1 rotate 0 10 0", "AssignShader obj1 DEFAULT_SHADING_GROUP sh1",
+                           "SetProperty2 ren1 resolution 64 48", "RenderScene ren1"]
+    with pytest.raises(TypeError):
+        si.NewMesh("a", "b")
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cube_c1", "plastic", "multi", "dome_light"])
+def test_scn_file_renders_like_the_reference(fuji, tmp_path, name):
+    """The exact command text the reference's bin/scene was given for the golden .fb, fed to libfjscene."""
+    from fujiyama_renderer_b200 import fbio
+    desc = golden_scenes.SCENES[name]()
+    out = str(tmp_path / "out.fb")
+    scn = desc.to_scn(str(tmp_path), out, threads=1, plugin_dir="/opt/fujiyama/lib")
+    with fuji.Session() as s:
+        s.run(scn)
+        img = s.framebuffer("fb1")
+        stats, info, _ = s.stats()
+    ref = np.load(os.path.join(GOLD, "ref_images.npz"))[name]
+    assert img.shape == ref.shape
+    d = img.astype(np.float64) - ref
+    assert np.sqrt((d * d).reshape(-1, 4).mean(0)).max() < 1e-4
+    assert stats.rays_camera == stats.camera_samples > 0
+    # the .fb it saved parses back to the same pixels at 6 significant digits
+    fb = fbio.read_fb(out)
+    assert np.allclose(fb, img, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_scn_pathtracing_matches_oracle_and_groups(fuji, tmp_path):
+    desc = golden_scenes.SCENES["pt_branching"]()
+    scn = desc.to_scn(str(tmp_path), None, plugin_dir="/x")
+    with fuji.Session() as s:
+        s.run(scn)
+        img = s.framebuffer("fb1")
+    ref, _ = sk.oracle_render(desc, rng_mode=0, threads=8)
+    d = img.astype(np.float64) - ref
+    assert np.sqrt((d * d).mean()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_tile_sharding_ranks_partition_the_frame(fuji, tmp_path):
+    desc = golden_scenes.SCENES["plastic"]()
+    scn = desc.to_scn(str(tmp_path), None, plugin_dir="/x")
+    with fuji.Session() as s:
+        s.run(scn)
+        full = s.framebuffer("fb1")
+    acc = np.zeros_like(full)
+    for rank in range(3):
+        with fuji.Session(rank=rank, world_size=3) as s:
+            s.run(scn)
+            part = s.framebuffer("fb1")
+        assert not (acc.astype(bool) & part.astype(bool)).any()
+        acc += part
+    assert np.array_equal(acc, full)
