@@ -34,6 +34,8 @@ WORKLOADS = {
                    "S-blob(707)=999698 tris + emissive shell, pathtracing_shader depth 3, 1920x1080, 8x8=64spp, tile 32, filter 2"),
     "config2": ("plastic_blob", dict(n=187, res=(1280, 720), rate=4),
                 "S-blob(187)=69938 tris, plastic_shader + 1 point light, 1280x720, 4x4=16spp"),
+    "profile": ("pathtracing_blob", dict(n=707, res=(480, 270), rate=8, depth=3),
+                "north-star scene at 480x270 (1/16 of the frame) for ncu --set full captures"),
     "small": ("pathtracing_blob", dict(n=64, res=(320, 180), rate=4, depth=3),
               "S-blob(64)=8192 tris + shell, pathtracing_shader, 320x180, 16spp (plumbing check)"),
 }
@@ -275,8 +277,8 @@ def own_arm(args, builder, kw, desc):
         t0 = time.perf_counter()
         ev0.record()
         tot = abi.Stats()
-        ms_trace = ms_resolve = 0.0
-        launches = 0
+        ms_trace = ms_resolve = ms_shade = 0.0
+        launches = trace_launches = 0
         for _ in range(args.steps):
             st, info, _ = step()
             flush.zero_()                   # L2 flush between timed iterations (256 MiB > 126 MB L2)
@@ -285,7 +287,9 @@ def own_arm(args, builder, kw, desc):
                     setattr(tot, f, getattr(tot, f) + getattr(st, f))
             ms_trace += st.ms_trace
             ms_resolve += st.ms_resolve
+            ms_shade += st.ms_shade
             launches += st.kernel_launches
+            trace_launches += st.trace_launches
         ev1.record()
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -303,8 +307,9 @@ def own_arm(args, builder, kw, desc):
         ms_per_step = dev_ms / args.steps
         value = total_rays / (dev_ms * 1e-3) / 1e6
 
-        # roofline of the dominant kernel (k_render_samples) on this rank: CUDA events on its launching stream
-        n_trace_launches = max(1, (launches // args.steps - (1 if world == 1 else 0)) // 2) * args.steps
+        # roofline of the dominant kernel (k_extend, the closest-hit kernel) on this rank: CUDA events around every one of
+        # its launches on the launching stream (fjgpu_stats.ms_trace / trace_launches)
+        n_trace_launches = max(1, trace_launches)
         algo = algorithmic_bytes(tot, int(info.instances))
         peaks = {}
         try:
@@ -321,7 +326,7 @@ def own_arm(args, builder, kw, desc):
                 traffic = json.load(open(tpath)).get(args.workload)
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_render_samples", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo / n_trace_launches, "launches": n_trace_launches,
                     "avg_launch_ms": ms_trace / n_trace_launches, "bytes_per_ray": algo / max(tot.rays, 1),
@@ -385,7 +390,8 @@ def own_arm(args, builder, kw, desc):
                           "blas_nodes": int(info.blas_nodes), "blas_max_depth": int(info.blas_max_depth)},
                "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": total_launches, "clocks": clk,
                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-               "kernel_ms_per_step": {"k_render_samples": ms_trace / args.steps, "k_resolve_tiles": ms_resolve / args.steps}}
+               "kernel_ms_per_step": {"k_extend": ms_trace / args.steps, "k_generate+k_shade": ms_shade / args.steps,
+                                      "k_resolve_tiles": ms_resolve / args.steps}}
         print(json.dumps(out))
     s.close()
     if world > 1:

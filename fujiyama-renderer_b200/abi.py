@@ -15,7 +15,7 @@ LIBFJSCENE = os.path.join(HERE, "host", "libfjscene.so")
 FJGPU_MAX_SHADING_GROUPS = 8
 SHADER_NONE, SHADER_CONSTANT, SHADER_PLASTIC, SHADER_PATHTRACING = 0, 1, 2, 3
 LIGHT_POINT, LIGHT_GRID, LIGHT_SPHERE, LIGHT_DOME = 0, 1, 2, 3
-FLAG_FP64_BOXES = 1
+FLAG_FP64_BOXES, FLAG_MEGAKERNEL = 1, 2
 
 
 class Instance(C.Structure):
@@ -67,9 +67,9 @@ class Stats(C.Structure):
                 ("rays_diffuse", C.c_uint64), ("rays_reflect", C.c_uint64),
                 ("rays_refract", C.c_uint64), ("camera_samples", C.c_uint64),
                 ("rays_hit", C.c_uint64), ("hit_mesh_levels", C.c_uint64),
-                ("kernel_launches", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("trace_launches", C.c_uint64),
                 ("ms_trace", C.c_float), ("ms_resolve", C.c_float),
-                ("ms_total", C.c_float), ("_pad", C.c_float)]
+                ("ms_total", C.c_float), ("ms_shade", C.c_float)]
 
     @property
     def rays(self):

@@ -17,7 +17,7 @@
 
 #define FJ_MAX_SHADING_GROUPS 8
 #define FJ_STACK 64              // traversal stack entries (BLAS depth + TLAS depth + 1 sentinel)
-#define FJ_PENDING 32            // pending secondary rays per path (DFS of the reflect/refract/diffuse tree)
+#define FJ_PENDING 32            // megakernel: pending secondary rays per path (DFS of the reflect/refract/diffuse tree)
 #define FJ_REAL_MAX DBL_MAX
 
 namespace fj {
@@ -65,6 +65,8 @@ struct DMesh {
   const int32_t *group;     // shading group per face (may be null -> 0)
   int32_t top_count;        // leading BFS-ordered nodes (reserved for shared-memory staging)
   int32_t log2_tris;        // ceil(log2(triangle count)): root-to-leaf path length of the algorithmic-bytes model
+  float bmag;               // max |coordinate| of the mesh bounds: scales the FP32 slab-test error bound (extend kernel)
+  float pad1;
 };
 struct DInstance {
   double inv[12];           // rows 0..2 of MatInverse(matrix): world -> object (fj_object_instance.cc:222-225)
@@ -73,7 +75,7 @@ struct DInstance {
   int32_t shader_of_group[FJ_MAX_SHADING_GROUPS];
   int32_t reflect_target, refract_target, shadow_target;
 };
-struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; int32_t pad; };   // TLAS leaf (first,count) -> order[first..] = instance indices
+struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; };   // TLAS leaf (first,count) -> order[first..] = instance indices
 struct DShader {
   int32_t kind, do_reflect, do_color_filter, pad;
   float diffuse[3], reflect[3], refract[3], emission[3], transmit[3];
@@ -323,18 +325,35 @@ __device__ __forceinline__ D3 sl_refract(const D3 &I, const D3 &N, double ior) {
 
 enum { RAY_CAMERA = 0, RAY_SHADOW = 1, RAY_DIFFUSE = 2, RAY_REFLECT = 3, RAY_REFRACT = 4 };   // enum RayContext, fj_shading.h:18-24
 
-// One entry of the per-path DFS stack: a secondary ray still to be traced, with the throughput that
-// multiplies whatever it returns (the reference multiplies after the recursive SlTrace returns;
-// every use is linear in the child's radiance).
-struct Pending {
-  D3 o, d; double tmin;
-  C3 thr;
-  C3 transmit;                    // refraction colour filter pow(transmit, t_hit) applied at the child's hit
+// One ray of the wavefront: an entry of the ray queues in HBM (and of the megakernel's per-path DFS stack).
+// `thr` is the throughput that multiplies whatever the ray returns — the reference multiplies after the recursive
+// SlTrace returns, and every use is linear in the child's radiance.  112 B = 7 x 16 B.
+struct RayRec {
+  double o[3], d[3];
+  double tmin, tmax;
+  float thr[3];
+  uint32_t slot;                  // sample slot in the batch's accumulator buffer
   unsigned long long node;        // path-tree code keying the counter RNG
   int32_t target;                 // object group traced
   uint8_t type, dd, rd, fd;       // ray context and the three depth counters of TraceContext (fj_shading.h:26-47)
-  uint8_t filter; uint8_t pad[3];
+  int32_t filter_shader;          // >= 0: refracted child whose radiance is scaled by pow(transmit, t_hit) of that shader
+  int32_t pad, pad2, pad3;
 };
+static_assert(sizeof(RayRec) == 112, "ray record must be 112 bytes");
+struct HitRec { double t, u, v; int32_t prim, inst; };     // 32 B, inst < 0 = miss
+static_assert(sizeof(HitRec) == 32, "hit record must be 32 bytes");
+// Per-sample radiance accumulator: 32.32 fixed point so that the sum is independent of the order in which the rays of
+// one sample are shaded (deterministic frames for any scheduling); alpha is written once by the camera ray.
+struct Accum { long long r, g, b; float a; uint32_t pad; };
+static_assert(sizeof(Accum) == 32, "accumulator must be 32 bytes");
+#define FJ_FIX_SCALE 4294967296.0
+#define FJ_FIX_INV 2.3283064365386963e-10
+__device__ __forceinline__ long long to_fix(float v) {
+  double d = dmul((double)v, FJ_FIX_SCALE);
+  d = fmin(fmax(d, -4.0e18), 4.0e18);
+  return __double2ll_rn(d);
+}
+__device__ __forceinline__ float from_fix(long long v) { return (float)dmul((double)v, FJ_FIX_INV); }
 
 // Surface at a hit: world-space P and N exactly as ObjectInstance::RayIntersect returns them
 // (fj_object_instance.cc:234-241) from Mesh::ray_intersect (fj_mesh.cc:277-305).

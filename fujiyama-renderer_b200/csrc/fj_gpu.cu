@@ -65,7 +65,8 @@ struct fjgpu_context {
   double build_seconds = 0;
 
   // frame resources
-  DevBuf d_samples, d_tiles, d_blocks, d_jitter, d_counters, d_frame;
+  DevBuf d_samples, d_tiles, d_blocks, d_jitter, d_counters, d_frame, d_queue[2], d_hits, d_ctl;
+  std::vector<cudaEvent_t> evpool;
   size_t jitter_count = 0;
   float *h_blocks = nullptr; size_t h_blocks_bytes = 0;
 };
@@ -192,7 +193,8 @@ int commit_scene(fjgpu_context *ctx) {
     if (int rc = dev_upload(ctx, ctx->d_group_order[g], order.data(), order.size() * sizeof(int32_t), true)) return rc;
     dg[g].nodes = (const float4 *)ctx->d_group_nodes[g].p;
     dg[g].order = (const int32_t *)ctx->d_group_order[g].p;
-    dg[g].ninst = (int32_t)ids.size(); dg[g].pad = 0;
+    dg[g].ninst = (int32_t)ids.size();
+    { double b = 0; for (int a = 0; a < 3 && !boxes.empty(); a++) b = std::max(b, std::max(std::fabs((double)br.bounds.lo[a]), std::fabs((double)br.bounds.hi[a]))); dg[g].bmag = fjb::round_up(b); }
     ctx->tlas_nodes += br.nodes.size();
   }
   if (int rc = dev_upload(ctx, ctx->d_groups, dg.data(), dg.size() * sizeof(fj::DGroup), true)) return rc;
@@ -241,7 +243,36 @@ struct FramePlan {
   fj::DFrame fr; fj::DCamera cam;
   uint32_t wstride = 0; int bw = 0, bh = 0;
   int tiles_per_batch = 0;
+  int waves = 1; double peak = 1;     // wavefront: number of extend/shade rounds, worst-case rays per camera sample in one round
 };
+
+// Worst-case width of the ray tree per camera sample (rays alive in one wavefront round) and the number of rounds,
+// from the lobes the scene's shaders can spawn and the per-type bounce limits (has_reached_bounce_limit,
+// src/fj_shading.cc:467-499).
+void frontier(const fjgpu_context *ctx, const fjgpu_render_params *p, int *waves, double *peak) {
+  bool D = false, R = false, F = false; int b = 0;
+  for (const fjgpu_shader &s : ctx->shaders) {
+    int n = 0;
+    if (s.kind == FJGPU_SHADER_PLASTIC) { if (s.do_reflect) { R = true; n = 1; } }
+    else if (s.kind == FJGPU_SHADER_PATHTRACING) {
+      if (s.diffuse[0] > 0 || s.diffuse[1] > 0 || s.diffuse[2] > 0) { D = true; n++; }
+      if (s.reflect[0] > 0 || s.reflect[1] > 0 || s.reflect[2] > 0) { R = true; n++; }
+      if (s.refract[0] > 0 || s.refract[1] > 0 || s.refract[2] > 0) { F = true; n++; }
+    }
+    b = std::max(b, n);
+  }
+  const int md = D ? p->max_diffuse_depth : 0, mr = R ? p->max_reflect_depth : 0, mf = F ? p->max_refract_depth : 0;
+  *waves = 1 + md + mr + mf;
+  *peak = 1;
+  if (b <= 1) return;
+  std::vector<double> fact(md + mr + mf + 1, 1.);
+  for (size_t i = 1; i < fact.size(); i++) fact[i] = fact[i - 1] * (double)i;
+  for (int w = 1; w <= md + mr + mf; w++) {
+    double width = 0;
+    for (int nd = 0; nd <= md; nd++) for (int nr = 0; nr <= mr; nr++) { const int nf = w - nd - nr; if (nf < 0 || nf > mf) continue; width += fact[w] / (fact[nd] * fact[nr] * fact[nf]); }
+    *peak = std::max(*peak, std::min(width, std::pow((double)b, w)));
+  }
+}
 
 int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_tile *tiles, int ntiles, FramePlan *pl) {
   if (!p || (!tiles && ntiles > 0) || ntiles < 0) return fail(ctx, FJGPU_ERR_INVALID, "null params/tiles");
@@ -300,18 +331,31 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
   pl->cam.uvy = 2 * std::tan((ctx->cam.fov / 2.) * PI / 180.);
   pl->cam.uvx = pl->cam.uvy * aspect;
   rows12(ctx->cam.fwd, pl->cam.fwd); pl->cam.znear = ctx->cam.znear; pl->cam.zfar = ctx->cam.zfar;
-  // batch so the sample buffer stays bounded (default 1 GiB)
-  const size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 1024) << 20;
-  long per = (long)(cap / ((size_t)pl->wstride * sizeof(float4)));
+  // batch so the per-batch buffers (accumulators + two ray queues + hit records) stay bounded
+  frontier(ctx, p, &pl->waves, &pl->peak);
+  const size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 4096) << 20;
+  const size_t per_slot = sizeof(fj::Accum) + (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec));
+  long per = (long)(cap / ((size_t)pl->wstride * per_slot));
   pl->tiles_per_batch = (int)std::max(1l, std::min<long>(per, std::max(ntiles, 1)));
   return 0;
 }
 
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
-template <typename T>
-void launch_samples(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
-  fj::k_render_samples<T><<<blocks, 128, 0, ctx->stream>>>(a);
+void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
+  a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 8)));
+  a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 8)));
+  const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 4);
+  const int g = grid / 4 * minb;
+  if (minb >= 8) fj::k_extend<8><<<g, 128, 0, ctx->stream>>>(a);
+  else if (minb >= 6) fj::k_extend<6><<<g, 128, 0, ctx->stream>>>(a);
+  else if (minb == 5) fj::k_extend<5><<<g, 128, 0, ctx->stream>>>(a);
+  else fj::k_extend<4><<<grid, 128, 0, ctx->stream>>>(a);
+}
+
+cudaEvent_t pool_event(fjgpu_context *ctx, size_t *next) {
+  if (*next >= ctx->evpool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->evpool.push_back(e); }
+  return ctx->evpool[(*next)++];
 }
 
 int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_tile *tiles, int ntiles, int mode,
@@ -327,10 +371,13 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   if (stats) memset(stats, 0, sizeof *stats);
   if (ntiles == 0) return 0;
   const size_t block_floats = (size_t)pl.bw * pl.bh * 4;
+  const bool fp64_boxes = (p->flags & FJGPU_FLAG_FP64_BOXES) != 0;
+  const bool mega = fp64_boxes || (p->flags & FJGPU_FLAG_MEGAKERNEL) != 0 || env_int("FJGPU_MEGAKERNEL", 0) != 0;
 
   if (int rc = dev_upload(ctx, ctx->d_tiles, tiles, (size_t)ntiles * sizeof(fjgpu_tile))) return rc;
-  if (int rc = dev_alloc(ctx, ctx->d_samples, (size_t)pl.tiles_per_batch * pl.wstride * sizeof(float4))) return rc;
+  if (int rc = dev_alloc(ctx, ctx->d_samples, (size_t)pl.tiles_per_batch * pl.wstride * sizeof(fj::Accum))) return rc;
   if (int rc = dev_alloc(ctx, ctx->d_counters, sizeof(fj::DCounters) + 64)) return rc;
+  if (int rc = dev_alloc(ctx, ctx->d_ctl, sizeof(fj::QueueCtl))) return rc;
   float4 *blocks = nullptr;
   if (mode == OUT_DEVICE_BLOCKS) {
     blocks = (float4 *)d_out_blocks;
@@ -349,37 +396,86 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   }
   CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(fj::DCounters) + 64, ctx->stream));
 
-  const int blocks_per_sm = env_int("FJGPU_BLOCKS_PER_SM", 4);
-  const int grid = ctx->sm_count * blocks_per_sm;
+  const int grid = ctx->sm_count * env_int("FJGPU_BLOCKS_PER_SM", 4);
   uint64_t launches = 0;
-  float ms_trace = 0, ms_resolve = 0;
+  size_t evn = 0;
+  std::vector<cudaEvent_t> ev_extend, ev_shade, ev_resolve;     // (start, stop) pairs read after the final sync
+  // ray-queue capacity: optimistic when the ray tree can branch, grown on overflow up to the worst case
+  double factor = std::min(pl.peak, 2.0);
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   for (int b0 = 0; b0 < ntiles; b0 += pl.tiles_per_batch) {
     const int nb = std::min(pl.tiles_per_batch, ntiles - b0);
     fj::RenderArgs a;
+    memset(&a, 0, sizeof a);
     a.sc = ctx->sc; a.cam = pl.cam; a.fr = pl.fr;
     a.tiles = (const fj::DTile *)ctx->d_tiles.p + b0; a.ntiles = nb; a.wstride = pl.wstride;
-    a.samples = (float4 *)ctx->d_samples.p;
+    a.accum = (fj::Accum *)ctx->d_samples.p;
     a.counters = (fj::DCounters *)ctx->d_counters.p;
     a.work = (unsigned long long *)((char *)ctx->d_counters.p + sizeof(fj::DCounters));
-    CK(cudaMemsetAsync(a.work, 0, 8, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (p->flags & FJGPU_FLAG_FP64_BOXES) launch_samples<double>(ctx, a, grid);
-    else launch_samples<float>(ctx, a, grid);
-    launches++;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (mode != OUT_SAMPLES_ONLY) {
-      fj::k_resolve_tiles<<<nb, 256, 0, ctx->stream>>>(pl.fr, a.tiles, pl.wstride, a.samples, blocks + (size_t)b0 * pl.bw * pl.bh, pl.bw, pl.bh);
+    if (mega) {
+      CK(cudaMemsetAsync(a.work, 0, 8, ctx->stream));
+      cudaEvent_t e0 = pool_event(ctx, &evn), e1 = pool_event(ctx, &evn);
+      CK(cudaEventRecord(e0, ctx->stream));
+      if (fp64_boxes) fj::k_render_samples<double><<<grid, 128, 0, ctx->stream>>>(a);
+      else fj::k_render_samples<float><<<grid, 128, 0, ctx->stream>>>(a);
       launches++;
       CK(cudaGetLastError());
+      CK(cudaEventRecord(e1, ctx->stream));
+      ev_extend.push_back(e0); ev_extend.push_back(e1);
+    } else {
+      for (;;) {      // retried with a larger queue only if a branching ray tree overflowed the optimistic capacity
+        const double want = (double)nb * pl.wstride * factor;
+        if (want > 4.0e9) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray tree too wide for one tile's ray queue");
+        const size_t capacity = (size_t)want;
+        if (int rc = dev_alloc(ctx, ctx->d_queue[0], capacity * sizeof(fj::RayRec))) return rc;
+        if (int rc = dev_alloc(ctx, ctx->d_queue[1], capacity * sizeof(fj::RayRec))) return rc;
+        if (int rc = dev_alloc(ctx, ctx->d_hits, capacity * sizeof(fj::HitRec))) return rc;
+        a.queue[0] = (fj::RayRec *)ctx->d_queue[0].p; a.queue[1] = (fj::RayRec *)ctx->d_queue[1].p;
+        a.hits = (fj::HitRec *)ctx->d_hits.p; a.ctl = (fj::QueueCtl *)ctx->d_ctl.p; a.capacity = (uint32_t)capacity; a.cur = 0;
+        CK(cudaMemsetAsync(ctx->d_ctl.p, 0, sizeof(fj::QueueCtl), ctx->stream));
+        cudaEvent_t s0 = pool_event(ctx, &evn), s1 = pool_event(ctx, &evn);
+        CK(cudaEventRecord(s0, ctx->stream));
+        const unsigned long long total = (unsigned long long)nb * pl.wstride;
+        fj::k_generate<<<(unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)ctx->sm_count * 16), 256, 0, ctx->stream>>>(a);
+        launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(s1, ctx->stream));
+        ev_shade.push_back(s0); ev_shade.push_back(s1);
+        for (int w = 0; w < pl.waves; w++) {
+          // head of the current queue and the count of the next one start at zero
+          CK(cudaMemsetAsync((char *)ctx->d_ctl.p + offsetof(fj::QueueCtl, head), 0, 4, ctx->stream));
+          CK(cudaMemsetAsync((char *)ctx->d_ctl.p + offsetof(fj::QueueCtl, count) + 4 * (a.cur ^ 1), 0, 4, ctx->stream));
+          cudaEvent_t e0 = pool_event(ctx, &evn), e1 = pool_event(ctx, &evn), e2 = pool_event(ctx, &evn);
+          CK(cudaEventRecord(e0, ctx->stream));
+          launch_extend(ctx, a, grid);
+          CK(cudaGetLastError());
+          CK(cudaEventRecord(e1, ctx->stream));
+          fj::k_shade<float><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a);
+          CK(cudaGetLastError());
+          CK(cudaEventRecord(e2, ctx->stream));
+          launches += 2;
+          ev_extend.push_back(e0); ev_extend.push_back(e1); ev_shade.push_back(e1); ev_shade.push_back(e2);
+          a.cur ^= 1;
+        }
+        if (factor >= pl.peak) break;           // cannot overflow
+        fj::QueueCtl hctl;
+        CK(cudaMemcpyAsync(&hctl, ctx->d_ctl.p, sizeof hctl, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!hctl.overflow) break;
+        factor = std::min(pl.peak, factor * 4.0);
+        // the batch is rendered again from scratch: discard what the overflowed attempt counted
+        CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(fj::DCounters), ctx->stream));
+        if (b0 > 0) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray queue overflow after the first batch");
+      }
     }
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (ntiles > pl.tiles_per_batch || stats) {     // per-batch timing needs the events read before reuse
-      CK(cudaEventSynchronize(ctx->ev[3]));
-      float t1 = 0, t2 = 0;
-      cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]); cudaEventElapsedTime(&t2, ctx->ev[2], ctx->ev[3]);
-      ms_trace += t1; ms_resolve += t2;
+    if (mode != OUT_SAMPLES_ONLY) {
+      cudaEvent_t e0 = pool_event(ctx, &evn), e1 = pool_event(ctx, &evn);
+      CK(cudaEventRecord(e0, ctx->stream));
+      fj::k_resolve_tiles<<<nb, 256, 0, ctx->stream>>>(pl.fr, a.tiles, pl.wstride, a.accum, blocks + (size_t)b0 * pl.bw * pl.bh, pl.bw, pl.bh);
+      launches++;
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(e1, ctx->stream));
+      ev_resolve.push_back(e0); ev_resolve.push_back(e1);
     }
   }
   if (mode == OUT_RESIDENT) {
@@ -406,7 +502,12 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
     stats->rays_camera = hc.rays[0]; stats->rays_shadow = hc.rays[1]; stats->rays_diffuse = hc.rays[2];
     stats->rays_reflect = hc.rays[3]; stats->rays_refract = hc.rays[4]; stats->camera_samples = hc.samples;
     stats->rays_hit = hc.hits; stats->hit_mesh_levels = hc.levels;
-    stats->kernel_launches = launches; stats->ms_trace = ms_trace; stats->ms_resolve = ms_resolve; stats->ms_total = tot;
+    float ms_trace = 0, ms_shade = 0, ms_resolve = 0, t = 0;
+    for (size_t i = 0; i + 1 < ev_extend.size(); i += 2) { cudaEventElapsedTime(&t, ev_extend[i], ev_extend[i + 1]); ms_trace += t; }
+    for (size_t i = 0; i + 1 < ev_shade.size(); i += 2) { cudaEventElapsedTime(&t, ev_shade[i], ev_shade[i + 1]); ms_shade += t; }
+    for (size_t i = 0; i + 1 < ev_resolve.size(); i += 2) { cudaEventElapsedTime(&t, ev_resolve[i], ev_resolve[i + 1]); ms_resolve += t; }
+    stats->kernel_launches = launches; stats->trace_launches = ev_extend.size() / 2;
+    stats->ms_trace = ms_trace; stats->ms_shade = ms_shade; stats->ms_resolve = ms_resolve; stats->ms_total = tot;
   }
   return 0;
 }
@@ -452,7 +553,8 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &b : ctx->d_group_order) b.release();
   for (auto &b : ctx->d_dome) b.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
-                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame};
+                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl};
+  for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
   for (DevBuf *b : all) b->release();
   if (ctx->h_blocks) cudaFreeHost(ctx->h_blocks);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -523,6 +625,7 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
   if (face_group_id) { if (int rc = dev_upload(ctx, m.group, face_group_id, (size_t)nfaces * 4, true)) return rc; m.d.group = (const int32_t *)m.group.p; }
   m.d.top_count = br.top_count;
   { int l = 0; while ((1ll << l) < (long long)std::max(nfaces, 1)) l++; m.d.log2_tris = l; }
+  { double b = 0; for (int a = 0; a < 3; a++) b = std::max(b, std::max(std::fabs((double)br.bounds.lo[a]), std::fabs((double)br.bounds.hi[a]))); m.d.bmag = nfaces > 0 ? fjb::round_up(b) : 0.f; }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->dirty = true;
   ctx->build_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -618,12 +721,26 @@ int fjgpu_trace_closest(fjgpu_context *ctx, int32_t group, int32_t n, const doub
     return rc;
   }
   const int grid = (n + 127) / 128;
+  DevBuf q, hits, ctl;
   if (flags & FJGPU_FLAG_FP64_BOXES)
     fj::k_trace_closest<double><<<grid, 128, 0, ctx->stream>>>(ctx->sc, group, n, (const double *)o.p, (const double *)d.p, (const double *)t0.p, (const double *)t1.p,
                                                                (double *)rt.p, (double *)ru.p, (double *)rv.p, (int32_t *)rp.p, (int32_t *)ri.p);
-  else
+  else if (flags & FJGPU_FLAG_MEGAKERNEL)
     fj::k_trace_closest<float><<<grid, 128, 0, ctx->stream>>>(ctx->sc, group, n, (const double *)o.p, (const double *)d.p, (const double *)t0.p, (const double *)t1.p,
                                                               (double *)rt.p, (double *)ru.p, (double *)rv.p, (int32_t *)rp.p, (int32_t *)ri.p);
+  else {      // the wavefront's closest-hit kernel: rays -> queue records -> k_extend -> hit records
+    if ((rc = dev_alloc(ctx, q, N * sizeof(fj::RayRec))) || (rc = dev_alloc(ctx, hits, N * sizeof(fj::HitRec))) || (rc = dev_alloc(ctx, ctl, sizeof(fj::QueueCtl)))) {
+      DevBuf *all[] = {&o, &d, &t0, &t1, &rt, &ru, &rv, &rp, &ri, &q, &hits, &ctl}; for (DevBuf *b : all) b->release();
+      return rc;
+    }
+    fj::QueueCtl h; memset(&h, 0, sizeof h); h.count[0] = (unsigned)n;
+    cudaMemcpyAsync(ctl.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream);
+    fj::k_probe_pack<<<grid, 128, 0, ctx->stream>>>(group, n, (const double *)o.p, (const double *)d.p, (const double *)t0.p, (const double *)t1.p, (fj::RayRec *)q.p);
+    fj::RenderArgs a; memset(&a, 0, sizeof a);
+    a.sc = ctx->sc; a.queue[0] = (fj::RayRec *)q.p; a.hits = (fj::HitRec *)hits.p; a.ctl = (fj::QueueCtl *)ctl.p; a.capacity = (uint32_t)n; a.cur = 0;
+    launch_extend(ctx, a, std::min(grid, ctx->sm_count * 4));
+    fj::k_probe_unpack<<<grid, 128, 0, ctx->stream>>>(n, (const fj::HitRec *)hits.p, (double *)rt.p, (double *)ru.p, (double *)rv.p, (int32_t *)rp.p, (int32_t *)ri.p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_t, rt.p, N * 8, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_u, ru.p, N * 8, cudaMemcpyDeviceToHost, ctx->stream);
@@ -631,7 +748,7 @@ int fjgpu_trace_closest(fjgpu_context *ctx, int32_t group, int32_t n, const doub
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_prim, rp.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_inst, ri.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  DevBuf *all[] = {&o, &d, &t0, &t1, &rt, &ru, &rv, &rp, &ri}; for (DevBuf *b : all) b->release();
+  DevBuf *all[] = {&o, &d, &t0, &t1, &rt, &ru, &rv, &rp, &ri, &q, &hits, &ctl}; for (DevBuf *b : all) b->release();
   if (e != cudaSuccess) return fail(ctx, FJGPU_ERR_CUDA, std::string("trace_closest: ") + cudaGetErrorString(e));
   return FJGPU_OK;
 }
@@ -650,7 +767,7 @@ int fjgpu_render_tile_samples(fjgpu_context *ctx, const fjgpu_render_params *par
   DevBuf duv, drgba;
   if ((rc = dev_alloc(ctx, duv, (size_t)n * 16)) || (rc = dev_alloc(ctx, drgba, (size_t)n * 16))) { duv.release(); drgba.release(); return rc; }
   fj::DTile t; t.id = tile->id; t.xmin = tile->xmin; t.ymin = tile->ymin; t.xmax = tile->xmax; t.ymax = tile->ymax;
-  fj::k_dump_tile_samples<<<std::min((n + 255) / 256, 1024), 256, 0, ctx->stream>>>(pl.fr, t, (const float4 *)ctx->d_samples.p, (double *)duv.p, (float4 *)drgba.p);
+  fj::k_dump_tile_samples<<<std::min((n + 255) / 256, 1024), 256, 0, ctx->stream>>>(pl.fr, t, (const fj::Accum *)ctx->d_samples.p, (double *)duv.p, (float4 *)drgba.p);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_uv, duv.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgba, drgba.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);

@@ -78,24 +78,21 @@ __device__ __forceinline__ C3 light_illuminate(const DLight &lt, const LightSamp
   }
 }
 
-// ------------------------------------------------------------------------------------------ path
+// ------------------------------------------------------------------------------------------ shading
 struct PathKey { uint32_t seed, tile, sample; };
+struct ShadeCounters { unsigned int rays[5]; unsigned int hits, levels; };
 
+// Shades one traced ray: adds its radiance (times the ray's throughput) to the sample through `sink.add`, and hands the
+// secondary rays it spawns to `sink.spawn` (SlTrace -> trace_surface -> Shader::evaluate, src/fj_shading.cc:140-179,
+// 527-572).  Shadow rays are traced inline (SlIlluminance needs the occluder's opacity before the light sample is
+// weighted).  Sink: add(r,g,b) in float, alpha(a) for camera rays, spawn(const RayRec&).
 template <typename T>
-struct PathTracer {
-  const DScene &sc; const DFrame &fr; PathKey key;
-  unsigned long long rays[5];
-  unsigned int hits, levels;
-  C3 acc;
-  Pending stack[FJ_PENDING];
-  int sp;
-
-  __device__ PathTracer(const DScene &s, const DFrame &f, PathKey k) : sc(s), fr(f), key(k), sp(0) {
-    rays[0] = rays[1] = rays[2] = rays[3] = rays[4] = 0; hits = levels = 0; acc = c3(0, 0, 0);
-  }
+struct Shading {
+  const DScene &sc; const DFrame &fr; PathKey key; ShadeCounters &cnt;
+  __device__ Shading(const DScene &s, const DFrame &f, PathKey k, ShadeCounters &c) : sc(s), fr(f), key(k), cnt(c) {}
   __device__ __forceinline__ double rnd(unsigned long long node, uint32_t dim) const { return ctr_rand(key.seed, key.tile, key.sample, node, dim); }
 
-  // SlIlluminance (src/fj_shading.cc:296-359) for one light sample; returns Kd * Cl contribution inputs.
+  // SlIlluminance (src/fj_shading.cc:296-359) for one light sample.
   __device__ __forceinline__ bool illuminance(const DLight &lt, const LightSample &ls, const D3 &Ps, const D3 &axis,
                                               int shaded_object, C3 *Cl, D3 *Ln_out) {
     D3 Ln = ls.P - Ps;
@@ -110,9 +107,9 @@ struct PathTracer {
     if (fr.cast_shadow) {                                        // SlShadowContext :266-279
       RayD sr; sr.o = Ps; sr.d = Ln; sr.tmin = .0001; sr.tmax = distance;
       Hit h;
-      rays[RAY_SHADOW]++;
+      cnt.rays[RAY_SHADOW]++;
       if (trace_closest<T>(sc, sc.inst[shaded_object].shadow_target, sr, &h)) {
-        hits++; levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
+        cnt.hits++; cnt.levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
         const float ac = fadd(1.f, -occluder_opacity(sc, h));
         lc.r = fmul(lc.r, ac); lc.g = fmul(lc.g, ac); lc.b = fmul(lc.b, ac);
       }
@@ -163,128 +160,136 @@ struct PathTracer {
     return diff;
   }
 
-  __device__ __forceinline__ void add(const C3 &thr, float r, float g, float b) {
-    acc.r = fadd(acc.r, fmul(thr.r, r)); acc.g = fadd(acc.g, fmul(thr.g, g)); acc.b = fadd(acc.b, fmul(thr.b, b));
-  }
-  __device__ __forceinline__ void push(const Pending &p) { if (sp < FJ_PENDING) stack[sp++] = p; }
-
-  // SlTrace for a camera sample and everything it spawns.  Returns (rgb, alpha) of the sample.
-  __device__ float4 run(const RayD &cam) {
-    float alpha = 0.f;
-    Pending cur;
-    cur.o = cam.o; cur.d = cam.d; cur.tmin = cam.tmin; cur.thr = c3(1, 1, 1); cur.transmit = c3(1, 1, 1);
-    cur.node = 1; cur.target = fr.target_group; cur.type = RAY_CAMERA; cur.dd = cur.rd = cur.fd = 0; cur.filter = 0;
-    double tmax = cam.tmax;
-    bool have = true;
-    while (have || sp > 0) {
-      if (!have) { cur = stack[--sp]; tmax = 1000.; }
-      have = false;
-      RayD ray; ray.o = cur.o; ray.d = cur.d; ray.tmin = cur.tmin; ray.tmax = tmax;
-      rays[cur.type]++;
-      Hit h;
-      if (!trace_closest<T>(sc, cur.target, ray, &h)) continue;
-      hits++; levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
-      C3 thr = cur.thr;
-      if (cur.filter) {    // pathtracing_shader.cc:247-251: C *= pow(transmit, t_hit) of the refracted child
-        thr.r = fmul(thr.r, (float)pow((double)cur.transmit.r, h.t));
-        thr.g = fmul(thr.g, (float)pow((double)cur.transmit.g, h.t));
-        thr.b = fmul(thr.b, (float)pow((double)cur.transmit.b, h.t));
-      }
-      D3 P, N; int slot;
-      hit_surface(sc, ray, h, &P, &N, &slot);
-      const DInstance &in = sc.inst[h.inst];
-      float Os = 1.f;
-      const int kind = slot < 0 ? 0 : sc.shaders[slot].kind;
-      if (kind == 0) {                                             // NO_SHADER_COLOR, fj_shading.cc:26,555-560
-        add(thr, .5f, 1.f, 0.f);
-      } else if (kind == 1) {                                      // ConstantShader::evaluate, constant_shader.cc:72-94
-        const DShader &sh = sc.shaders[slot];
-        add(thr, sh.diffuse[0], sh.diffuse[1], sh.diffuse[2]);
-      } else if (kind == 2) {                                      // PlasticShader::evaluate, plastic_shader.cc:101-179
-        const DShader &sh = sc.shaders[slot];
-        const D3 Nf = sl_faceforward(ray.d, N);
-        const C3 diff = gather_lights(P, Nf, h.inst, cur.node);
-        add(thr, fmul(diff.r, sh.diffuse[0]), fmul(diff.g, sh.diffuse[1]), fmul(diff.b, sh.diffuse[2]));
-        if (sh.do_reflect && (int)cur.rd + 1 <= fr.max_reflect) {  // SlReflectContext :242-252, gate :467-499
-          const double Kr = sl_fresnel(ray.d, Nf, ddiv(1., (double)sh.ior));
-          Pending c;
-          c.o = P; c.d = normalize(sl_reflect(ray.d, Nf)); c.tmin = .001;
-          c.thr = c3(fmul(thr.r, (float)dmul(Kr, (double)sh.reflect[0])), fmul(thr.g, (float)dmul(Kr, (double)sh.reflect[1])),
-                     fmul(thr.b, (float)dmul(Kr, (double)sh.reflect[2])));
-          c.transmit = c3(1, 1, 1); c.filter = 0;
-          c.node = cur.node * 4 + 2; c.target = in.reflect_target; c.type = RAY_REFLECT;
-          c.dd = cur.dd; c.rd = cur.rd + 1; c.fd = cur.fd;
-          push(c);
-        }
-        Os = sh.opacity;
-      } else {                                                     // PathtracingShader::evaluate, pathtracing_shader.cc:125-257
-        const DShader &sh = sc.shaders[slot];
-        add(thr, sh.emission[0], sh.emission[1], sh.emission[2]);
-        if (luminance(sh.refract) > 0.f && (int)cur.fd + 1 <= fr.max_refract) {     // integrate_refract :231-257
-          const double ior = ddiv(1., (double)sh.ior);
-          const double Kt = dsub(1., sl_fresnel(ray.d, N, ior));
-          Pending c;
-          c.o = P; c.d = normalize(sl_refract(ray.d, N, ior)); c.tmin = .0001;
-          const float kt = (float)Kt;
-          c.thr = c3(fmul(thr.r, fmul(kt, sh.refract[0])), fmul(thr.g, fmul(kt, sh.refract[1])), fmul(thr.b, fmul(kt, sh.refract[2])));
-          c.filter = (sh.do_color_filter && dot(ray.d, N) < 0) ? 1 : 0;
-          c.transmit = c3(sh.transmit[0], sh.transmit[1], sh.transmit[2]);
-          c.node = cur.node * 4 + 3; c.target = in.refract_target; c.type = RAY_REFRACT;
-          c.dd = cur.dd; c.rd = cur.rd; c.fd = cur.fd + 1;
-          push(c);
-        }
-        if (luminance(sh.reflect) > 0.f && (int)cur.rd + 1 <= fr.max_reflect) {     // integrate_reflect :210-229
-          const double Kr = sl_fresnel(ray.d, N, ddiv(1., (double)sh.ior));
-          Pending c;
-          c.o = P; c.d = normalize(sl_reflect(ray.d, N)); c.tmin = .001;
-          const float kr = (float)Kr;
-          c.thr = c3(fmul(thr.r, fmul(kr, sh.reflect[0])), fmul(thr.g, fmul(kr, sh.reflect[1])), fmul(thr.b, fmul(kr, sh.reflect[2])));
-          c.transmit = c3(1, 1, 1); c.filter = 0;
-          c.node = cur.node * 4 + 2; c.target = in.reflect_target; c.type = RAY_REFLECT;
-          c.dd = cur.dd; c.rd = cur.rd + 1; c.fd = cur.fd;
-          push(c);
-        }
-        if (luminance(sh.diffuse) > 0.f && (int)cur.dd + 1 <= fr.max_diffuse) {     // integrate_diffuse :176-208
-          const D3 w = N;
-          D3 u = fabs(w.x) > .001 ? mk(0., 1., 0.) : mk(1., 0., 0.);
-          u = normalize(cross(u, w));
-          const D3 v = cross(w, u);
-          const double x1 = rnd(cur.node, 0), x2 = rnd(cur.node, 1);
-          const double r1 = dmul(dmul(2., 3.14159265358979323846), x1), r2 = x2, r2s = __dsqrt_rn(r2);
-          const D3 D = normalize(((u * cos(r1)) * r2s + (v * sin(r1)) * r2s) + w * __dsqrt_rn(dsub(1., r2)));
-          const float Kd = (float)dot(N, D);
-          // the next ray continues in registers (it is the deepest branch of the DFS)
-          cur.thr = c3(fmul(thr.r, fmul(Kd, sh.diffuse[0])), fmul(thr.g, fmul(Kd, sh.diffuse[1])), fmul(thr.b, fmul(Kd, sh.diffuse[2])));
-          cur.o = P; cur.d = D; cur.tmin = .001; cur.transmit = c3(1, 1, 1); cur.filter = 0;
-          cur.node = cur.node * 4 + 1; cur.target = in.reflect_target;
-          const bool was_camera = cur.type == RAY_CAMERA;
-          cur.type = RAY_DIFFUSE; cur.dd = cur.dd + 1;
-          tmax = 1000.; have = true;
-          if (was_camera) alpha = 1.f;
-          continue;
-        }
-      }
-      if (cur.type == RAY_CAMERA) alpha = fminf(fmaxf(Os, 0.f), 1.f);             // trace_surface :562-566
+  template <typename Sink>
+  __device__ void shade(const RayRec &cur, const Hit &h, Sink &sink) {
+    RayD ray; ray.o = mk(cur.o[0], cur.o[1], cur.o[2]); ray.d = mk(cur.d[0], cur.d[1], cur.d[2]); ray.tmin = cur.tmin; ray.tmax = cur.tmax;
+    cnt.hits++; cnt.levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
+    C3 thr = c3(cur.thr[0], cur.thr[1], cur.thr[2]);
+    if (cur.filter_shader >= 0) {    // pathtracing_shader.cc:247-251: C *= pow(transmit, t_hit) of the refracted child
+      const DShader &fs = sc.shaders[cur.filter_shader];
+      thr.r = fmul(thr.r, (float)pow((double)fs.transmit[0], h.t));
+      thr.g = fmul(thr.g, (float)pow((double)fs.transmit[1], h.t));
+      thr.b = fmul(thr.b, (float)pow((double)fs.transmit[2], h.t));
     }
-    return make_float4(acc.r, acc.g, acc.b, alpha);
+    D3 P, N; int slot;
+    hit_surface(sc, ray, h, &P, &N, &slot);
+    const DInstance &in = sc.inst[h.inst];
+    float Os = 1.f;
+    const int kind = slot < 0 ? 0 : sc.shaders[slot].kind;
+    RayRec c;
+    c.o[0] = P.x; c.o[1] = P.y; c.o[2] = P.z; c.tmax = 1000.; c.slot = cur.slot; c.pad = 0; c.filter_shader = -1;
+    c.dd = cur.dd; c.rd = cur.rd; c.fd = cur.fd;
+    if (kind == 0) {                                               // NO_SHADER_COLOR, fj_shading.cc:26,555-560
+      sink.add(fmul(thr.r, .5f), thr.g, 0.f);
+    } else if (kind == 1) {                                        // ConstantShader::evaluate, constant_shader.cc:72-94
+      const DShader &sh = sc.shaders[slot];
+      sink.add(fmul(thr.r, sh.diffuse[0]), fmul(thr.g, sh.diffuse[1]), fmul(thr.b, sh.diffuse[2]));
+    } else if (kind == 2) {                                        // PlasticShader::evaluate, plastic_shader.cc:101-179
+      const DShader &sh = sc.shaders[slot];
+      const D3 Nf = sl_faceforward(ray.d, N);
+      const C3 diff = gather_lights(P, Nf, h.inst, cur.node);
+      sink.add(fmul(thr.r, fmul(diff.r, sh.diffuse[0])), fmul(thr.g, fmul(diff.g, sh.diffuse[1])), fmul(thr.b, fmul(diff.b, sh.diffuse[2])));
+      if (sh.do_reflect && (int)cur.rd + 1 <= fr.max_reflect) {    // SlReflectContext :242-252, gate :467-499
+        const double Kr = sl_fresnel(ray.d, Nf, ddiv(1., (double)sh.ior));
+        const D3 R = normalize(sl_reflect(ray.d, Nf));
+        c.d[0] = R.x; c.d[1] = R.y; c.d[2] = R.z; c.tmin = .001;
+        c.thr[0] = fmul(thr.r, (float)dmul(Kr, (double)sh.reflect[0])); c.thr[1] = fmul(thr.g, (float)dmul(Kr, (double)sh.reflect[1]));
+        c.thr[2] = fmul(thr.b, (float)dmul(Kr, (double)sh.reflect[2]));
+        c.node = cur.node * 4 + 2; c.target = in.reflect_target; c.type = RAY_REFLECT; c.rd = cur.rd + 1;
+        sink.spawn(c);
+        c.rd = cur.rd;
+      }
+      Os = sh.opacity;
+    } else {                                                       // PathtracingShader::evaluate, pathtracing_shader.cc:125-257
+      const DShader &sh = sc.shaders[slot];
+      sink.add(fmul(thr.r, sh.emission[0]), fmul(thr.g, sh.emission[1]), fmul(thr.b, sh.emission[2]));
+      if (luminance(sh.diffuse) > 0.f && (int)cur.dd + 1 <= fr.max_diffuse) {       // integrate_diffuse :176-208
+        const D3 w = N;
+        D3 u = fabs(w.x) > .001 ? mk(0., 1., 0.) : mk(1., 0., 0.);
+        u = normalize(cross(u, w));
+        const D3 v = cross(w, u);
+        const double x1 = rnd(cur.node, 0), x2 = rnd(cur.node, 1);
+        const double r1 = dmul(dmul(2., 3.14159265358979323846), x1), r2 = x2, r2s = __dsqrt_rn(r2);
+        const D3 D = normalize(((u * cos(r1)) * r2s + (v * sin(r1)) * r2s) + w * __dsqrt_rn(dsub(1., r2)));
+        const float Kd = (float)dot(N, D);
+        c.d[0] = D.x; c.d[1] = D.y; c.d[2] = D.z; c.tmin = .001;
+        c.thr[0] = fmul(thr.r, fmul(Kd, sh.diffuse[0])); c.thr[1] = fmul(thr.g, fmul(Kd, sh.diffuse[1])); c.thr[2] = fmul(thr.b, fmul(Kd, sh.diffuse[2]));
+        c.node = cur.node * 4 + 1; c.target = in.reflect_target; c.type = RAY_DIFFUSE; c.dd = cur.dd + 1;
+        sink.spawn(c);
+        c.dd = cur.dd;
+      }
+      if (luminance(sh.reflect) > 0.f && (int)cur.rd + 1 <= fr.max_reflect) {       // integrate_reflect :210-229
+        const float kr = (float)sl_fresnel(ray.d, N, ddiv(1., (double)sh.ior));
+        const D3 R = normalize(sl_reflect(ray.d, N));
+        c.d[0] = R.x; c.d[1] = R.y; c.d[2] = R.z; c.tmin = .001;
+        c.thr[0] = fmul(thr.r, fmul(kr, sh.reflect[0])); c.thr[1] = fmul(thr.g, fmul(kr, sh.reflect[1])); c.thr[2] = fmul(thr.b, fmul(kr, sh.reflect[2]));
+        c.node = cur.node * 4 + 2; c.target = in.reflect_target; c.type = RAY_REFLECT; c.rd = cur.rd + 1;
+        sink.spawn(c);
+        c.rd = cur.rd;
+      }
+      if (luminance(sh.refract) > 0.f && (int)cur.fd + 1 <= fr.max_refract) {       // integrate_refract :231-257
+        const double ior = ddiv(1., (double)sh.ior);
+        const float kt = (float)dsub(1., sl_fresnel(ray.d, N, ior));
+        const D3 Tr = normalize(sl_refract(ray.d, N, ior));
+        c.d[0] = Tr.x; c.d[1] = Tr.y; c.d[2] = Tr.z; c.tmin = .0001;
+        c.thr[0] = fmul(thr.r, fmul(kt, sh.refract[0])); c.thr[1] = fmul(thr.g, fmul(kt, sh.refract[1])); c.thr[2] = fmul(thr.b, fmul(kt, sh.refract[2]));
+        c.filter_shader = (sh.do_color_filter && dot(ray.d, N) < 0) ? slot : -1;
+        c.node = cur.node * 4 + 3; c.target = in.refract_target; c.type = RAY_REFRACT; c.fd = cur.fd + 1;
+        sink.spawn(c);
+      }
+    }
+    if (cur.type == RAY_CAMERA) sink.alpha(fminf(fmaxf(Os, 0.f), 1.f));               // trace_surface :562-566
   }
 };
 
-// ------------------------------------------------------------------------------------------ kernels
+// Sample (x, y) and tile of a slot — inverse of sample_slot().
+__device__ __forceinline__ void slot_decode(const DFrame &fr, const DTile *tiles, uint32_t wstride, uint32_t slot, int *ti, TileGrid *g, int *x, int *y) {
+  *ti = (int)(slot / wstride);
+  const uint32_t r = slot % wstride, blk = r >> 5, l = r & 31;
+  *g = tile_grid(fr, tiles[*ti]);
+  *x = (int)(blk % g->nbx) * 8 + (int)(l & 7); *y = (int)(blk / g->nbx) * 4 + (int)(l >> 3);
+}
+
+// ------------------------------------------------------------------------------------------ frame arguments
+struct QueueCtl { unsigned int count[2]; unsigned int head; unsigned int overflow; };
 struct RenderArgs {
   DScene sc; DCamera cam; DFrame fr;
   const DTile *tiles; int ntiles;         // tiles of this batch
-  uint32_t wstride;                       // sample slots per tile in `samples` (multiple of 32)
-  float4 *samples;                        // ntiles * wstride
+  uint32_t wstride;                       // sample slots per tile (multiple of 32)
+  Accum *accum;                           // ntiles * wstride per-sample accumulators
   DCounters *counters;
-  unsigned long long *work;               // global work counter (units of 32 slots)
+  unsigned long long *work;               // megakernel: global work counter (units of 32 slots)
+  RayRec *queue[2]; HitRec *hits; QueueCtl *ctl; uint32_t capacity; int cur;     // wavefront
+  int refill, phase_a_min;                // k_extend scheduling thresholds (lanes)
+};
+
+__device__ __forceinline__ void flush_counters(const ShadeCounters &c, unsigned long long nsamp, DCounters *out, int lane) {
+  unsigned long long v[8] = {c.rays[0], c.rays[1], c.rays[2], c.rays[3], c.rays[4], c.hits, c.levels, nsamp};
+  for (int k = 0; k < 8; k++) {
+    unsigned long long x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0 && x) atomicAdd(k < 5 ? &out->rays[k] : (k == 5 ? &out->hits : (k == 6 ? &out->levels : &out->samples)), x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ megakernel (cross-check path)
+// One camera sample per lane with a private DFS stack of pending rays; warps pull 8x4 sample blocks from a global
+// counter.  Kept as the independent second implementation the parity tests compare the wavefront against
+// (FJGPU_FLAG_MEGAKERNEL), with FP32 or FP64 (FJGPU_FLAG_FP64_BOXES) box culling.
+struct StackSink {
+  RayRec *stack; int sp; C3 acc; float a;
+  __device__ __forceinline__ void add(float r, float g, float b) { acc.r = fadd(acc.r, r); acc.g = fadd(acc.g, g); acc.b = fadd(acc.b, b); }
+  __device__ __forceinline__ void alpha(float v) { a = v; }
+  __device__ __forceinline__ void spawn(const RayRec &c) { if (sp < FJ_PENDING) stack[sp++] = c; }
 };
 
 template <typename T>
 __global__ void __launch_bounds__(128) k_render_samples(const RenderArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned long long total = (unsigned long long)a.ntiles * a.wstride;
-  unsigned long long cnt[7] = {0, 0, 0, 0, 0, 0, 0}; unsigned long long nsamp = 0;
+  ShadeCounters cnt; memset(&cnt, 0, sizeof cnt);
+  unsigned long long nsamp = 0;
+  RayRec stack[FJ_PENDING];
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(a.work, 32ull);
@@ -296,39 +301,308 @@ __global__ void __launch_bounds__(128) k_render_samples(const RenderArgs a) {
     const TileGrid g = tile_grid(a.fr, tile);
     if (blk >= (uint32_t)(g.nbx * g.nby)) continue;
     const int x = (int)(blk % g.nbx) * 8 + (lane & 7), y = (int)(blk / g.nbx) * 4 + (lane >> 3);
-    float4 out = make_float4(0, 0, 0, 0);
+    Accum out; out.r = out.g = out.b = 0; out.a = 0.f; out.pad = 0;
     if (x < g.nsx && y < g.nsy) {
       double u, v; sample_uv(a.fr, g, x, y, &u, &v);
       RayD ray; camera_ray(a.cam, u, v, &ray);
       PathKey key; key.seed = a.fr.seed; key.tile = (uint32_t)tile.id; key.sample = (uint32_t)(y * g.nsx + x);
-      PathTracer<T> pt(a.sc, a.fr, key);
-      out = pt.run(ray);
-      for (int k = 0; k < 5; k++) cnt[k] += pt.rays[k];
-      cnt[5] += pt.hits; cnt[6] += pt.levels;
+      Shading<T> sh(a.sc, a.fr, key, cnt);
+      StackSink sink; sink.stack = stack; sink.sp = 0; sink.acc = c3(0, 0, 0); sink.a = 0.f;
+      RayRec cur;
+      cur.o[0] = ray.o.x; cur.o[1] = ray.o.y; cur.o[2] = ray.o.z; cur.d[0] = ray.d.x; cur.d[1] = ray.d.y; cur.d[2] = ray.d.z;
+      cur.tmin = ray.tmin; cur.tmax = ray.tmax; cur.thr[0] = cur.thr[1] = cur.thr[2] = 1.f; cur.slot = 0; cur.node = 1;
+      cur.target = a.fr.target_group; cur.type = RAY_CAMERA; cur.dd = cur.rd = cur.fd = 0; cur.filter_shader = -1; cur.pad = 0;
+      sink.spawn(cur);
+      while (sink.sp > 0) {
+        cur = stack[--sink.sp];
+        RayD r; r.o = mk(cur.o[0], cur.o[1], cur.o[2]); r.d = mk(cur.d[0], cur.d[1], cur.d[2]); r.tmin = cur.tmin; r.tmax = cur.tmax;
+        cnt.rays[cur.type]++;
+        Hit h;
+        if (!trace_closest<T>(a.sc, cur.target, r, &h)) continue;
+        sh.shade(cur, h, sink);
+      }
+      out.r = to_fix(sink.acc.r); out.g = to_fix(sink.acc.g); out.b = to_fix(sink.acc.b); out.a = sink.a;
       nsamp++;
     }
-    a.samples[(size_t)ti * a.wstride + (blk << 5) + lane] = out;
+    a.accum[(size_t)ti * a.wstride + (blk << 5) + lane] = out;
   }
-  for (int k = 0; k < 7; k++) {
-    unsigned long long v = cnt[k];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0 && v) atomicAdd(k < 5 ? &a.counters->rays[k] : (k == 5 ? &a.counters->hits : &a.counters->levels), v);
+  flush_counters(cnt, nsamp, a.counters, lane);
+}
+
+// ------------------------------------------------------------------------------------------ wavefront: generate
+// Sampler + camera: one camera ray per sample of the batch into queue[cur]; zeroes the accumulators
+// (FixedGridSampler::generate_samples + Camera::GetRay, integrate_samples loop head src/fj_renderer.cc:1061-1075).
+__global__ void __launch_bounds__(256) k_generate(const RenderArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long total = (unsigned long long)a.ntiles * a.wstride;
+  RayRec *q = a.queue[a.cur];
+  unsigned long long nsamp = 0;
+  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w - lane < total; w += (unsigned long long)gridDim.x * blockDim.x) {
+    bool valid = false; RayRec r;
+    if (w < total) {
+      int ti, x, y; TileGrid g;
+      slot_decode(a.fr, a.tiles, a.wstride, (uint32_t)w, &ti, &g, &x, &y);
+      Accum z; z.r = z.g = z.b = 0; z.a = 0.f; z.pad = 0;
+      a.accum[w] = z;
+      if (x < g.nsx && y < g.nsy) {
+        double u, v; sample_uv(a.fr, g, x, y, &u, &v);
+        RayD ray; camera_ray(a.cam, u, v, &ray);
+        r.o[0] = ray.o.x; r.o[1] = ray.o.y; r.o[2] = ray.o.z; r.d[0] = ray.d.x; r.d[1] = ray.d.y; r.d[2] = ray.d.z;
+        r.tmin = ray.tmin; r.tmax = ray.tmax; r.thr[0] = r.thr[1] = r.thr[2] = 1.f; r.slot = (uint32_t)w; r.node = 1;
+        r.target = a.fr.target_group; r.type = RAY_CAMERA; r.dd = r.rd = r.fd = 0; r.filter_shader = -1; r.pad = 0;
+        valid = true; nsamp++;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (m) {
+      unsigned base = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(&a.ctl->count[a.cur], __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (valid) {
+        const unsigned i = base + __popc(m & ((1u << lane) - 1));
+        if (i < a.capacity) q[i] = r; else a.ctl->overflow = 1;
+      }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) nsamp += __shfl_down_sync(0xffffffffu, nsamp, o);
   if (lane == 0 && nsamp) atomicAdd(&a.counters->samples, nsamp);
 }
 
+// ------------------------------------------------------------------------------------------ wavefront: extend
+// Persistent-threads closest-hit kernel over queue[cur]: every lane owns one ray at a time and pulls the next one from
+// the queue head as soon as a quarter of the warp has run dry (warp-aggregated atomic), so the traversal loop keeps
+// >= 24 lanes busy instead of waiting for the slowest ray of a fixed batch.  Semantics of trace_closest():
+// Accelerator::Intersect on the group's accelerator (src/fj_shading.cc:538-541).
+//
+// Box culling is FP32 with a rigorous error bound folded into the FMA constants (no per-node slack arithmetic):
+//   t(plane) = fma(plane, 1/d, -(o/d) -+ e),  e = 2^-20 (|o| + B) |1/d|  >=  every rounding of o, 1/d, the product and the
+//   fma for planes with |plane| <= B (B = bound magnitude of the space being traversed), so a box the exact FP64 ray
+//   touches within [tmin, best_t] is never culled.  Triangles are then tested in exact FP64 (tri_intersect).
+struct BoxRay32 { float ix, iy, iz, nx, ny, nz, fx, fy, fz; };
+__device__ __forceinline__ void box_axis(double o, double d, float B, float *inv, float *cn, float *cf) {
+  float df = (float)d;
+  if (!(fabsf(df) >= 1e-18f)) df = (df < 0.f || (df == 0.f && signbit(df))) ? -1e-18f : 1e-18f;
+  const float i = __frcp_rn(df);
+  const float of = (float)o;
+  const float p = __fmul_rn(of, i);
+  const float e = __fmul_rn(__fmul_rn(__fadd_rn(fabsf(of), B), fabsf(i)), 9.5367431640625e-07f);
+  *inv = i; *cn = __fsub_rn(-p, e); *cf = __fadd_rn(-p, e);
+}
+__device__ __forceinline__ void make_box_ray32(const D3 &o, const D3 &d, float B, BoxRay32 &r) {
+  box_axis(o.x, d.x, B, &r.ix, &r.nx, &r.fx);
+  box_axis(o.y, d.y, B, &r.iy, &r.ny, &r.fy);
+  box_axis(o.z, d.z, B, &r.iz, &r.nz, &r.fz);
+}
+
+// Warp-synchronous structure (every loop is controlled by a ballot, so the 32 lanes stay converged by construction):
+//   refill   when >= FJ_REFILL lanes are idle, they take the next rays from the queue head (one warp-aggregated atomic)
+//   phase A  inner-node steps for all lanes that have one; a lane that reaches a triangle leaf parks it in `leaf`
+//            and keeps descending with the next stack entry (speculative traversal) until it holds a second leaf
+//   phase B  the parked leaves: one exact FP64 triangle test per lane per iteration; then the rare transitions
+//            (enter an instance, leave it, finish the ray and write its hit record)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const RayRec *rays = a.queue[a.cur];
+  const unsigned count = min(a.ctl->count[a.cur], a.capacity);
+  const DScene &sc = a.sc;
+  int stack[FJ_STACK];
+  const int SENTINEL = (int)0x80000000, DONE = (int)0x80000001;
+
+  bool active = false, drained = false;
+  unsigned ridx = 0;
+  int sp = 0, node = DONE, leaf = 0, cur_inst = -1, best_prim = -1, best_inst = -1;
+  bool in_blas = false, found = false;
+  double tmin = 0, tmax = 0, best_t = 0, best_u = 0, best_v = 0;
+  float tn = 0, tf = 0;
+  D3 o = mk(0, 0, 0), d = mk(0, 0, 0);          // object-space ray while inside a BLAS
+  BoxRay32 br; br.ix = br.iy = br.iz = br.nx = br.ny = br.nz = br.fx = br.fy = br.fz = 0.f;
+  const float4 *nodes = nullptr, *tlas = nullptr; const int32_t *order = nullptr; float tlas_B = 0;
+  const float4 *tri32 = nullptr; const double *tri64 = nullptr;
+
+  for (;;) {
+    // ---- refill idle lanes from the queue head
+    const unsigned idle = __ballot_sync(FULL, !active);
+    if (idle == FULL && drained) break;
+    if (!drained && __popc(idle) >= a.refill) {
+      const int n = __popc(idle), leader = __ffs(idle) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(&a.ctl->head, (unsigned)n);
+      base = __shfl_sync(FULL, base, leader);
+      if (base + n >= count) drained = true;
+      if (!active) {
+        const unsigned i = base + __popc(idle & ((1u << lane) - 1));
+        if (i < count) {
+          ridx = i;
+          const RayRec &r = rays[i];
+          tmin = r.tmin; tmax = r.tmax; best_t = tmax; found = false; best_prim = -1; best_inst = -1; best_u = best_v = 0;
+          tn = __double2float_rd(tmin); tf = __double2float_ru(best_t);
+          const DGroup grp = sc.groups[r.target];
+          tlas = grp.nodes; order = grp.order; tlas_B = grp.bmag;
+          nodes = tlas; in_blas = false; sp = 0; node = 0; leaf = 0;
+          make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br);
+          active = true;
+        }
+      }
+      if (__ballot_sync(FULL, active) == 0) break;
+    }
+
+    // ---- phase A: inner nodes (both children, nearer first)
+    for (;;) {
+      const bool want = active && node >= 0;
+      const unsigned wm = __ballot_sync(FULL, want);
+      if (wm == 0) break;
+      // few lanes left descending: switch to the parked leaves / transitions if there are any to work on
+      if (__popc(wm) < a.phase_a_min && __any_sync(FULL, active && (leaf != 0 || node < 0))) break;
+      if (want) {
+        const float4 *np = nodes + 4 * (size_t)node;
+        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+        // child0: x,y in n0 (lo.x hi.x lo.y hi.y), z in n2.xy ; child1: x,y in n1, z in n2.zw
+        const bool sx = br.ix < 0.f, sy = br.iy < 0.f, sz = br.iz < 0.f;
+        const float a0 = fmaf(sx ? n0.y : n0.x, br.ix, br.nx), b0 = fmaf(sx ? n0.x : n0.y, br.ix, br.fx);
+        const float a1 = fmaf(sy ? n0.w : n0.z, br.iy, br.ny), b1 = fmaf(sy ? n0.z : n0.w, br.iy, br.fy);
+        const float a2 = fmaf(sz ? n2.y : n2.x, br.iz, br.nz), b2 = fmaf(sz ? n2.x : n2.y, br.iz, br.fz);
+        const float c0 = fmaf(sx ? n1.y : n1.x, br.ix, br.nx), d0 = fmaf(sx ? n1.x : n1.y, br.ix, br.fx);
+        const float c1 = fmaf(sy ? n1.w : n1.z, br.iy, br.ny), d1 = fmaf(sy ? n1.z : n1.w, br.iy, br.fy);
+        const float c2 = fmaf(sz ? n2.w : n2.z, br.iz, br.nz), d2 = fmaf(sz ? n2.z : n2.w, br.iz, br.fz);
+        const float near0 = fmaxf(fmaxf(a0, a1), fmaxf(a2, tn)), far0 = fminf(fminf(b0, b1), fminf(b2, tf));
+        const float near1 = fmaxf(fmaxf(c0, c1), fmaxf(c2, tn)), far1 = fminf(fminf(d0, d1), fminf(d2, tf));
+        const bool h0 = near0 <= far0, h1 = near1 <= far1;
+        const int k0 = __float_as_int(n3.x), k1 = __float_as_int(n3.y);
+        const bool swap = h1 && (!h0 || near1 < near0);          // visit child 1 first
+        const int kf = swap ? k1 : k0, ks = swap ? k0 : k1;
+        if (h0 && h1) stack[sp++] = ks;
+        if (h0 || h1) node = kf;
+        else node = sp > 0 ? stack[--sp] : DONE;
+        // park a triangle leaf and keep descending
+        if (node < 0 && in_blas && node != SENTINEL && leaf == 0) { leaf = node; node = stack[--sp]; }     // SENTINEL is below every BLAS entry
+      }
+    }
+
+    // ---- phase B1: parked triangle leaves, exact FP64 tests, one triangle per lane per iteration
+    {
+      const int ref = ~leaf;
+      const int first = ref >> 3, cnt = leaf != 0 ? (ref & 7) + 1 : 0;
+      for (int k = 0;; k++) {
+        const bool want = k < cnt;
+        if (!__any_sync(FULL, want)) break;
+        if (want) {
+          D3 v0, v1, v2; int prim;
+          if (tri32) {
+            const float4 *tp = tri32 + 3 * (size_t)(first + k);
+            const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+            v0 = mk(p0.x, p0.y, p0.z); v1 = mk(p1.x, p1.y, p1.z); v2 = mk(p2.x, p2.y, p2.z); prim = __float_as_int(p0.w);
+          } else {
+            const double *p = tri64 + 10 * (size_t)(first + k);
+            v0 = mk(p[0], p[1], p[2]); v1 = mk(p[3], p[4], p[5]); v2 = mk(p[6], p[7], p[8]); prim = (int)__double_as_longlong(p[9]);
+          }
+          double t, u, v;
+          if (tri_intersect(v0, v1, v2, o, d, &t, &u, &v) && tmin <= t && t <= tmax) {       // RayInRange, src/fj_ray.h:29-32
+            const bool better = !found ? true : (t < best_t || (t == best_t && (cur_inst < best_inst || (cur_inst == best_inst && prim > best_prim))));
+            if (better) { found = true; best_t = t; best_u = u; best_v = v; best_prim = prim; best_inst = cur_inst; tf = __double2float_ru(t); }
+          }
+        }
+      }
+      leaf = 0;
+    }
+
+    // ---- phase B2: transitions of lanes whose next stack entry is not an inner node
+    const bool special = active && node < 0;
+    if (__any_sync(FULL, special)) {
+      if (special) {
+        if (node == DONE) {                        // traversal finished: write the hit record
+          HitRec hr; hr.t = found ? best_t : FJ_REAL_MAX; hr.u = best_u; hr.v = best_v; hr.prim = best_prim; hr.inst = found ? best_inst : -1;
+          a.hits[ridx] = hr;
+          active = false;
+        } else if (node == SENTINEL) {             // the instance's BLAS is done: back to world space
+          const RayRec &r = rays[ridx];
+          make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br);
+          in_blas = false; nodes = tlas;
+          node = sp > 0 ? stack[--sp] : DONE;
+        } else if (in_blas) {                      // a second triangle leaf: park it now that the slot is free
+          leaf = node; node = stack[--sp];
+        } else {                                   // TLAS leaf: enter the first instance, re-queue the others
+          const int ref = ~node;
+          const int first = ref >> 3, cnt = (ref & 7) + 1;
+          for (int k = cnt - 1; k >= 1; k--) stack[sp++] = ~(((first + k) << 3) | 0);
+          cur_inst = order[first];
+          const DInstance &in = sc.inst[cur_inst];
+          const RayRec &r = rays[ridx];
+          o = mat_point(in.inv, mk(r.o[0], r.o[1], r.o[2]));
+          d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
+          const DMesh &m = sc.meshes[in.mesh];
+          make_box_ray32(o, d, m.bmag, br);
+          nodes = m.nodes; tri32 = m.tri32; tri64 = m.tri64;
+          in_blas = true;
+          stack[sp++] = SENTINEL;
+          node = 0;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ wavefront: shade
+struct QueueSink {
+  const RenderArgs &a; RayRec *next; int lane;
+  long long r, g, b; bool has_alpha; float av;
+  __device__ __forceinline__ void add(float x, float y, float z) { r += to_fix(x); g += to_fix(y); b += to_fix(z); }
+  __device__ __forceinline__ void alpha(float v) { has_alpha = true; av = v; }
+  // the warp may be diverged here: aggregate over whichever lanes arrive together
+  __device__ __forceinline__ void spawn(const RayRec &c) {
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&a.ctl->count[a.cur ^ 1], (unsigned)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const unsigned i = base + __popc(m & ((1u << lane) - 1));
+    if (i < a.capacity) next[i] = c; else a.ctl->overflow = 1;
+  }
+};
+
+// One thread per traced ray of queue[cur]: shader evaluation, radiance into the sample accumulators, secondary rays
+// compacted into queue[cur ^ 1] by warp ballot (Shader::Evaluate + the Sl*Context/SlTrace calls the plugins make).
+template <typename T>
+__global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned count = min(a.ctl->count[a.cur], a.capacity);
+  const RayRec *rays = a.queue[a.cur];
+  ShadeCounters cnt; memset(&cnt, 0, sizeof cnt);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const RayRec cur = rays[i];
+    const HitRec hr = a.hits[i];
+    cnt.rays[cur.type]++;
+    if (hr.inst < 0) continue;
+    int ti, x, y; TileGrid g;
+    slot_decode(a.fr, a.tiles, a.wstride, cur.slot, &ti, &g, &x, &y);
+    PathKey key; key.seed = a.fr.seed; key.tile = (uint32_t)a.tiles[ti].id; key.sample = (uint32_t)(y * g.nsx + x);
+    Shading<T> sh(a.sc, a.fr, key, cnt);
+    QueueSink sink{a, a.queue[a.cur ^ 1], lane, 0, 0, 0, false, 0.f};
+    Hit h; h.t = hr.t; h.u = hr.u; h.v = hr.v; h.prim = hr.prim; h.inst = hr.inst;
+    sh.shade(cur, h, sink);
+    Accum *acc = a.accum + cur.slot;
+    if (sink.r) atomicAdd((unsigned long long *)&acc->r, (unsigned long long)sink.r);
+    if (sink.g) atomicAdd((unsigned long long *)&acc->g, (unsigned long long)sink.g);
+    if (sink.b) atomicAdd((unsigned long long *)&acc->b, (unsigned long long)sink.b);
+    if (sink.has_alpha) acc->a = sink.av;
+  }
+  flush_counters(cnt, 0, a.counters, lane);
+}
+
+// ------------------------------------------------------------------------------------------ resolve
 // reconstruct_image + apply_pixel_filter (src/fj_renderer.cc:939-995), get_sampleset_in_pixel
 // (src/fj_fixed_grid_sampler.cc:97-124), Gaussian (src/fj_filter.cc:49-58).  One CTA per tile, one thread per pixel.
 // Output: packed tile blocks, block ti = bw*bh float4 (row-major inside the tile; texels outside the tile untouched).
 __global__ void __launch_bounds__(256) k_resolve_tiles(const DFrame fr, const DTile *tiles, uint32_t wstride,
-                                                       const float4 *samples, float4 *blocks, int bw, int bh) {
+                                                       const Accum *samples, float4 *blocks, int bw, int bh) {
   const int ti = blockIdx.x;
   const DTile t = tiles[ti];
   const TileGrid g = tile_grid(fr, t);
   const int w = t.xmax - t.xmin, h = t.ymax - t.ymin;
   const int npx = fr.xrate + 2 * fr.mx, npy = fr.yrate + 2 * fr.my;
-  const float4 *smp = samples + (size_t)ti * wstride;
+  const Accum *smp = samples + (size_t)ti * wstride;
   for (int p = threadIdx.x; p < w * h; p += blockDim.x) {
     const int px = p % w, py = p / w;
     const int x = t.xmin + px, y = t.ymin + py;
@@ -338,16 +612,16 @@ __global__ void __launch_bounds__(256) k_resolve_tiles(const DFrame fr, const DT
       for (int sx = 0; sx < npx; sx++) {
         const int gx = px * fr.xrate + sx;
         double u, v; sample_uv(fr, g, gx, gy, &u, &v);
-        const float4 s = smp[sample_slot(g, gx, gy)];
+        const Accum s = smp[sample_slot(g, gx, gy)];
         const double fx = dsub(dmul((double)fr.xres, u), dadd((double)x, .5));
         const double fy = dsub(dmul((double)fr.yres, dsub(1., v)), dadd((double)y, .5));
         const double xx = ddiv(dmul(2., fx), fr.xfw), yy = ddiv(dmul(2., fy), fr.yfw);
         const double wgt = exp(dmul(-2., dadd(dmul(xx, xx), dmul(yy, yy))));
         // float accumulators, double products (fj_renderer.cc:953-961: `pixel.r += wgt * sample.data.r`)
-        pr = (float)dadd((double)pr, dmul(wgt, (double)s.x));
-        pg = (float)dadd((double)pg, dmul(wgt, (double)s.y));
-        pb = (float)dadd((double)pb, dmul(wgt, (double)s.z));
-        pa = (float)dadd((double)pa, dmul(wgt, (double)s.w));
+        pr = (float)dadd((double)pr, dmul(wgt, (double)from_fix(s.r)));
+        pg = (float)dadd((double)pg, dmul(wgt, (double)from_fix(s.g)));
+        pb = (float)dadd((double)pb, dmul(wgt, (double)from_fix(s.b)));
+        pa = (float)dadd((double)pa, dmul(wgt, (double)s.a));
         wsum = (float)dadd((double)wsum, wgt);
       }
     }
@@ -367,6 +641,8 @@ __global__ void k_blocks_to_frame(const DTile *tiles, int ntiles, const float4 *
   }
 }
 
+// ------------------------------------------------------------------------------------------ probes
+// Closest hit of caller-supplied rays through the megakernel's traversal (FP32 or FP64 box culling).
 template <typename T>
 __global__ void __launch_bounds__(128) k_trace_closest(const DScene sc, int group, int n, const double *orig, const double *dir,
                                                        const double *tmin, const double *tmax,
@@ -380,16 +656,34 @@ __global__ void __launch_bounds__(128) k_trace_closest(const DScene sc, int grou
   out_t[i] = hit ? h.t : FJ_REAL_MAX; out_u[i] = hit ? h.u : 0.; out_v[i] = hit ? h.v : 0.;
   out_prim[i] = hit ? h.prim : -1; out_inst[i] = hit ? h.inst : -1;
 }
+// The same probe through the wavefront's extend kernel: rays -> queue records, hit records -> arrays.
+__global__ void k_probe_pack(int group, int n, const double *orig, const double *dir, const double *tmin, const double *tmax, RayRec *q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RayRec r; memset(&r, 0, sizeof r);
+  for (int k = 0; k < 3; k++) { r.o[k] = orig[3 * i + k]; r.d[k] = dir[3 * i + k]; }
+  r.tmin = tmin[i]; r.tmax = tmax[i]; r.target = group; r.filter_shader = -1;
+  q[i] = r;
+}
+__global__ void k_probe_unpack(int n, const HitRec *hits, double *out_t, double *out_u, double *out_v, int32_t *out_prim, int32_t *out_inst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HitRec h = hits[i];
+  const bool hit = h.inst >= 0;
+  out_t[i] = hit ? h.t : FJ_REAL_MAX; out_u[i] = hit ? h.u : 0.; out_v[i] = hit ? h.v : 0.;
+  out_prim[i] = hit ? h.prim : -1; out_inst[i] = h.inst;
+}
 
 // Per-sample dump of one tile (probe): uv + radiance in row-major sample order.
-__global__ void k_dump_tile_samples(const DFrame fr, const DTile t, const float4 *samples, double *out_uv, float4 *out_rgba) {
+__global__ void k_dump_tile_samples(const DFrame fr, const DTile t, const Accum *samples, double *out_uv, float4 *out_rgba) {
   const TileGrid g = tile_grid(fr, t);
   const int n = g.nsx * g.nsy;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int x = i % g.nsx, y = i / g.nsx;
     double u, v; sample_uv(fr, g, x, y, &u, &v);
     out_uv[2 * i] = u; out_uv[2 * i + 1] = v;
-    out_rgba[i] = samples[sample_slot(g, x, y)];
+    const Accum s = samples[sample_slot(g, x, y)];
+    out_rgba[i] = make_float4(from_fix(s.r), from_fix(s.g), from_fix(s.b), s.a);
   }
 }
 

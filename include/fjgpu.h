@@ -157,8 +157,11 @@ typedef struct fjgpu_render_params {
   int32_t _pad;
 } fjgpu_render_params;
 
-enum { FJGPU_FLAG_FP64_BOXES = 1    /* cull BVH boxes with FP64 slab arithmetic instead of the default
-                                       conservative FP32 (same hits; a cross-check for the parity tests) */ };
+enum { FJGPU_FLAG_FP64_BOXES = 1,   /* cull BVH boxes with FP64 slab arithmetic instead of the default conservative
+                                       FP32 (same hits; a cross-check for the parity tests; implies the megakernel) */
+       FJGPU_FLAG_MEGAKERNEL = 2    /* one camera sample per lane with a private ray stack instead of the wavefront
+                                       (generate / extend / shade rounds over ray queues): the independent second
+                                       implementation the wavefront is checked against */ };
 
 typedef struct fjgpu_tile {         /* Tile of src/fj_tiler.h; [xmin,xmax) x [ymin,ymax) pixels */
   int32_t id;                       /* global tile id in the frame's tile list (keys the RNG) */
@@ -172,10 +175,11 @@ typedef struct fjgpu_stats {
   uint64_t hit_mesh_levels;         /* sum over those rays of ceil(log2(triangles of the mesh hit)): the root-to-leaf
                                        path lengths of the algorithmic-bytes model */
   uint64_t kernel_launches;         /* launches of this library's kernels in the call */
-  float    ms_trace;                /* device time of the sample/trace/shade kernels (CUDA events) */
+  uint64_t trace_launches;          /* launches of the closest-hit kernel (k_extend; k_render_samples in megakernel mode) */
+  float    ms_trace;                /* device time of the closest-hit kernel launches (CUDA events on the launching stream) */
   float    ms_resolve;              /* device time of the pixel-filter kernels */
   float    ms_total;                /* device time of the whole call incl. copies */
-  float    _pad;
+  float    ms_shade;                /* device time of the generate + shade kernels */
 } fjgpu_stats;
 
 /* Renders `ntiles` tiles (sampler -> camera rays -> trace/shade -> Gaussian resolve), i.e. the

@@ -49,7 +49,7 @@ def random_rays(n, seed, radius=4.0):
 
 
 @pytest.mark.parametrize("scene", ["cube_c1", "plastic", "multi"])
-@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("flags", [0, 1, 2])      # wavefront extend kernel, megakernel FP64 boxes, megakernel FP32 boxes
 def test_trace_closest_bit_exact(sk, device, scene, flags):
     desc = golden_scenes.SCENES[scene]()
     st = desc.to_structs()
@@ -176,6 +176,22 @@ def test_frame_matches_oracle(sk, device, name):
     for k in ("rays_camera", "rays_shadow", "rays_diffuse", "rays_reflect", "rays_refract", "camera_samples"):
         assert getattr(stats, k) == getattr(rstats, k), k
     assert stats.kernel_launches >= 2
+
+
+@pytest.mark.parametrize("name", ["plastic_4l", "multi", "pt_branching", "sphere_light"])
+@pytest.mark.parametrize("flags", [1, 2])
+def test_megakernel_cross_check(sk, device, name, flags):
+    """The two independent device implementations (wavefront rounds over ray queues vs one sample per lane with a
+    private ray stack, FP32 or FP64 box culling) trace identical ray trees and agree to float rounding."""
+    desc = golden_scenes.SCENES[name]()
+    st = desc.to_structs()
+    a, sa = gpu_render(device, desc, st)
+    st["params"].flags = flags
+    b, sb = gpu_render(device, desc, st)
+    st["params"].flags = 0
+    assert np.abs(a - b).max() < 2e-6 * max(1.0, float(np.abs(a).max()))
+    for k in ("rays_camera", "rays_shadow", "rays_diffuse", "rays_reflect", "rays_refract", "rays_hit", "hit_mesh_levels"):
+        assert getattr(sa, k) == getattr(sb, k), k
 
 
 @pytest.mark.parametrize("name", golden_scenes.DETERMINISTIC)
