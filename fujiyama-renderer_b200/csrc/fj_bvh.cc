@@ -138,12 +138,16 @@ inline int32_t leaf_ref(int32_t first, int32_t count) { return ~((first << 3) | 
 
 void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int top_levels, BuildResult *out) {
   out->nodes.clear(); out->order.clear(); out->top_count = 0; out->max_depth = 0;
+  out->nodes4.clear(); out->max_depth4 = 0;
+  Node128 empty4; memset(&empty4, 0, sizeof empty4);
+  for (int k = 0; k < 4; k++) { empty4.lox[k] = empty4.loy[k] = empty4.loz[k] = 3e38f; empty4.hix[k] = empty4.hiy[k] = empty4.hiz[k] = -3e38f; empty4.c[k] = ~0; }
   box_empty(out->bounds);
   Node64 empty_node; memset(&empty_node, 0, sizeof empty_node);
   for (int k = 0; k < 12; k++) empty_node.f[k] = (k % 2 == 0) ? 3e38f : -3e38f;   // lo = +big, hi = -big: never hit
   empty_node.c[0] = empty_node.c[1] = leaf_ref(0, 1);
   if (n <= 0) {   // an empty set: one node with two never-hit children
     out->nodes.push_back(empty_node); out->top_count = 1;
+    out->nodes4.push_back(empty4); out->max_depth4 = 1;
     return;
   }
   Builder B;
@@ -170,6 +174,11 @@ void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int 
     Node64 nd = empty_node;
     set_child(nd, 0, B.nodes[root], leaf_ref(0, B.nodes[root].count));
     out->nodes.push_back(nd); out->top_count = 1; out->max_depth = 1;
+    Node128 w = empty4;
+    const BNode &r = B.nodes[root];
+    w.lox[0] = r.box.lo[0]; w.hix[0] = r.box.hi[0]; w.loy[0] = r.box.lo[1]; w.hiy[0] = r.box.hi[1]; w.loz[0] = r.box.lo[2]; w.hiz[0] = r.box.hi[2];
+    w.c[0] = leaf_ref(0, r.count);
+    out->nodes4.push_back(w); out->max_depth4 = 1;
     return;
   }
 
@@ -211,6 +220,41 @@ void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int 
     set_child(o, 0, l, l.left >= 0 ? newid[nd.left] : leaf_ref(l.first, l.count));
     set_child(o, 1, r, r.left >= 0 ? newid[nd.right] : leaf_ref(r.first, r.count));
     out->nodes[k] = o;
+  }
+
+  // ---- collapse to 4-wide nodes: open the inner child with the largest surface area until four slots are used
+  struct Item { int32_t bnode; int32_t wide; int depth; };
+  std::vector<Item> todo{{root, 0, 1}};
+  out->nodes4.push_back(empty4);
+  while (!todo.empty()) {
+    const Item it = todo.back(); todo.pop_back();
+    out->max_depth4 = std::max(out->max_depth4, it.depth);
+    int32_t slots[4]; int ns = 0;
+    slots[ns++] = B.nodes[it.bnode].left; slots[ns++] = B.nodes[it.bnode].right;
+    while (ns < 4) {
+      int best = -1; float best_area = -1.f;
+      for (int k = 0; k < ns; k++) {
+        const BNode &c = B.nodes[slots[k]];
+        if (c.left < 0) continue;
+        const float ar = box_area(c.box);
+        if (ar > best_area) { best_area = ar; best = k; }
+      }
+      if (best < 0) break;
+      const BNode c = B.nodes[slots[best]];
+      slots[best] = c.left; slots[ns++] = c.right;
+    }
+    Node128 w = empty4;
+    for (int k = 0; k < ns; k++) {
+      const BNode &c = B.nodes[slots[k]];
+      w.lox[k] = c.box.lo[0]; w.hix[k] = c.box.hi[0]; w.loy[k] = c.box.lo[1]; w.hiy[k] = c.box.hi[1]; w.loz[k] = c.box.lo[2]; w.hiz[k] = c.box.hi[2];
+      if (c.left < 0) w.c[k] = leaf_ref(c.first, c.count);
+      else {
+        w.c[k] = (int32_t)out->nodes4.size();
+        out->nodes4.push_back(empty4);
+        todo.push_back({slots[k], w.c[k], it.depth + 1});
+      }
+    }
+    out->nodes4[it.wide] = w;
   }
 }
 

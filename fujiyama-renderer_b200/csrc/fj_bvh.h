@@ -28,6 +28,17 @@ struct Node64 {
 };
 static_assert(sizeof(Node64) == 64, "node must be 64 bytes");
 
+// 4-wide node of the wavefront's closest-hit kernel (128 B = one cache line, fetched as 8 x 16-B loads by one lane):
+// child boxes SoA (lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4]), then the four child references in the
+// encoding above.  Unused slots hold a box that is never hit (lo = +3e38, hi = -3e38).  Built by collapsing the
+// binary tree (the child with the largest surface area is opened first).
+struct Node128 {
+  float lox[4], hix[4], loy[4], hiy[4], loz[4], hiz[4];
+  int32_t c[4];
+  int32_t pad[4];
+};
+static_assert(sizeof(Node128) == 128, "wide node must be 128 bytes");
+
 struct Aabb {
   float lo[3], hi[3];
 };
@@ -38,6 +49,8 @@ struct BuildResult {
   int32_t top_count = 0;
   int32_t max_depth = 0;
   Aabb bounds;
+  std::vector<Node128> nodes4;   // the same tree collapsed to 4-wide nodes, DFS preorder, nodes4[0] is the root
+  int32_t max_depth4 = 0;
 };
 
 // Builds a binned-SAH BVH2 over `n` primitive boxes.  max_leaf <= 8.  `top_levels` BFS levels are laid

@@ -16,7 +16,8 @@
 #include <float.h>
 
 #define FJ_MAX_SHADING_GROUPS 8
-#define FJ_STACK 64              // traversal stack entries (BLAS depth + TLAS depth + 1 sentinel)
+#define FJ_STACK 64              // binary-tree traversal stack entries (BLAS depth + TLAS depth + 1 sentinel)
+#define FJ_STACK4 96             // 4-wide traversal: up to 3 pushes per level
 #define FJ_PENDING 32            // megakernel: pending secondary rays per path (DFS of the reflect/refract/diffuse tree)
 #define FJ_REAL_MAX DBL_MAX
 
@@ -67,6 +68,7 @@ struct DMesh {
   int32_t log2_tris;        // ceil(log2(triangle count)): root-to-leaf path length of the algorithmic-bytes model
   float bmag;               // max |coordinate| of the mesh bounds: scales the FP32 slab-test error bound (extend kernel)
   float pad1;
+  const float4 *nodes4;     // the same tree as 4-wide 128-B nodes (fj_bvh.h Node128) for the wavefront's k_extend
 };
 struct DInstance {
   double inv[12];           // rows 0..2 of MatInverse(matrix): world -> object (fj_object_instance.cc:222-225)
@@ -75,7 +77,7 @@ struct DInstance {
   int32_t shader_of_group[FJ_MAX_SHADING_GROUPS];
   int32_t reflect_target, refract_target, shadow_target;
 };
-struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; };   // TLAS leaf (first,count) -> order[first..] = instance indices
+struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; };   // TLAS leaf (first,count) -> order[first..] = instance indices
 struct DShader {
   int32_t kind, do_reflect, do_color_filter, pad;
   float diffuse[3], reflect[3], refract[3], emission[3], transmit[3];

@@ -30,11 +30,11 @@ struct DevBuf {
 };
 
 struct MeshRec {
-  DevBuf nodes, tri, N, idx, group;
+  DevBuf nodes, nodes4, tri, N, idx, group;
   fj::DMesh d;
   double bmin[3], bmax[3];      // exact FP64 bounds of the mesh (Mesh::ComputeBounds, fj_mesh.cc:235-244)
-  int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0;
-  void release() { nodes.release(); tri.release(); N.release(); idx.release(); group.release(); }
+  int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0, max_depth4 = 0, nnodes4 = 0;
+  void release() { nodes.release(); nodes4.release(); tri.release(); N.release(); idx.release(); group.release(); }
 };
 
 }  // namespace
@@ -58,10 +58,11 @@ struct fjgpu_context {
 
   // device scene
   DevBuf d_meshes, d_inst, d_groups, d_shaders, d_lights;
-  std::vector<DevBuf> d_group_nodes, d_group_order, d_dome;
+  std::vector<DevBuf> d_group_nodes, d_group_nodes4, d_group_order, d_dome;
   fj::DScene sc;
   std::vector<int> mesh_slot_of_id;   // dense slot per mesh id (map order)
   uint64_t tlas_nodes = 0;
+  int tlas_depth4 = 0;
   double build_seconds = 0;
 
   // frame resources
@@ -171,8 +172,10 @@ int commit_scene(fjgpu_context *ctx) {
 
   const int ngroups = (int)ctx->group_off.size() - 1;
   for (auto &b : ctx->d_group_nodes) b.release();
+  for (auto &b : ctx->d_group_nodes4) b.release();
   for (auto &b : ctx->d_group_order) b.release();
   ctx->d_group_nodes.assign(std::max(ngroups, 0), DevBuf());
+  ctx->d_group_nodes4.assign(std::max(ngroups, 0), DevBuf());
   ctx->d_group_order.assign(std::max(ngroups, 0), DevBuf());
   std::vector<fj::DGroup> dg(std::max(ngroups, 0));
   ctx->tlas_nodes = 0;
@@ -191,6 +194,9 @@ int commit_scene(fjgpu_context *ctx) {
     for (size_t k = 0; k < br.order.size(); k++) order[k] = ids[br.order[k]];
     if (int rc = dev_upload(ctx, ctx->d_group_nodes[g], br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64), true)) return rc;
     if (int rc = dev_upload(ctx, ctx->d_group_order[g], order.data(), order.size() * sizeof(int32_t), true)) return rc;
+    if (int rc = dev_upload(ctx, ctx->d_group_nodes4[g], br.nodes4.data(), br.nodes4.size() * sizeof(fjb::Node128), true)) return rc;
+    dg[g].nodes4 = (const float4 *)ctx->d_group_nodes4[g].p;
+    ctx->tlas_depth4 = std::max(ctx->tlas_depth4, br.max_depth4);
     dg[g].nodes = (const float4 *)ctx->d_group_nodes[g].p;
     dg[g].order = (const int32_t *)ctx->d_group_order[g].p;
     dg[g].ninst = (int32_t)ids.size();
@@ -343,10 +349,10 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
 void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
-  a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 8)));
-  a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 8)));
-  const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 4);
-  const int g = grid / 4 * minb;
+  a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
+  a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 12)));
+  const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 5);
+  const int g = std::max(1, (grid * minb + 3) / 4);
   if (minb >= 8) fj::k_extend<8><<<g, 128, 0, ctx->stream>>>(a);
   else if (minb >= 6) fj::k_extend<6><<<g, 128, 0, ctx->stream>>>(a);
   else if (minb == 5) fj::k_extend<5><<<g, 128, 0, ctx->stream>>>(a);
@@ -550,6 +556,7 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->meshes) kv.second.release();
   for (auto &b : ctx->d_group_nodes) b.release();
+  for (auto &b : ctx->d_group_nodes4) b.release();
   for (auto &b : ctx->d_group_order) b.release();
   for (auto &b : ctx->d_dome) b.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
@@ -591,10 +598,13 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
   fjb::BuildResult br;
   fjb::build_bvh(boxes.data(), nfaces, env_int("FJGPU_MAX_LEAF", 4), (float)env_int("FJGPU_LEAF_COST_X10", 15) / 10.f, 0, &br);
   m.nnodes = (int32_t)br.nodes.size(); m.max_depth = br.max_depth;
-  if (br.max_depth + 8 > FJ_STACK) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+  if (br.max_depth + 8 > FJ_STACK || 3 * br.max_depth4 + 16 > FJ_STACK4) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
   if (int rc = dev_upload(ctx, m.nodes, br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64), true)) return rc;
+  if (int rc = dev_upload(ctx, m.nodes4, br.nodes4.data(), br.nodes4.size() * sizeof(fjb::Node128), true)) return rc;
+  m.max_depth4 = br.max_depth4; m.nnodes4 = (int32_t)br.nodes4.size();
   memset(&m.d, 0, sizeof m.d);
   m.d.nodes = (const float4 *)m.nodes.p;
+  m.d.nodes4 = (const float4 *)m.nodes4.p;
   const size_t nt = br.order.size();
   if (f32ok) {
     std::vector<float> tri(std::max<size_t>(nt, 1) * 12, 0.f);
@@ -782,7 +792,7 @@ int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info) {
   memset(info, 0, sizeof *info);
   for (auto &kv : ctx->meshes) {
     const MeshRec &m = kv.second;
-    info->hbm_bytes += m.nodes.bytes + m.tri.bytes + m.N.bytes + m.idx.bytes + m.group.bytes;
+    info->hbm_bytes += m.nodes.bytes + m.nodes4.bytes + m.tri.bytes + m.N.bytes + m.idx.bytes + m.group.bytes;
     info->blas_nodes += m.nnodes; info->blas_tris += m.nfaces;
     info->blas_max_depth = std::max<uint32_t>(info->blas_max_depth, (uint32_t)m.max_depth);
   }
@@ -798,8 +808,9 @@ int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent) {
   CK(cudaSetDevice(ctx->device));
   if (int rc = commit_scene(ctx)) return rc;
   std::vector<DevBuf *> all = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights};
-  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.tri, &m.N, &m.idx, &m.group}) all.push_back(b); }
+  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.tri, &m.N, &m.idx, &m.group}) all.push_back(b); }
   for (auto &b : ctx->d_group_nodes) all.push_back(&b);
+  for (auto &b : ctx->d_group_nodes4) all.push_back(&b);
   for (auto &b : ctx->d_group_order) all.push_back(&b);
   uint64_t total = 0;
   for (DevBuf *b : all) {

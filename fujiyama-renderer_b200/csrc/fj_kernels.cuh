@@ -408,8 +408,9 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
   const RayRec *rays = a.queue[a.cur];
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
   const DScene &sc = a.sc;
-  int stack[FJ_STACK];
+  int stack[FJ_STACK4];
   const int SENTINEL = (int)0x80000000, DONE = (int)0x80000001;
+  const unsigned MISS = 0xffffffffu;
 
   bool active = false, drained = false;
   unsigned ridx = 0;
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
           tmin = r.tmin; tmax = r.tmax; best_t = tmax; found = false; best_prim = -1; best_inst = -1; best_u = best_v = 0;
           tn = __double2float_rd(tmin); tf = __double2float_ru(best_t);
           const DGroup grp = sc.groups[r.target];
-          tlas = grp.nodes; order = grp.order; tlas_B = grp.bmag;
+          tlas = grp.nodes4; order = grp.order; tlas_B = grp.bmag;
           nodes = tlas; in_blas = false; sp = 0; node = 0; leaf = 0;
           make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br);
           active = true;
@@ -457,25 +458,37 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
       // few lanes left descending: switch to the parked leaves / transitions if there are any to work on
       if (__popc(wm) < a.phase_a_min && __any_sync(FULL, active && (leaf != 0 || node < 0))) break;
       if (want) {
-        const float4 *np = nodes + 4 * (size_t)node;
-        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-        // child0: x,y in n0 (lo.x hi.x lo.y hi.y), z in n2.xy ; child1: x,y in n1, z in n2.zw
+        // 4-wide node: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] child[4]
+        const float4 *np = nodes + 8 * (size_t)node;
+        const float4 lx = __ldg(np), hx = __ldg(np + 1), ly = __ldg(np + 2), hy = __ldg(np + 3), lz = __ldg(np + 4), hz = __ldg(np + 5);
+        const int4 ch = __ldg((const int4 *)(np + 6));
         const bool sx = br.ix < 0.f, sy = br.iy < 0.f, sz = br.iz < 0.f;
-        const float a0 = fmaf(sx ? n0.y : n0.x, br.ix, br.nx), b0 = fmaf(sx ? n0.x : n0.y, br.ix, br.fx);
-        const float a1 = fmaf(sy ? n0.w : n0.z, br.iy, br.ny), b1 = fmaf(sy ? n0.z : n0.w, br.iy, br.fy);
-        const float a2 = fmaf(sz ? n2.y : n2.x, br.iz, br.nz), b2 = fmaf(sz ? n2.x : n2.y, br.iz, br.fz);
-        const float c0 = fmaf(sx ? n1.y : n1.x, br.ix, br.nx), d0 = fmaf(sx ? n1.x : n1.y, br.ix, br.fx);
-        const float c1 = fmaf(sy ? n1.w : n1.z, br.iy, br.ny), d1 = fmaf(sy ? n1.z : n1.w, br.iy, br.fy);
-        const float c2 = fmaf(sz ? n2.w : n2.z, br.iz, br.nz), d2 = fmaf(sz ? n2.z : n2.w, br.iz, br.fz);
-        const float near0 = fmaxf(fmaxf(a0, a1), fmaxf(a2, tn)), far0 = fminf(fminf(b0, b1), fminf(b2, tf));
-        const float near1 = fmaxf(fmaxf(c0, c1), fmaxf(c2, tn)), far1 = fminf(fminf(d0, d1), fminf(d2, tf));
-        const bool h0 = near0 <= far0, h1 = near1 <= far1;
-        const int k0 = __float_as_int(n3.x), k1 = __float_as_int(n3.y);
-        const bool swap = h1 && (!h0 || near1 < near0);          // visit child 1 first
-        const int kf = swap ? k1 : k0, ks = swap ? k0 : k1;
-        if (h0 && h1) stack[sp++] = ks;
-        if (h0 || h1) node = kf;
+        const float4 nxp = sx ? hx : lx, fxp = sx ? lx : hx, nyp = sy ? hy : ly, fyp = sy ? ly : hy, nzp = sz ? hz : lz, fzp = sz ? lz : hz;
+        unsigned key[4];
+#define FJ_CHILD(K, C)                                                                                                           \
+        {                                                                                                                          \
+          const float nr = fmaxf(fmaxf(fmaf(nxp.C, br.ix, br.nx), fmaf(nyp.C, br.iy, br.ny)), fmaxf(fmaf(nzp.C, br.iz, br.nz), tn));  \
+          const float fr_ = fminf(fminf(fmaf(fxp.C, br.ix, br.fx), fmaf(fyp.C, br.iy, br.fy)), fminf(fmaf(fzp.C, br.iz, br.fz), tf)); \
+          key[K] = nr <= fr_ ? ((__float_as_uint(nr) & ~3u) | K) : MISS;                                                           \
+        }
+        FJ_CHILD(0, x) FJ_CHILD(1, y) FJ_CHILD(2, z) FJ_CHILD(3, w)
+#undef FJ_CHILD
+        // entry distances are positive (tn > 0), so their bit patterns order like unsigned integers: sort the four keys
+        // (child slot in the two low bits, misses last) and visit front to back
+#define FJ_CSWAP(A, B) { const unsigned lo_ = min(key[A], key[B]), hi_ = max(key[A], key[B]); key[A] = lo_; key[B] = hi_; }
+        FJ_CSWAP(0, 1) FJ_CSWAP(2, 3) FJ_CSWAP(0, 2) FJ_CSWAP(1, 3) FJ_CSWAP(1, 2)
+#undef FJ_CSWAP
+#define FJ_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
+        const int nh = (key[0] != MISS) + (key[1] != MISS) + (key[2] != MISS) + (key[3] != MISS);
+        const int c1 = FJ_PICK(key[1]), c2 = FJ_PICK(key[2]), c3 = FJ_PICK(key[3]);
+        // farthest first: the hit with sorted rank i (1..nh-1) lands at stack[sp + nh-1-i]
+        if (nh > 3) stack[sp] = c3;
+        if (nh > 2) stack[sp + nh - 3] = c2;
+        if (nh > 1) stack[sp + nh - 2] = c1;
+        sp += nh > 1 ? nh - 1 : 0;
+        if (nh > 0) node = FJ_PICK(key[0]);
         else node = sp > 0 ? stack[--sp] : DONE;
+#undef FJ_PICK
         // park a triangle leaf and keep descending
         if (node < 0 && in_blas && node != SENTINEL && leaf == 0) { leaf = node; node = stack[--sp]; }     // SENTINEL is below every BLAS entry
       }
@@ -534,7 +547,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
           d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
           const DMesh &m = sc.meshes[in.mesh];
           make_box_ray32(o, d, m.bmag, br);
-          nodes = m.nodes; tri32 = m.tri32; tri64 = m.tri64;
+          nodes = m.nodes4; tri32 = m.tri32; tri64 = m.tri64;
           in_blas = true;
           stack[sp++] = SENTINEL;
           node = 0;
