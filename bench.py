@@ -224,7 +224,7 @@ def own_arm(args, builder, kw, desc):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     entry.load_package()
-    from fujiyama_renderer_b200 import fujiyama, scenes, abi
+    from fujiyama_renderer_b200 import fujiyama, scenes, abi, sharding
 
     wd = workdir()
     if rank == 0:
@@ -244,15 +244,14 @@ def own_arm(args, builder, kw, desc):
 
     try:
         s.run(text)
-        tx, ty = -(-res[0] // 32), -(-res[1] // 32)
-        ntiles = tx * ty
-        my_tiles = len(range(rank, ntiles, world))
-        max_tiles = -(-ntiles // world)
+        tiles = sharding.make_tiles(res[0], res[1], 32)
+        ntiles = len(tiles)
+        my_tiles = len(sharding.rank_tiles(tiles, rank, world))
+        max_tiles = sharding.blocks_per_rank(ntiles, world)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         blocks = gathered = None
         if world > 1:
             blocks = torch.zeros((max_tiles, 32, 32, 4), dtype=torch.float32, device="cuda")
-            gathered = torch.empty((world * max_tiles, 32, 32, 4), dtype=torch.float32, device="cuda")
             s.set_device_blocks(blocks.data_ptr(), 32, 32)
         else:
             s.set_resident(True)
@@ -260,7 +259,8 @@ def own_arm(args, builder, kw, desc):
         def step():
             st = frame()
             if world > 1:
-                dist.all_gather_into_tensor(gathered, blocks)
+                nonlocal gathered
+                gathered = sharding.all_gather_blocks(blocks, world, dist)
             return st
 
         for _ in range(max(args.warmup, 1)):
@@ -360,7 +360,7 @@ def own_arm(args, builder, kw, desc):
             for _ in range(args.steps):
                 st, _, _ = step()
                 e_rays += st.rays
-                host = gathered.cpu() if rank == 0 else None
+                host = sharding.assemble_frame(gathered.cpu().numpy(), tiles, world, res[0], res[1]) if rank == 0 else None
             torch.cuda.synchronize()
             dist.barrier()
             t_e2e = time.perf_counter() - t0

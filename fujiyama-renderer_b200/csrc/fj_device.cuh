@@ -339,7 +339,8 @@ struct RayRec {
   int32_t target;                 // object group traced
   uint8_t type, dd, rd, fd;       // ray context and the three depth counters of TraceContext (fj_shading.h:26-47)
   int32_t filter_shader;          // >= 0: refracted child whose radiance is scaled by pow(transmit, t_hit) of that shader
-  int32_t pad, pad2, pad3;
+  uint32_t key;                   // sort key of the ray (direction octant | Morton code of the origin cell), see k_shade
+  int32_t pad2, pad3;
 };
 static_assert(sizeof(RayRec) == 112, "ray record must be 112 bytes");
 struct HitRec { double t, u, v; int32_t prim, inst; };     // 32 B, inst < 0 = miss

@@ -66,7 +66,8 @@ struct fjgpu_context {
   double build_seconds = 0;
 
   // frame resources
-  DevBuf d_samples, d_tiles, d_blocks, d_jitter, d_counters, d_frame, d_queue[2], d_hits, d_ctl;
+  DevBuf d_samples, d_tiles, d_blocks, d_jitter, d_counters, d_frame, d_queue[2], d_hits, d_ctl, d_hist, d_perm;
+  float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
   std::vector<cudaEvent_t> evpool;
   size_t jitter_count = 0;
   float *h_blocks = nullptr; size_t h_blocks_bytes = 0;
@@ -169,6 +170,10 @@ int commit_scene(fjgpu_context *ctx) {
     }
   }
   if (int rc = dev_upload(ctx, ctx->d_inst, di.data(), di.size() * sizeof(fj::DInstance), true)) return rc;
+  for (int a = 0; a < 3; a++) { ctx->scene_lo[a] = 3e38f; ctx->scene_hi[a] = -3e38f; }
+  for (int i = 0; i < ninst; i++) for (int a = 0; a < 3; a++) if (ibox[i].lo[a] <= ibox[i].hi[a]) {
+    ctx->scene_lo[a] = std::min(ctx->scene_lo[a], ibox[i].lo[a]); ctx->scene_hi[a] = std::max(ctx->scene_hi[a], ibox[i].hi[a]);
+  }
 
   const int ngroups = (int)ctx->group_off.size() - 1;
   for (auto &b : ctx->d_group_nodes) b.release();
@@ -438,6 +443,17 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         if (int rc = dev_alloc(ctx, ctx->d_hits, capacity * sizeof(fj::HitRec))) return rc;
         a.queue[0] = (fj::RayRec *)ctx->d_queue[0].p; a.queue[1] = (fj::RayRec *)ctx->d_queue[1].p;
         a.hits = (fj::HitRec *)ctx->d_hits.p; a.ctl = (fj::QueueCtl *)ctx->d_ctl.p; a.capacity = (uint32_t)capacity; a.cur = 0;
+        const int sort_bits = pl.waves > 1 ? std::min(7, std::max(0, env_int("FJGPU_SORT_BITS", 0))) : 0;
+        a.hist = nullptr; a.perm = nullptr; a.sort_bits = sort_bits; a.sort_bins = 8u << (3 * sort_bits);
+        if (sort_bits > 0) {
+          if (int rc = dev_alloc(ctx, ctx->d_hist, ((size_t)a.sort_bins + 1) * 4)) return rc;
+          if (int rc = dev_alloc(ctx, ctx->d_perm, capacity * 4)) return rc;
+          a.hist = (unsigned int *)ctx->d_hist.p;
+          for (int k = 0; k < 3; k++) {
+            const float ext = ctx->scene_hi[k] - ctx->scene_lo[k];
+            a.sort_lo[k] = ctx->scene_lo[k]; a.sort_scale[k] = ext > 0 ? (float)(1 << sort_bits) / ext : 0.f;
+          }
+        }
         CK(cudaMemsetAsync(ctx->d_ctl.p, 0, sizeof(fj::QueueCtl), ctx->stream));
         cudaEvent_t s0 = pool_event(ctx, &evn), s1 = pool_event(ctx, &evn);
         CK(cudaEventRecord(s0, ctx->stream));
@@ -452,14 +468,23 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
           CK(cudaMemsetAsync((char *)ctx->d_ctl.p + offsetof(fj::QueueCtl, head), 0, 4, ctx->stream));
           CK(cudaMemsetAsync((char *)ctx->d_ctl.p + offsetof(fj::QueueCtl, count) + 4 * (a.cur ^ 1), 0, 4, ctx->stream));
           cudaEvent_t e0 = pool_event(ctx, &evn), e1 = pool_event(ctx, &evn), e2 = pool_event(ctx, &evn);
+          if (a.hist) CK(cudaMemsetAsync(a.hist, 0, ((size_t)a.sort_bins + 1) * 4, ctx->stream));
           CK(cudaEventRecord(e0, ctx->stream));
           launch_extend(ctx, a, grid);
           CK(cudaGetLastError());
           CK(cudaEventRecord(e1, ctx->stream));
           fj::k_shade<float><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a);
           CK(cudaGetLastError());
-          CK(cudaEventRecord(e2, ctx->stream));
           launches += 2;
+          if (a.hist && w + 1 < pl.waves) {       // order the next queue for the next extend
+            fj::RenderArgs n = a; n.cur = a.cur ^ 1; n.perm = (unsigned int *)ctx->d_perm.p;
+            fj::k_sort_scan<<<1, 1024, 0, ctx->stream>>>(a.hist, a.sort_bins);
+            fj::k_sort_scatter<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(n);
+            CK(cudaGetLastError());
+            launches += 2;
+            a.perm = n.perm;
+          }
+          CK(cudaEventRecord(e2, ctx->stream));
           ev_extend.push_back(e0); ev_extend.push_back(e1); ev_shade.push_back(e1); ev_shade.push_back(e2);
           a.cur ^= 1;
         }
@@ -560,7 +585,7 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &b : ctx->d_group_order) b.release();
   for (auto &b : ctx->d_dome) b.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
-                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl};
+                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl, &ctx->d_hist, &ctx->d_perm};
   for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
   for (DevBuf *b : all) b->release();
   if (ctx->h_blocks) cudaFreeHost(ctx->h_blocks);

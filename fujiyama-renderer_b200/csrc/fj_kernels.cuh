@@ -177,7 +177,7 @@ struct Shading {
     float Os = 1.f;
     const int kind = slot < 0 ? 0 : sc.shaders[slot].kind;
     RayRec c;
-    c.o[0] = P.x; c.o[1] = P.y; c.o[2] = P.z; c.tmax = 1000.; c.slot = cur.slot; c.pad = 0; c.filter_shader = -1;
+    c.o[0] = P.x; c.o[1] = P.y; c.o[2] = P.z; c.tmax = 1000.; c.slot = cur.slot; c.key = 0; c.pad2 = c.pad3 = 0; c.filter_shader = -1;
     c.dd = cur.dd; c.rd = cur.rd; c.fd = cur.fd;
     if (kind == 0) {                                               // NO_SHADER_COLOR, fj_shading.cc:26,555-560
       sink.add(fmul(thr.r, .5f), thr.g, 0.f);
@@ -261,6 +261,10 @@ struct RenderArgs {
   unsigned long long *work;               // megakernel: global work counter (units of 32 slots)
   RayRec *queue[2]; HitRec *hits; QueueCtl *ctl; uint32_t capacity; int cur;     // wavefront
   int refill, phase_a_min;                // k_extend scheduling thresholds (lanes)
+  // ray sorting between bounces: counting sort of the next queue by (direction octant | origin cell)
+  unsigned int *hist;                     // sort_bins + 1 counters (null = no sorting)
+  unsigned int *perm;                     // order in which k_extend walks queue[cur] (null = queue order)
+  float sort_lo[3], sort_scale[3]; int sort_bits; unsigned int sort_bins;
 };
 
 __device__ __forceinline__ void flush_counters(const ShadeCounters &c, unsigned long long nsamp, DCounters *out, int lane) {
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(128) k_render_samples(const RenderArgs a) {
       RayRec cur;
       cur.o[0] = ray.o.x; cur.o[1] = ray.o.y; cur.o[2] = ray.o.z; cur.d[0] = ray.d.x; cur.d[1] = ray.d.y; cur.d[2] = ray.d.z;
       cur.tmin = ray.tmin; cur.tmax = ray.tmax; cur.thr[0] = cur.thr[1] = cur.thr[2] = 1.f; cur.slot = 0; cur.node = 1;
-      cur.target = a.fr.target_group; cur.type = RAY_CAMERA; cur.dd = cur.rd = cur.fd = 0; cur.filter_shader = -1; cur.pad = 0;
+      cur.target = a.fr.target_group; cur.type = RAY_CAMERA; cur.dd = cur.rd = cur.fd = 0; cur.filter_shader = -1; cur.key = 0; cur.pad2 = cur.pad3 = 0;
       sink.spawn(cur);
       while (sink.sp > 0) {
         cur = stack[--sink.sp];
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(256) k_generate(const RenderArgs a) {
         RayD ray; camera_ray(a.cam, u, v, &ray);
         r.o[0] = ray.o.x; r.o[1] = ray.o.y; r.o[2] = ray.o.z; r.d[0] = ray.d.x; r.d[1] = ray.d.y; r.d[2] = ray.d.z;
         r.tmin = ray.tmin; r.tmax = ray.tmax; r.thr[0] = r.thr[1] = r.thr[2] = 1.f; r.slot = (uint32_t)w; r.node = 1;
-        r.target = a.fr.target_group; r.type = RAY_CAMERA; r.dd = r.rd = r.fd = 0; r.filter_shader = -1; r.pad = 0;
+        r.target = a.fr.target_group; r.type = RAY_CAMERA; r.dd = r.rd = r.fd = 0; r.filter_shader = -1; r.key = 0; r.pad2 = r.pad3 = 0;
         valid = true; nsamp++;
       }
     }
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
   bool active = false, drained = false;
   unsigned ridx = 0;
   int sp = 0, node = DONE, leaf = 0, cur_inst = -1, best_prim = -1, best_inst = -1;
-  bool in_blas = false, found = false;
+  bool in_blas = false, found = false, br_world = false;
   double tmin = 0, tmax = 0, best_t = 0, best_u = 0, best_v = 0;
   float tn = 0, tf = 0;
   D3 o = mk(0, 0, 0), d = mk(0, 0, 0);          // object-space ray while inside a BLAS
@@ -436,14 +440,15 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
       if (!active) {
         const unsigned i = base + __popc(idle & ((1u << lane) - 1));
         if (i < count) {
-          ridx = i;
-          const RayRec &r = rays[i];
+          ridx = a.perm ? a.perm[i] : i;
+          const RayRec &r = rays[ridx];
           tmin = r.tmin; tmax = r.tmax; best_t = tmax; found = false; best_prim = -1; best_inst = -1; best_u = best_v = 0;
           tn = __double2float_rd(tmin); tf = __double2float_ru(best_t);
           const DGroup grp = sc.groups[r.target];
           tlas = grp.nodes4; order = grp.order; tlas_B = grp.bmag;
           nodes = tlas; in_blas = false; sp = 0; node = 0; leaf = 0;
           make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br);
+          br_world = true;
           active = true;
         }
       }
@@ -458,6 +463,11 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
       // few lanes left descending: switch to the parked leaves / transitions if there are any to work on
       if (__popc(wm) < a.phase_a_min && __any_sync(FULL, active && (leaf != 0 || node < 0))) break;
       if (want) {
+        if (!in_blas && !br_world) {             // back in the instance tree after a BLAS: rebuild the world-space box ray
+          const RayRec &r = rays[ridx];
+          make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br);
+          br_world = true;
+        }
         // 4-wide node: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] child[4]
         const float4 *np = nodes + 8 * (size_t)node;
         const float4 lx = __ldg(np), hx = __ldg(np + 1), ly = __ldg(np + 2), hy = __ldg(np + 3), lz = __ldg(np + 4), hz = __ldg(np + 5);
@@ -529,10 +539,8 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
           HitRec hr; hr.t = found ? best_t : FJ_REAL_MAX; hr.u = best_u; hr.v = best_v; hr.prim = best_prim; hr.inst = found ? best_inst : -1;
           a.hits[ridx] = hr;
           active = false;
-        } else if (node == SENTINEL) {             // the instance's BLAS is done: back to world space
-          const RayRec &r = rays[ridx];
-          make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br);
-          in_blas = false; nodes = tlas;
+        } else if (node == SENTINEL) {             // the instance's BLAS is done: back to the instance tree (its box ray is
+          in_blas = false; nodes = tlas; br_world = false;      // rebuilt only if an inner node of that tree is still to be visited)
           node = sp > 0 ? stack[--sp] : DONE;
         } else if (in_blas) {                      // a second triangle leaf: park it now that the slot is free
           leaf = node; node = stack[--sp];
@@ -547,6 +555,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
           d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
           const DMesh &m = sc.meshes[in.mesh];
           make_box_ray32(o, d, m.bmag, br);
+          br_world = false;
           nodes = m.nodes4; tri32 = m.tri32; tri64 = m.tri64;
           in_blas = true;
           stack[sp++] = SENTINEL;
@@ -571,9 +580,48 @@ struct QueueSink {
     if (lane == leader) base = atomicAdd(&a.ctl->count[a.cur ^ 1], (unsigned)__popc(m));
     base = __shfl_sync(m, base, leader);
     const unsigned i = base + __popc(m & ((1u << lane) - 1));
-    if (i < a.capacity) next[i] = c; else a.ctl->overflow = 1;
+    if (i < a.capacity) {
+      next[i] = c;
+      if (a.hist) {       // sort key: rays leaving the same cell of the scene in the same octant walk the same part of the BVH
+        const unsigned cells = (1u << a.sort_bits) - 1u;
+        const unsigned cx = min((unsigned)fmaxf(((float)c.o[0] - a.sort_lo[0]) * a.sort_scale[0], 0.f), cells);
+        const unsigned cy = min((unsigned)fmaxf(((float)c.o[1] - a.sort_lo[1]) * a.sort_scale[1], 0.f), cells);
+        const unsigned cz = min((unsigned)fmaxf(((float)c.o[2] - a.sort_lo[2]) * a.sort_scale[2], 0.f), cells);
+        unsigned mort = 0;
+        for (int b = 0; b < a.sort_bits; b++) mort |= (((cx >> b) & 1u) << (3 * b)) | (((cy >> b) & 1u) << (3 * b + 1)) | (((cz >> b) & 1u) << (3 * b + 2));
+        const unsigned oct = (c.d[0] < 0. ? 1u : 0u) | (c.d[1] < 0. ? 2u : 0u) | (c.d[2] < 0. ? 4u : 0u);
+        const unsigned key = (oct << (3 * a.sort_bits)) | mort;
+        next[i].key = key;
+        atomicAdd(&a.hist[key], 1u);
+      }
+    } else a.ctl->overflow = 1;
   }
 };
+
+// Counting sort of queue[cur] by RayRec::key: exclusive scan of the histogram k_shade filled, then one pass that hands
+// every ray a position inside its bin (order inside a bin is arbitrary and does not influence any result).
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned int *hist, unsigned int bins) {
+  __shared__ unsigned int part[1024];
+  const unsigned per = (bins + 1023) / 1024, b0 = threadIdx.x * per;
+  unsigned sum = 0;
+  for (unsigned k = 0; k < per && b0 + k < bins; k++) sum += hist[b0 + k];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const unsigned v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned run = part[threadIdx.x] - sum;
+  for (unsigned k = 0; k < per && b0 + k < bins; k++) { const unsigned c = hist[b0 + k]; hist[b0 + k] = run; run += c; }
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(const RenderArgs a) {
+  const unsigned count = min(a.ctl->count[a.cur], a.capacity);
+  const RayRec *q = a.queue[a.cur];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    a.perm[atomicAdd(&a.hist[q[i].key], 1u)] = i;
+}
 
 // One thread per traced ray of queue[cur]: shader evaluation, radiance into the sample accumulators, secondary rays
 // compacted into queue[cur ^ 1] by warp ballot (Shader::Evaluate + the Sl*Context/SlTrace calls the plugins make).
