@@ -408,6 +408,8 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(fj::DCounters) + 64, ctx->stream));
 
   const int grid = ctx->sm_count * env_int("FJGPU_BLOCKS_PER_SM", 4);
+  bool has_plastic = false;
+  for (const fjgpu_shader &sdr : ctx->shaders) has_plastic = has_plastic || sdr.kind == FJGPU_SHADER_PLASTIC;
   uint64_t launches = 0;
   size_t evn = 0;
   std::vector<cudaEvent_t> ev_extend, ev_shade, ev_resolve;     // (start, stop) pairs read after the final sync
@@ -473,7 +475,8 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
           launch_extend(ctx, a, grid);
           CK(cudaGetLastError());
           CK(cudaEventRecord(e1, ctx->stream));
-          fj::k_shade<float><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a);
+          if (has_plastic) fj::k_shade<float, true><<<ctx->sm_count * 6, 128, 0, ctx->stream>>>(a);
+          else fj::k_shade<float, false><<<ctx->sm_count * 10, 128, 0, ctx->stream>>>(a);
           CK(cudaGetLastError());
           launches += 2;
           if (a.hist && w + 1 < pl.waves) {       // order the next queue for the next extend

@@ -86,7 +86,7 @@ struct ShadeCounters { unsigned int rays[5]; unsigned int hits, levels; };
 // secondary rays it spawns to `sink.spawn` (SlTrace -> trace_surface -> Shader::evaluate, src/fj_shading.cc:140-179,
 // 527-572).  Shadow rays are traced inline (SlIlluminance needs the occluder's opacity before the light sample is
 // weighted).  Sink: add(r,g,b) in float, alpha(a) for camera rays, spawn(const RayRec&).
-template <typename T>
+template <typename T, bool PLASTIC = true>
 struct Shading {
   const DScene &sc; const DFrame &fr; PathKey key; ShadeCounters &cnt;
   __device__ Shading(const DScene &s, const DFrame &f, PathKey k, ShadeCounters &c) : sc(s), fr(f), key(k), cnt(c) {}
@@ -184,7 +184,7 @@ struct Shading {
     } else if (kind == 1) {                                        // ConstantShader::evaluate, constant_shader.cc:72-94
       const DShader &sh = sc.shaders[slot];
       sink.add(fmul(thr.r, sh.diffuse[0]), fmul(thr.g, sh.diffuse[1]), fmul(thr.b, sh.diffuse[2]));
-    } else if (kind == 2) {                                        // PlasticShader::evaluate, plastic_shader.cc:101-179
+    } else if (PLASTIC && kind == 2) {                             // PlasticShader::evaluate, plastic_shader.cc:101-179
       const DShader &sh = sc.shaders[slot];
       const D3 Nf = sl_faceforward(ray.d, N);
       const C3 diff = gather_lights(P, Nf, h.inst, cur.node);
@@ -625,8 +625,10 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const RenderArgs a) {
 
 // One thread per traced ray of queue[cur]: shader evaluation, radiance into the sample accumulators, secondary rays
 // compacted into queue[cur ^ 1] by warp ballot (Shader::Evaluate + the Sl*Context/SlTrace calls the plugins make).
-template <typename T>
-__global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
+// PLASTIC = false drops the light loop and its inline shadow-ray traversal from the kernel (scenes without a plastic
+// shader): fewer registers, more resident warps.
+template <typename T, bool PLASTIC>
+__global__ void __launch_bounds__(128, PLASTIC ? 3 : 5) k_shade(const RenderArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
   const RayRec *rays = a.queue[a.cur];
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
     int ti, x, y; TileGrid g;
     slot_decode(a.fr, a.tiles, a.wstride, cur.slot, &ti, &g, &x, &y);
     PathKey key; key.seed = a.fr.seed; key.tile = (uint32_t)a.tiles[ti].id; key.sample = (uint32_t)(y * g.nsx + x);
-    Shading<T> sh(a.sc, a.fr, key, cnt);
+    Shading<T, PLASTIC> sh(a.sc, a.fr, key, cnt);
     QueueSink sink{a, a.queue[a.cur ^ 1], lane, 0, 0, 0, false, 0.f};
     Hit h; h.t = hr.t; h.u = hr.u; h.v = hr.v; h.prim = hr.prim; h.inst = hr.inst;
     sh.shade(cur, h, sink);
