@@ -283,7 +283,7 @@ def own_arm(args, builder, kw, desc):
             st, info, _ = step()
             flush.zero_()                   # L2 flush between timed iterations (256 MiB > 126 MB L2)
             for f, _t in abi.Stats._fields_:
-                if f.startswith("rays_") or f in ("camera_samples", "hit_mesh_levels"):
+                if f.startswith("rays_") or f in ("camera_samples", "hit_mesh_levels", "node_steps", "tri_tests"):
                     setattr(tot, f, getattr(tot, f) + getattr(st, f))
             ms_trace += st.ms_trace
             ms_resolve += st.ms_resolve
@@ -387,7 +387,8 @@ def own_arm(args, builder, kw, desc):
                           "parallelism": "tiles round-robin over %d rank(s)%s" % (world, ", NCCL all_gather of tile blocks" if world > 1 else ""),
                           "rays_per_frame": total_rays / args.steps, "camera_samples_per_frame": total_samples / args.steps,
                           "scene_hbm_bytes": int(info.hbm_bytes), "bvh_build_s": info.build_seconds, "scene_upload_s": upload_s,
-                          "blas_nodes": int(info.blas_nodes), "blas_max_depth": int(info.blas_max_depth)},
+                          "blas_nodes": int(info.blas_nodes), "blas_max_depth": int(info.blas_max_depth),
+                          "node_steps_per_ray": tot.node_steps / max(tot.rays, 1), "tri_tests_per_ray": tot.tri_tests / max(tot.rays, 1)},
                "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": total_launches, "clocks": clk,
                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
                "kernel_ms_per_step": {"k_extend": ms_trace / args.steps, "k_generate+k_shade": ms_shade / args.steps,
@@ -408,6 +409,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     builder, kw, desc = WORKLOADS[args.workload]
+    if os.environ.get("FJ_BENCH_N"):          # experiment knob: mesh resolution of the blob (not used by the driver)
+        kw = dict(kw, n=int(os.environ["FJ_BENCH_N"]))
+        desc += " [n=%d]" % kw["n"]
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return

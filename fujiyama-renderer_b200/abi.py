@@ -67,6 +67,7 @@ class Stats(C.Structure):
                 ("rays_diffuse", C.c_uint64), ("rays_reflect", C.c_uint64),
                 ("rays_refract", C.c_uint64), ("camera_samples", C.c_uint64),
                 ("rays_hit", C.c_uint64), ("hit_mesh_levels", C.c_uint64),
+                ("node_steps", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("trace_launches", C.c_uint64),
                 ("ms_trace", C.c_float), ("ms_resolve", C.c_float),
                 ("ms_total", C.c_float), ("ms_shade", C.c_float)]

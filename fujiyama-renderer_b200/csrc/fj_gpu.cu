@@ -356,6 +356,7 @@ enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY =
 void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
   a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
   a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 12)));
+  a.park = env_int("FJGPU_PARK", 1);
   const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 5);
   const int g = std::max(1, (grid * minb + 3) / 4);
   if (minb >= 8) fj::k_extend<8><<<g, 128, 0, ctx->stream>>>(a);
@@ -535,7 +536,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
     float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[3]);
     stats->rays_camera = hc.rays[0]; stats->rays_shadow = hc.rays[1]; stats->rays_diffuse = hc.rays[2];
     stats->rays_reflect = hc.rays[3]; stats->rays_refract = hc.rays[4]; stats->camera_samples = hc.samples;
-    stats->rays_hit = hc.hits; stats->hit_mesh_levels = hc.levels;
+    stats->rays_hit = hc.hits; stats->hit_mesh_levels = hc.levels; stats->node_steps = hc.node_steps; stats->tri_tests = hc.tri_tests;
     float ms_trace = 0, ms_shade = 0, ms_resolve = 0, t = 0;
     for (size_t i = 0; i + 1 < ev_extend.size(); i += 2) { cudaEventElapsedTime(&t, ev_extend[i], ev_extend[i + 1]); ms_trace += t; }
     for (size_t i = 0; i + 1 < ev_shade.size(); i += 2) { cudaEventElapsedTime(&t, ev_shade[i], ev_shade[i + 1]); ms_shade += t; }

@@ -16,6 +16,28 @@
 
 namespace fj {
 
+// ------------------------------------------------------------------------------------------ streaming access
+// Ray / hit records and accumulators are touched once per round and are far larger than L2; the BVH is re-read by every
+// ray and almost fits in L2.  Stream the former with evict-first hints so they do not push the latter out.
+__device__ __forceinline__ void store_ray_cs(RayRec *dst, const RayRec &r) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(&r); uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+  for (int k = 0; k < 7; k++) __stcs(d + k, s[k]);
+}
+__device__ __forceinline__ void load_ray_cs(RayRec *dst, const RayRec *src) {
+  uint4 *d = reinterpret_cast<uint4 *>(dst); const uint4 *s = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+  for (int k = 0; k < 7; k++) d[k] = __ldcs(s + k);
+}
+__device__ __forceinline__ void store_hit_cs(HitRec *dst, const HitRec &h) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(&h); uint4 *d = reinterpret_cast<uint4 *>(dst);
+  __stcs(d, s[0]); __stcs(d + 1, s[1]);
+}
+__device__ __forceinline__ void load_hit_cs(HitRec *dst, const HitRec *src) {
+  uint4 *d = reinterpret_cast<uint4 *>(dst); const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  d[0] = __ldcs(s); d[1] = __ldcs(s + 1);
+}
+
 // ------------------------------------------------------------------------------------------ sampler
 // Tile sample grid, FixedGridSampler::generate_samples (src/fj_fixed_grid_sampler.cc:33-84).
 struct TileGrid { int nsx, nsy, xoff, yoff, nbx, nby; };
@@ -260,7 +282,7 @@ struct RenderArgs {
   DCounters *counters;
   unsigned long long *work;               // megakernel: global work counter (units of 32 slots)
   RayRec *queue[2]; HitRec *hits; QueueCtl *ctl; uint32_t capacity; int cur;     // wavefront
-  int refill, phase_a_min;                // k_extend scheduling thresholds (lanes)
+  int refill, phase_a_min, park;          // k_extend scheduling: refill / phase-A thresholds (lanes), speculative leaf parking
   // ray sorting between bounces: counting sort of the next queue by (direction octant | origin cell)
   unsigned int *hist;                     // sort_bins + 1 counters (null = no sorting)
   unsigned int *perm;                     // order in which k_extend walks queue[cur] (null = queue order)
@@ -365,7 +387,7 @@ __global__ void __launch_bounds__(256) k_generate(const RenderArgs a) {
       base = __shfl_sync(0xffffffffu, base, leader);
       if (valid) {
         const unsigned i = base + __popc(m & ((1u << lane) - 1));
-        if (i < a.capacity) q[i] = r; else a.ctl->overflow = 1;
+        if (i < a.capacity) store_ray_cs(q + i, r); else a.ctl->overflow = 1;
       }
     }
   }
@@ -384,6 +406,7 @@ __global__ void __launch_bounds__(256) k_generate(const RenderArgs a) {
 //   fma for planes with |plane| <= B (B = bound magnitude of the space being traversed), so a box the exact FP64 ray
 //   touches within [tmin, best_t] is never culled.  Triangles are then tested in exact FP64 (tri_intersect).
 struct BoxRay32 { float ix, iy, iz, nx, ny, nz, fx, fy, fz; };
+__device__ __forceinline__ int box_octant(const BoxRay32 &r) { return (r.ix < 0.f ? 1 : 0) | (r.iy < 0.f ? 2 : 0) | (r.iz < 0.f ? 4 : 0); }
 __device__ __forceinline__ void box_axis(double o, double d, float B, float *inv, float *cn, float *cf) {
   float df = (float)d;
   if (!(fabsf(df) >= 1e-18f)) df = (df < 0.f || (df == 0.f && signbit(df))) ? -1e-18f : 1e-18f;
@@ -417,13 +440,14 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
   const unsigned MISS = 0xffffffffu;
 
   bool active = false, drained = false;
-  unsigned ridx = 0;
+  unsigned ridx = 0, n_steps = 0, n_tris = 0;
   int sp = 0, node = DONE, leaf = 0, cur_inst = -1, best_prim = -1, best_inst = -1;
   bool in_blas = false, found = false, br_world = false;
   double tmin = 0, tmax = 0, best_t = 0, best_u = 0, best_v = 0;
   float tn = 0, tf = 0;
   D3 o = mk(0, 0, 0), d = mk(0, 0, 0);          // object-space ray while inside a BLAS
   BoxRay32 br; br.ix = br.iy = br.iz = br.nx = br.ny = br.nz = br.fx = br.fy = br.fz = 0.f;
+  int oct = 0;                                  // direction signs of the current box ray (bit a: 1/d[a] < 0)
   const float4 *nodes = nullptr, *tlas = nullptr; const int32_t *order = nullptr; float tlas_B = 0;
   const float4 *tri32 = nullptr; const double *tri64 = nullptr;
 
@@ -447,7 +471,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
           const DGroup grp = sc.groups[r.target];
           tlas = grp.nodes4; order = grp.order; tlas_B = grp.bmag;
           nodes = tlas; in_blas = false; sp = 0; node = 0; leaf = 0;
-          make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br);
+          make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br); oct = box_octant(br);
           br_world = true;
           active = true;
         }
@@ -457,7 +481,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
 
     // ---- phase A: inner nodes (both children, nearer first)
     for (;;) {
-      const bool want = active && node >= 0;
+      const bool want = active && node >= 0 && (a.park || leaf == 0);
       const unsigned wm = __ballot_sync(FULL, want);
       if (wm == 0) break;
       // few lanes left descending: switch to the parked leaves / transitions if there are any to work on
@@ -465,42 +489,38 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
       if (want) {
         if (!in_blas && !br_world) {             // back in the instance tree after a BLAS: rebuild the world-space box ray
           const RayRec &r = rays[ridx];
-          make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br);
+          make_box_ray32(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), tlas_B, br); oct = box_octant(br);
           br_world = true;
         }
-        // 4-wide node: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] child[4]
+        // 4-wide node: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] child[4].  The near / far plane of every axis is
+        // picked by ADDRESS from the ray's direction signs (oct bit a set: hi is the near plane of axis a), not by selects.
         const float4 *np = nodes + 8 * (size_t)node;
-        const float4 lx = __ldg(np), hx = __ldg(np + 1), ly = __ldg(np + 2), hy = __ldg(np + 3), lz = __ldg(np + 4), hz = __ldg(np + 5);
+        const int ox_ = oct & 1, oy_ = (oct >> 1) & 1, oz_ = (oct >> 2) & 1;
+        const float4 nxp = __ldg(np + ox_), fxp = __ldg(np + (ox_ ^ 1)), nyp = __ldg(np + 2 + oy_), fyp = __ldg(np + 2 + (oy_ ^ 1));
+        const float4 nzp = __ldg(np + 4 + oz_), fzp = __ldg(np + 4 + (oz_ ^ 1));
         const int4 ch = __ldg((const int4 *)(np + 6));
-        const bool sx = br.ix < 0.f, sy = br.iy < 0.f, sz = br.iz < 0.f;
-        const float4 nxp = sx ? hx : lx, fxp = sx ? lx : hx, nyp = sy ? hy : ly, fyp = sy ? ly : hy, nzp = sz ? hz : lz, fzp = sz ? lz : hz;
-        unsigned key[4];
-#define FJ_CHILD(K, C)                                                                                                           \
+        unsigned key0, key1, key2, key3;
+#define FJ_CHILD(KEY, K, C)                                                                                                     \
         {                                                                                                                          \
           const float nr = fmaxf(fmaxf(fmaf(nxp.C, br.ix, br.nx), fmaf(nyp.C, br.iy, br.ny)), fmaxf(fmaf(nzp.C, br.iz, br.nz), tn));  \
           const float fr_ = fminf(fminf(fmaf(fxp.C, br.ix, br.fx), fmaf(fyp.C, br.iy, br.fy)), fminf(fmaf(fzp.C, br.iz, br.fz), tf)); \
-          key[K] = nr <= fr_ ? ((__float_as_uint(nr) & ~3u) | K) : MISS;                                                           \
+          KEY = nr <= fr_ ? ((__float_as_uint(nr) & ~3u) | K) : MISS;                                                              \
         }
-        FJ_CHILD(0, x) FJ_CHILD(1, y) FJ_CHILD(2, z) FJ_CHILD(3, w)
+        FJ_CHILD(key0, 0u, x) FJ_CHILD(key1, 1u, y) FJ_CHILD(key2, 2u, z) FJ_CHILD(key3, 3u, w)
 #undef FJ_CHILD
-        // entry distances are positive (tn > 0), so their bit patterns order like unsigned integers: sort the four keys
-        // (child slot in the two low bits, misses last) and visit front to back
-#define FJ_CSWAP(A, B) { const unsigned lo_ = min(key[A], key[B]), hi_ = max(key[A], key[B]); key[A] = lo_; key[B] = hi_; }
-        FJ_CSWAP(0, 1) FJ_CSWAP(2, 3) FJ_CSWAP(0, 2) FJ_CSWAP(1, 3) FJ_CSWAP(1, 2)
-#undef FJ_CSWAP
-#define FJ_PICK(KEY) (((KEY) & 2u) ? (((KEY) & 1u) ? ch.w : ch.z) : (((KEY) & 1u) ? ch.y : ch.x))
-        const int nh = (key[0] != MISS) + (key[1] != MISS) + (key[2] != MISS) + (key[3] != MISS);
-        const int c1 = FJ_PICK(key[1]), c2 = FJ_PICK(key[2]), c3 = FJ_PICK(key[3]);
-        // farthest first: the hit with sorted rank i (1..nh-1) lands at stack[sp + nh-1-i]
-        if (nh > 3) stack[sp] = c3;
-        if (nh > 2) stack[sp + nh - 3] = c2;
-        if (nh > 1) stack[sp + nh - 2] = c1;
-        sp += nh > 1 ? nh - 1 : 0;
-        if (nh > 0) node = FJ_PICK(key[0]);
-        else node = sp > 0 ? stack[--sp] : DONE;
-#undef FJ_PICK
-        // park a triangle leaf and keep descending
-        if (node < 0 && in_blas && node != SENTINEL && leaf == 0) { leaf = node; node = stack[--sp]; }     // SENTINEL is below every BLAS entry
+        // entry distances are positive (tn > 0), so their bit patterns order like unsigned integers.  The nearest hit child
+        // is visited next; the other hit children are pushed (exact front-to-back order for up to two hits, slot order beyond)
+        const unsigned kmin = min(min(key0, key1), min(key2, key3));
+        if (kmin != MISS) {
+          const unsigned w = kmin & 3u;
+          if (key0 != MISS && w != 0u) stack[sp++] = ch.x;
+          if (key1 != MISS && w != 1u) stack[sp++] = ch.y;
+          if (key2 != MISS && w != 2u) stack[sp++] = ch.z;
+          if (key3 != MISS && w != 3u) stack[sp++] = ch.w;
+          node = (w & 2u) ? ((w & 1u) ? ch.w : ch.z) : ((w & 1u) ? ch.y : ch.x);
+        } else node = sp > 0 ? stack[--sp] : DONE;
+        n_steps++;
+        if (a.park && node < 0 && in_blas && node != SENTINEL && leaf == 0) { leaf = node; node = stack[--sp]; }     // SENTINEL is below every BLAS entry
       }
     }
 
@@ -512,6 +532,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
         const bool want = k < cnt;
         if (!__any_sync(FULL, want)) break;
         if (want) {
+          n_tris++;
           D3 v0, v1, v2; int prim;
           if (tri32) {
             const float4 *tp = tri32 + 3 * (size_t)(first + k);
@@ -537,7 +558,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
       if (special) {
         if (node == DONE) {                        // traversal finished: write the hit record
           HitRec hr; hr.t = found ? best_t : FJ_REAL_MAX; hr.u = best_u; hr.v = best_v; hr.prim = best_prim; hr.inst = found ? best_inst : -1;
-          a.hits[ridx] = hr;
+          store_hit_cs(a.hits + ridx, hr);
           active = false;
         } else if (node == SENTINEL) {             // the instance's BLAS is done: back to the instance tree (its box ray is
           in_blas = false; nodes = tlas; br_world = false;      // rebuilt only if an inner node of that tree is still to be visited)
@@ -554,7 +575,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
           o = mat_point(in.inv, mk(r.o[0], r.o[1], r.o[2]));
           d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
           const DMesh &m = sc.meshes[in.mesh];
-          make_box_ray32(o, d, m.bmag, br);
+          make_box_ray32(o, d, m.bmag, br); oct = box_octant(br);
           br_world = false;
           nodes = m.nodes4; tri32 = m.tri32; tri64 = m.tri64;
           in_blas = true;
@@ -564,6 +585,10 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
       }
     }
   }
+  // traversal statistics (4-wide node steps and exact triangle tests) for DESIGN.md / bench.py
+  unsigned long long ns = n_steps, nt = n_tris;
+  for (int off = 16; off > 0; off >>= 1) { ns += __shfl_down_sync(FULL, ns, off); nt += __shfl_down_sync(FULL, nt, off); }
+  if (lane == 0 && a.counters) { atomicAdd(&a.counters->node_steps, ns); atomicAdd(&a.counters->tri_tests, nt); }
 }
 
 // ------------------------------------------------------------------------------------------ wavefront: shade
@@ -581,7 +606,7 @@ struct QueueSink {
     base = __shfl_sync(m, base, leader);
     const unsigned i = base + __popc(m & ((1u << lane) - 1));
     if (i < a.capacity) {
-      next[i] = c;
+      store_ray_cs(next + i, c);
       if (a.hist) {       // sort key: rays leaving the same cell of the scene in the same octant walk the same part of the BVH
         const unsigned cells = (1u << a.sort_bits) - 1u;
         const unsigned cx = min((unsigned)fmaxf(((float)c.o[0] - a.sort_lo[0]) * a.sort_scale[0], 0.f), cells);
@@ -634,8 +659,8 @@ __global__ void __launch_bounds__(128, PLASTIC ? 3 : 5) k_shade(const RenderArgs
   const RayRec *rays = a.queue[a.cur];
   ShadeCounters cnt; memset(&cnt, 0, sizeof cnt);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    const RayRec cur = rays[i];
-    const HitRec hr = a.hits[i];
+    RayRec cur; load_ray_cs(&cur, rays + i);
+    HitRec hr; load_hit_cs(&hr, a.hits + i);
     cnt.rays[cur.type]++;
     if (hr.inst < 0) continue;
     int ti, x, y; TileGrid g;

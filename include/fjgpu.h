@@ -174,6 +174,7 @@ typedef struct fjgpu_stats {
   uint64_t rays_hit;                /* rays (any type) that found a surface */
   uint64_t hit_mesh_levels;         /* sum over those rays of ceil(log2(triangles of the mesh hit)): the root-to-leaf
                                        path lengths of the algorithmic-bytes model */
+  uint64_t node_steps, tri_tests;   /* k_extend: 4-wide BVH node visits and exact FP64 triangle tests (all rays) */
   uint64_t kernel_launches;         /* launches of this library's kernels in the call */
   uint64_t trace_launches;          /* launches of the closest-hit kernel (k_extend; k_render_samples in megakernel mode) */
   float    ms_trace;                /* device time of the closest-hit kernel launches (CUDA events on the launching stream) */

@@ -5,5 +5,5 @@ for cfg in "$@"; do
   env $cfg timeout 600 python bench.py --steps 2 --warmup 2 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('%.1f Mrays/s  %.1f ms/frame  kernels %s  e2e %.1f' % (d['value'], d['ms_per_step'], {k: round(v,1) for k,v in d['kernel_ms_per_step'].items()}, d['e2e']['value']))"
+print('%.1f Mrays/s  %.1f ms/frame  kernels %s  e2e %.1f' % (d['value'], d['ms_per_step'], {k: round(v,1) for k,v in d['kernel_ms_per_step'].items()}, d['e2e']['value']), ' steps/ray %.1f tris/ray %.1f' % (d['config']['node_steps_per_ray'], d['config']['tri_tests_per_ray']))"
 done
