@@ -140,7 +140,8 @@ void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int 
   out->nodes.clear(); out->order.clear(); out->top_count = 0; out->max_depth = 0;
   out->nodes4.clear(); out->max_depth4 = 0;
   Node128 empty4; memset(&empty4, 0, sizeof empty4);
-  for (int k = 0; k < 4; k++) { empty4.lox[k] = empty4.loy[k] = empty4.loz[k] = 3e38f; empty4.hix[k] = empty4.hiy[k] = empty4.hiz[k] = -3e38f; empty4.c[k] = ~0; }
+  // unused slots: a valid box (lo == hi) at +3e38 that no ray interval reaches — the min/max slab test of k_extend2 needs lo <= hi
+  for (int k = 0; k < 4; k++) { empty4.lox[k] = empty4.loy[k] = empty4.loz[k] = 3e38f; empty4.hix[k] = empty4.hiy[k] = empty4.hiz[k] = 3e38f; empty4.c[k] = ~0; }
   box_empty(out->bounds);
   Node64 empty_node; memset(&empty_node, 0, sizeof empty_node);
   for (int k = 0; k < 12; k++) empty_node.f[k] = (k % 2 == 0) ? 3e38f : -3e38f;   // lo = +big, hi = -big: never hit
@@ -256,6 +257,90 @@ void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int 
     }
     out->nodes4[it.wide] = w;
   }
+  // Worst-case stack depth of the wavefront's walk (nearest hit child first, the other hit children pushed): entering a
+  // child leaves at most (valid children - 1) siblings on the stack at every level.  Children have larger indices than
+  // their parent (DFS preorder), so one backward sweep is enough.
+  {
+    const size_t n4 = out->nodes4.size();
+    std::vector<int32_t> need(n4, 0);
+    for (size_t i = n4; i-- > 0;) {
+      const Node128 &w = out->nodes4[i];
+      int valid = 0, deepest = 0;
+      for (int k = 0; k < 4; k++) {
+        if (w.lox[k] > w.hix[k] || w.lox[k] >= 3e38f) continue;
+        valid++;
+        if (w.c[k] >= 0) deepest = std::max(deepest, need[w.c[k]]);
+      }
+      need[i] = std::max(valid - 1, 0) + deepest;
+    }
+    out->stack_need4 = n4 ? need[0] : 0;
+  }
+}
+
+bool quantize_nodes(const Node128 *in, size_t n, NodeQ64 *out, float *bmag) {
+  double mag = 0;
+  for (size_t i = 0; i < n; i++) {
+    const Node128 &w = in[i];
+    NodeQ64 &q = out[i];
+    memset(&q, 0, sizeof q);
+    const float *lo[3] = {w.lox, w.loy, w.loz}, *hi[3] = {w.hix, w.hiy, w.hiz};
+    bool valid[4]; int nvalid = 0;
+    for (int k = 0; k < 4; k++) { valid[k] = !(w.lox[k] > w.hix[k]) && w.lox[k] < 3e38f; nvalid += valid[k]; }
+    uint32_t sbits[3];
+    for (int a = 0; a < 3; a++) {
+      double plo = 1e300, phi = -1e300;
+      for (int k = 0; k < 4; k++) if (valid[k]) { plo = std::min(plo, (double)lo[a][k]); phi = std::max(phi, (double)hi[a][k]); }
+      if (nvalid == 0) { plo = phi = 0; }
+      const float p = (float)plo;                       // exact: plo is one of the float planes
+      // smallest power of two s with extent <= 254 s (one step of headroom for the outward rounding below)
+      const double extent = phi - plo;
+      int e = -100;
+      if (extent > 0) { int ex; std::frexp(extent / 254.0, &ex); e = ex; if (std::ldexp(1.0, e - 1) * 254.0 >= extent) e--; }
+      if (e < -60) e = -60;                             // keeps s / d inside the normal FP32 range for any direction
+      uint32_t qlo = 0, qhi = 0;
+      double sc = 0;
+      for (;; e++) {                                    // (one more step only if the outward rounding ran out of range)
+        if (e > 60) return false;
+        sc = std::ldexp(1.0, e);
+        qlo = qhi = 0;
+        bool fits = true;
+        for (int k = 0; k < 4 && fits; k++) {
+          int l = 255, h = 0;                           // unused slot: inverted box
+          if (valid[k]) {
+            l = (int)std::floor(((double)lo[a][k] - plo) / sc); h = (int)std::ceil(((double)hi[a][k] - plo) / sc);
+            if (l > 255) l = 255;
+            if (h < 0) h = 0;
+            while (l > 0 && plo + l * sc > (double)lo[a][k]) l--;
+            while (h < 255 && plo + h * sc < (double)hi[a][k]) h++;
+            if (l < 0) l = 0;
+            if (plo + h * sc < (double)hi[a][k]) fits = false;
+          }
+          qlo |= (uint32_t)l << (8 * k); qhi |= (uint32_t)h << (8 * k);
+        }
+        if (fits) break;
+      }
+      for (int k = 0; k < 4; k++) if (valid[k])
+        mag = std::max(mag, std::max(std::fabs(plo + ((qlo >> (8 * k)) & 255) * sc), std::fabs(plo + ((qhi >> (8 * k)) & 255) * sc)));
+      memcpy(&q.w[a], &p, 4);
+      const float sf = (float)sc; memcpy(&sbits[a], &sf, 4);
+      q.w[a == 0 ? 4 : (a == 1 ? 6 : 8)] = qlo; q.w[a == 0 ? 5 : (a == 1 ? 7 : 9)] = qhi;
+    }
+    q.w[3] = (sbits[0] & 0xffff0000u) | (sbits[1] >> 16);
+    q.w[14] = sbits[2] & 0xffff0000u;
+    for (int k = 0; k < 4; k++) q.w[10 + k] = (uint32_t)w.c[k];
+  }
+  *bmag = round_up(mag * (1.0 + 1e-6));
+  return true;
+}
+
+void to_quad_layout(const Node128 *in, size_t n, Node4Q *out) {
+  for (size_t i = 0; i < n; i++)
+    for (int k = 0; k < 4; k++) {
+      Child32 &c = out[i].c[k];
+      c.lo[0] = in[i].lox[k]; c.lo[1] = in[i].loy[k]; c.lo[2] = in[i].loz[k];
+      c.hi[0] = in[i].hix[k]; c.hi[1] = in[i].hiy[k]; c.hi[2] = in[i].hiz[k];
+      c.ref = in[i].c[k]; c.pad = 0;
+    }
 }
 
 }  // namespace fjb

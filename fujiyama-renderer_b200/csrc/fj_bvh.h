@@ -51,7 +51,33 @@ struct BuildResult {
   Aabb bounds;
   std::vector<Node128> nodes4;   // the same tree collapsed to 4-wide nodes, DFS preorder, nodes4[0] is the root
   int32_t max_depth4 = 0;
+  int32_t stack_need4 = 0;       // worst-case traversal-stack entries of a nearest-first walk of nodes4 (see stack_need())
 };
+
+// The 4-wide tree in the child-major layout of the quad-per-ray kernel (k_extend3): child k of a node occupies bytes
+// 32k..32k+31 = lo.x lo.y lo.z hi.x | hi.y hi.z ref pad, so the four lanes of a quad fetch one child each with a single
+// 32-B load and the quad reads the node's 128-B line exactly once.
+struct Child32 { float lo[3]; float hi[3]; int32_t ref; int32_t pad; };
+struct Node4Q { Child32 c[4]; };
+static_assert(sizeof(Node4Q) == 128, "quad node must be 128 bytes");
+void to_quad_layout(const Node128 *in, size_t n, Node4Q *out);
+
+// The 4-wide tree with child boxes quantised to 8 bits per plane inside the node's own box (64 B per node, two 32-B
+// loads): the closest-hit kernel is bound by the L1 data pipe, which moves 16 B per lane per pass when every lane reads
+// its own node, so bytes per node step are what it pays for.
+//   w[0..2]  p = lo corner of the union of the valid child boxes (float)
+//   w[3]     (bits of sx) & 0xffff0000 | (bits of sy) >> 16      scale per axis, a power of two (exact in 16 bits)
+//   w[4..7]  qlo.x[4] qhi.x[4] qlo.y[4] qhi.y[4]                  one byte per child: plane = p + q * s
+//   w[8..9]  qlo.z[4] qhi.z[4]
+//   w[10..13] child references (as Node128::c)
+//   w[14]    (bits of sz) & 0xffff0000
+// qlo is rounded down and qhi up, so a decoded box contains the FP32 box it came from.  Unused slots hold the inverted
+// box qlo = 255, qhi = 0, which the sign-selected slab test never enters.
+struct NodeQ64 { uint32_t w[16]; };
+static_assert(sizeof(NodeQ64) == 64, "quantised node must be 64 bytes");
+// Returns false when a node cannot be represented (extent beyond the exponent range kept for the FP32 error bound).
+// *bmag receives the largest |coordinate| of any decoded plane.
+bool quantize_nodes(const Node128 *in, size_t n, NodeQ64 *out, float *bmag);
 
 // Builds a binned-SAH BVH2 over `n` primitive boxes.  max_leaf <= 8.  `top_levels` BFS levels are laid
 // out contiguously at the front of `nodes` (they are staged in shared memory by the kernels).

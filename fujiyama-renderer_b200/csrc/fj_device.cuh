@@ -69,6 +69,9 @@ struct DMesh {
   float bmag;               // max |coordinate| of the mesh bounds: scales the FP32 slab-test error bound (extend kernel)
   float pad1;
   const float4 *nodes4;     // the same tree as 4-wide 128-B nodes (fj_bvh.h Node128) for the wavefront's k_extend
+  const float4 *nodes4q;    // the 4-wide tree in child-major layout (fj_bvh.h Node4Q) for the quad-per-ray k_extend3
+  const float4 *nodesq;     // the 4-wide tree with 8-bit quantised child boxes (fj_bvh.h NodeQ64), null if not representable
+  float bmagq, pad2;        // bound magnitude of the decoded planes
 };
 struct DInstance {
   double inv[12];           // rows 0..2 of MatInverse(matrix): world -> object (fj_object_instance.cc:222-225)
@@ -77,7 +80,7 @@ struct DInstance {
   int32_t shader_of_group[FJ_MAX_SHADING_GROUPS];
   int32_t reflect_target, refract_target, shadow_target;
 };
-struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; };   // TLAS leaf (first,count) -> order[first..] = instance indices
+struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; const float4 *nodes4q; const float4 *nodesq; float bmagq, pad2; };   // TLAS leaf (first,count) -> order[first..] = instance indices
 struct DShader {
   int32_t kind, do_reflect, do_color_filter, pad;
   float diffuse[3], reflect[3], refract[3], emission[3], transmit[3];

@@ -1,0 +1,298 @@
+// fj_extend.cuh — k_extend2: the closest-hit kernel of the wavefront with the exact (FP64) half of every ray's state
+// in shared memory.
+//
+// Same algorithm and results as k_extend (fj_kernels.cuh): persistent threads, one ray per lane, warp-synchronous
+// phases (refill / 4-wide node steps with speculative leaf parking / exact FP64 triangle tests / transitions).
+// What changed is where the state lives.  k_extend keeps everything in registers (112 unconstrained, 96 with spills
+// at 5 CTAs/SM) and is bound by latency x occupancy: 5 warps per scheduler cannot cover the dependent-issue latency
+// of the node step, let alone the node fetch.  Here the node loop only carries the FP32 box ray, the
+// stack pointer and the node reference; object-space origin/direction, tmin, the best hit and the triangle pointer
+// (104 B per lane) sit in shared memory, SoA so that a warp's accesses are conflict-free, and are touched only by the
+// triangle and transition phases.  That fits the kernel in 64 registers: 8 CTAs (32 warps) per SM.
+#pragma once
+
+#include "fj_kernels.cuh"
+
+namespace fj {
+
+#define FJ_XT 128      // threads per CTA
+
+struct ExtShared {
+  double ox[FJ_XT], oy[FJ_XT], oz[FJ_XT], dx[FJ_XT], dy[FJ_XT], dz[FJ_XT];    // ray in the space being traversed (object space inside a BLAS)
+  double tmin[FJ_XT], best_t[FJ_XT], best_u[FJ_XT], best_v[FJ_XT];
+  const void *tri[FJ_XT];                                                     // triangle packets of the current mesh (tri32 or tri64)
+  int cur_inst[FJ_XT], best_inst[FJ_XT], best_prim[FJ_XT], leaf[FJ_XT];
+  unsigned ridx[FJ_XT];
+};
+
+// 256-bit read-only global load (sm_100: LDG.E.ENL2.256.CONSTANT).  The closest-hit kernel is bound by L1 wavefronts —
+// every lane reads its own node, so each load instruction costs one wavefront per lane whatever its width; a 128-B
+// node is four 32-B loads instead of seven 16-B ones.  `p` must be 32-byte aligned.
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const void *p) {
+  F8 r;
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+  return r;
+}
+
+// Box ray of the min/max slab test: per axis 1/d and the two FMA constants of the lo and the hi plane,
+//   t(lo plane) = fma(lo, inv, c_lo),  t(hi plane) = fma(hi, inv, c_hi),  near = min of the two, far = max of the two.
+// The conservative widening of make_box_ray32 (near lowered, far raised by e) is kept by handing the lowered constant to
+// whichever plane is the near one for this direction sign: (c_lo, c_hi) = inv >= 0 ? (cn, cf) : (cf, cn).  For a valid
+// box (lo <= hi) this yields exactly the values of the address-selected form, with no per-step sign decoding.
+struct BoxRayMM { float ix, iy, iz, lx, ly, lz, hx, hy, hz; };
+__device__ __forceinline__ void make_box_ray_mm(const D3 &o, const D3 &d, float B, BoxRayMM &r) {
+  float cn, cf;
+  box_axis(o.x, d.x, B, &r.ix, &cn, &cf); r.lx = r.ix < 0.f ? cf : cn; r.hx = r.ix < 0.f ? cn : cf;
+  box_axis(o.y, d.y, B, &r.iy, &cn, &cf); r.ly = r.iy < 0.f ? cf : cn; r.hy = r.iy < 0.f ? cn : cf;
+  box_axis(o.z, d.z, B, &r.iz, &cn, &cf); r.lz = r.iz < 0.f ? cf : cn; r.hz = r.iz < 0.f ? cn : cf;
+}
+
+// TriRayIntersect (tri_intersect, fj_device.cuh) with the ray fetched from shared memory where it is used, so that origin
+// and direction do not occupy twelve registers across the whole test.  Same operations in the same order: bit-identical.
+__device__ __forceinline__ bool tri_intersect_smem(const D3 &v0, const D3 &v1, const D3 &v2, const volatile ExtShared &V, int tid,
+                                                   double *t, double *u, double *v) {
+  const D3 e1 = v1 - v0, e2 = v2 - v0;
+  D3 pvec;
+  { const D3 dir = mk(V.dx[tid], V.dy[tid], V.dz[tid]); pvec = cross(dir, e2); }
+  const double det = dot(e1, pvec);
+  if (det > -1e-6 && det < 1e-6) return false;
+  const double inv_det = ddiv(1.0, det);
+  const D3 tvec = mk(V.ox[tid], V.oy[tid], V.oz[tid]) - v0;
+  *u = dmul(dot(tvec, pvec), inv_det);
+  if (*u < 0.0 || *u > 1.0) return false;
+  const D3 qvec = cross(tvec, e1);
+  { const D3 dir = mk(V.dx[tid], V.dy[tid], V.dz[tid]); *v = dmul(dot(dir, qvec), inv_det); }
+  if (*v < 0.0 || dadd(*u, *v) > 1.0) return false;
+  *t = dmul(dot(e2, qvec), inv_det);
+  return true;
+}
+
+// Lane state word: what the node loop has to know about the exact half of the state.
+enum { XS_BLAS = 1, XS_WORLD = 2, XS_TRI64 = 4, XS_LEAF = 8 };
+
+template <int MINB, bool STATS, bool QUANT>
+__global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
+  __shared__ ExtShared S;
+  const unsigned FULL = 0xffffffffu;
+  const int tid = threadIdx.x;
+  const RayRec *rays = a.queue[a.cur];
+  const unsigned count = min(a.ctl->count[a.cur], a.capacity);
+  const DScene &sc = a.sc;
+  int stack[FJ_STACK4];
+  // negative node references that are not leaves: end of a BLAS, end of the traversal, lane without a ray
+  const int SENTINEL = (int)0x80000000, DONE = (int)0x80000001, IDLE = (int)0x80000002;
+  const unsigned MISS = 0xffffffffu;
+
+  bool drained = false;
+  unsigned st = 0;
+  int sp = 0, node = IDLE;
+  float tn = 0, tf = 0;
+  BoxRayMM br; br.ix = br.iy = br.iz = br.lx = br.ly = br.lz = br.hx = br.hy = br.hz = 0.f;
+  const char *nodes = nullptr;                  // 4-wide nodes of the tree being walked: Node128, or NodeQ64 when QUANT
+  unsigned n_steps = 0, n_tris = 0;             // warp totals (every lane carries the same value)
+
+  for (;;) {
+    // ---- refill idle lanes from the queue head
+    const unsigned idle = __ballot_sync(FULL, node == IDLE);
+    if (idle == FULL && drained) break;
+    if (!drained && __popc(idle) >= a.refill) {
+      const int lane = tid & 31;
+      const int n = __popc(idle), leader = __ffs(idle) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(&a.ctl->head, (unsigned)n);
+      base = __shfl_sync(FULL, base, leader);
+      if (base + n >= count) drained = true;
+      if (node == IDLE) {
+        const unsigned i = base + __popc(idle & ((1u << lane) - 1));
+        if (i < count) {
+          const unsigned ridx = a.perm ? a.perm[i] : i;
+          const RayRec &r = rays[ridx];
+          const double tmin = r.tmin, tmax = r.tmax;
+          S.ridx[tid] = ridx; S.tmin[tid] = tmin; S.best_t[tid] = tmax; S.best_u[tid] = 0; S.best_v[tid] = 0;
+          S.best_inst[tid] = -1; S.best_prim[tid] = -1; S.cur_inst[tid] = -1;
+          tn = __double2float_rd(tmin); tf = __double2float_ru(tmax);
+          const DGroup grp = sc.groups[r.target];
+          nodes = (const char *)(QUANT ? grp.nodesq : grp.nodes4); sp = 0; node = 0;
+          make_box_ray_mm(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), QUANT ? grp.bmagq : grp.bmag, br);
+          st = XS_WORLD;
+        }
+      }
+      if (STATS && (n_steps | n_tris) > 0x40000000u) {      // keep the 32-bit warp totals from wrapping
+        if (lane == 0) { atomicAdd(&a.counters->node_steps, (unsigned long long)n_steps); atomicAdd(&a.counters->tri_tests, (unsigned long long)n_tris); }
+        n_steps = n_tris = 0;
+      }
+      if (__ballot_sync(FULL, node != IDLE) == 0) break;
+    }
+
+    // ---- phase A: 4-wide inner nodes, nearest hit child first
+    for (;;) {
+      const bool want = node >= 0;
+      const unsigned wm = __ballot_sync(FULL, want);
+      if (wm == 0) break;
+      // few lanes left descending: switch to the parked leaves / transitions if there are any to work on
+      if (__popc(wm) < a.phase_a_min && __any_sync(FULL, (st & XS_LEAF) || (node < 0 && node != IDLE))) break;
+      if (STATS) n_steps += __popc(wm);
+      if (want) {
+        if (!(st & (XS_BLAS | XS_WORLD))) {      // back in the instance tree after a BLAS: world-space box ray and tree again
+          const RayRec &r = rays[S.ridx[tid]];
+          const DGroup grp = sc.groups[r.target];
+          nodes = (const char *)(QUANT ? grp.nodesq : grp.nodes4);
+          make_box_ray_mm(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), QUANT ? grp.bmagq : grp.bmag, br);
+          st |= XS_WORLD;
+        }
+        unsigned key0, key1, key2, key3; int4 ch;
+        if (QUANT) {
+          // 64-B node with 8-bit planes (fj_bvh.h NodeQ64): plane = p + q s, so t(plane) = fma(q, s/d, fma(p, 1/d, c)) — two more
+          // roundings of at most 2^-24 (|o| + B) |1/d| each, inside the 2^-20 widening c already carries
+          const char *np = nodes + 64 * (size_t)node;
+          const F8 A = ldg256(np), Q = ldg256(np + 32);
+          const unsigned sw = __float_as_uint(A.a.w);
+          const float six = __fmul_rn(__uint_as_float(sw & 0xffff0000u), br.ix), siy = __fmul_rn(__uint_as_float(sw << 16), br.iy);
+          const float siz = __fmul_rn(Q.b.z, br.iz);
+          const float bx0 = fmaf(A.a.x, br.ix, br.lx), bx1 = fmaf(A.a.x, br.ix, br.hx);
+          const float by0 = fmaf(A.a.y, br.iy, br.ly), by1 = fmaf(A.a.y, br.iy, br.hy);
+          const float bz0 = fmaf(A.a.z, br.iz, br.lz), bz1 = fmaf(A.a.z, br.iz, br.hz);
+          const unsigned qlx = __float_as_uint(A.b.x), qhx = __float_as_uint(A.b.y), qly = __float_as_uint(A.b.z), qhy = __float_as_uint(A.b.w);
+          const unsigned qlz = __float_as_uint(Q.a.x), qhz = __float_as_uint(Q.a.y);
+          ch = make_int4(__float_as_int(Q.a.z), __float_as_int(Q.a.w), __float_as_int(Q.b.x), __float_as_int(Q.b.y));
+          // near / far plane by direction sign (not min/max: unused slots hold an inverted box that must stay a miss)
+          const bool gx = br.ix < 0.f, gy = br.iy < 0.f, gz = br.iz < 0.f;
+#define FJ_CHILD(KEY, K)                                                                                                        \
+          {                                                                                                                        \
+            const float x0 = fmaf((float)((qlx >> (8 * K)) & 255u), six, bx0), x1 = fmaf((float)((qhx >> (8 * K)) & 255u), six, bx1); \
+            const float y0 = fmaf((float)((qly >> (8 * K)) & 255u), siy, by0), y1 = fmaf((float)((qhy >> (8 * K)) & 255u), siy, by1); \
+            const float z0 = fmaf((float)((qlz >> (8 * K)) & 255u), siz, bz0), z1 = fmaf((float)((qhz >> (8 * K)) & 255u), siz, bz1); \
+            const float nr = fmaxf(fmaxf(gx ? x1 : x0, gy ? y1 : y0), fmaxf(gz ? z1 : z0, tn));                                   \
+            const float fr_ = fminf(fminf(gx ? x0 : x1, gy ? y0 : y1), fminf(gz ? z0 : z1, tf));                                  \
+            KEY = nr <= fr_ ? ((__float_as_uint(nr) & ~3u) | K##u) : MISS;                                                        \
+          }
+          FJ_CHILD(key0, 0) FJ_CHILD(key1, 1) FJ_CHILD(key2, 2) FJ_CHILD(key3, 3)
+#undef FJ_CHILD
+        } else {
+        // 4-wide node: lo.x[4] hi.x[4] | lo.y[4] hi.y[4] | lo.z[4] hi.z[4] | child[4] — three 32-B loads and one 16-B load
+        const char *np = nodes + 128 * (size_t)node;
+        const F8 X = ldg256(np), Y = ldg256(np + 32), Z = ldg256(np + 64);
+        ch = __ldg((const int4 *)(np + 96));
+#define FJ_CHILD(KEY, K, C)                                                                                                     \
+        {                                                                                                                          \
+          const float x0 = fmaf(X.a.C, br.ix, br.lx), x1 = fmaf(X.b.C, br.ix, br.hx);                                            \
+          const float y0 = fmaf(Y.a.C, br.iy, br.ly), y1 = fmaf(Y.b.C, br.iy, br.hy);                                            \
+          const float z0 = fmaf(Z.a.C, br.iz, br.lz), z1 = fmaf(Z.b.C, br.iz, br.hz);                                            \
+          const float nr = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tn));                                   \
+          const float fr_ = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tf));                                  \
+          KEY = nr <= fr_ ? ((__float_as_uint(nr) & ~3u) | K) : MISS;                                                              \
+        }
+        FJ_CHILD(key0, 0u, x) FJ_CHILD(key1, 1u, y) FJ_CHILD(key2, 2u, z) FJ_CHILD(key3, 3u, w)
+#undef FJ_CHILD
+        }
+        // entry distances are positive (tn > 0), so their bit patterns order like unsigned integers.  The nearest hit child
+        // is visited next; the other hit children are pushed (exact front-to-back order for up to two hits, slot order beyond)
+        const unsigned kmin = min(min(key0, key1), min(key2, key3));
+        if (kmin != MISS) {
+          const unsigned w = kmin & 3u;
+          if (key0 != MISS && w != 0u) stack[sp++] = ch.x;
+          if (key1 != MISS && w != 1u) stack[sp++] = ch.y;
+          if (key2 != MISS && w != 2u) stack[sp++] = ch.z;
+          if (key3 != MISS && w != 3u) stack[sp++] = ch.w;
+          node = (w & 2u) ? ((w & 1u) ? ch.w : ch.z) : ((w & 1u) ? ch.y : ch.x);
+        } else node = sp > 0 ? stack[--sp] : DONE;
+        // speculative traversal: park the first triangle leaf and keep descending.  Inside a BLAS the bottom stack entry is
+        // SENTINEL, so a negative reference there is SENTINEL or a triangle leaf and the pop below cannot underflow.
+        if (node < 0 && (st & (XS_BLAS | XS_LEAF)) == XS_BLAS && node != SENTINEL) { S.leaf[tid] = node; st |= XS_LEAF; node = stack[--sp]; }
+      }
+    }
+
+    // ---- phase B1: parked triangle leaves, exact FP64 tests, one triangle per lane per iteration
+    if (__any_sync(FULL, st & XS_LEAF)) {
+      int first = 0, cnt = 0;
+      double tmin = 0, best_t = 0; bool found = false;
+      const void *tp_ = nullptr;
+      if (st & XS_LEAF) {
+        const int ref = ~S.leaf[tid];
+        first = ref >> 3; cnt = (ref & 7) + 1;
+        tmin = S.tmin[tid]; best_t = S.best_t[tid]; found = S.best_inst[tid] >= 0; tp_ = S.tri[tid];
+        st &= ~XS_LEAF;
+      }
+      for (int k = 0;; k++) {
+        const bool want = k < cnt;
+        const unsigned wm = __ballot_sync(FULL, want);
+        if (wm == 0) break;
+        if (STATS) n_tris += __popc(wm);
+        if (want) {
+          D3 v0, v1, v2; int prim;
+          if (!(st & XS_TRI64)) {
+            // 48-B packet, 16-B aligned: one 32-B and one 16-B load, which comes first depends on the packet's parity
+            const unsigned ti = (unsigned)(first + k);
+            const char *tb = (const char *)tp_ + 48 * (size_t)ti;
+            const bool odd = ti & 1u;
+            const float4 s4 = __ldg((const float4 *)(tb + (odd ? 0 : 32)));
+            const F8 w8 = ldg256(tb + (odd ? 16 : 0));
+            const float4 p0 = odd ? s4 : w8.a, p1 = odd ? w8.a : w8.b, p2 = odd ? w8.b : s4;
+            v0 = mk(p0.x, p0.y, p0.z); v1 = mk(p1.x, p1.y, p1.z); v2 = mk(p2.x, p2.y, p2.z); prim = __float_as_int(p0.w);
+          } else {
+            const double *p = (const double *)tp_ + 10 * (size_t)(first + k);
+            v0 = mk(__ldg(p), __ldg(p + 1), __ldg(p + 2)); v1 = mk(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5)); v2 = mk(__ldg(p + 6), __ldg(p + 7), __ldg(p + 8));
+            prim = (int)__double_as_longlong(__ldg(p + 9));
+          }
+          double t, u, v;
+          // RayInRange (src/fj_ray.h:29-32): tmin <= t <= tmax; best_t starts at tmax, so `t <= best_t` is the upper test
+          if (tri_intersect_smem(v0, v1, v2, S, tid, &t, &u, &v) && tmin <= t && t <= best_t) {
+            bool better = !found || t < best_t;
+            if (!better) {                         // exact tie in t: lower instance, then higher face id
+              const int ci = S.cur_inst[tid], bi = S.best_inst[tid];
+              better = ci < bi || (ci == bi && prim > S.best_prim[tid]);
+            }
+            if (better) {
+              found = true; best_t = t;
+              S.best_t[tid] = t; S.best_u[tid] = u; S.best_v[tid] = v; S.best_prim[tid] = prim; S.best_inst[tid] = S.cur_inst[tid];
+              tf = __double2float_ru(t);
+            }
+          }
+        }
+      }
+    }
+
+    // ---- phase B2: transitions of lanes whose next stack entry is not an inner node
+    const bool special = node < 0 && node != IDLE;
+    if (__any_sync(FULL, special)) {
+      if (special) {
+        if (node == DONE) {                        // traversal finished: write the hit record
+          const int bi = S.best_inst[tid];
+          HitRec hr; hr.t = bi >= 0 ? S.best_t[tid] : FJ_REAL_MAX; hr.u = S.best_u[tid]; hr.v = S.best_v[tid]; hr.prim = S.best_prim[tid]; hr.inst = bi;
+          store_hit_cs(a.hits + S.ridx[tid], hr);
+          node = IDLE;
+        } else if (node == SENTINEL) {             // the instance's BLAS is done: back to the instance tree (its nodes and box
+          st &= ~(XS_BLAS | XS_WORLD);             // ray are fetched again only if an inner node of that tree is still to be visited)
+          node = sp > 0 ? stack[--sp] : DONE;
+        } else if (st & XS_BLAS) {                 // a second triangle leaf: park it now that the slot is free
+          S.leaf[tid] = node; st |= XS_LEAF; node = stack[--sp];
+        } else {                                   // TLAS leaf: enter the first instance, re-queue the others
+          const int ref = ~node;
+          const int first = ref >> 3, cnt = (ref & 7) + 1;
+          for (int k = cnt - 1; k >= 1; k--) stack[sp++] = ~(((first + k) << 3) | 0);
+          const RayRec &r = rays[S.ridx[tid]];
+          const int ci = sc.groups[r.target].order[first];
+          S.cur_inst[tid] = ci;
+          const DInstance &in = sc.inst[ci];
+          const D3 o = mat_point(in.inv, mk(r.o[0], r.o[1], r.o[2]));
+          const D3 d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
+          S.ox[tid] = o.x; S.oy[tid] = o.y; S.oz[tid] = o.z; S.dx[tid] = d.x; S.dy[tid] = d.y; S.dz[tid] = d.z;
+          const DMesh &m = sc.meshes[in.mesh];
+          make_box_ray_mm(o, d, QUANT ? m.bmagq : m.bmag, br);
+          nodes = (const char *)(QUANT ? m.nodesq : m.nodes4);
+          const bool t64 = m.tri32 == nullptr;
+          S.tri[tid] = t64 ? (const void *)m.tri64 : (const void *)m.tri32;
+          st = XS_BLAS | (t64 ? XS_TRI64 : 0);
+          stack[sp++] = SENTINEL;
+          node = 0;
+        }
+      }
+    }
+  }
+  // traversal statistics (4-wide node steps and exact triangle tests) for DESIGN.md / bench.py
+  if (STATS && (tid & 31) == 0 && a.counters) { atomicAdd(&a.counters->node_steps, (unsigned long long)n_steps); atomicAdd(&a.counters->tri_tests, (unsigned long long)n_tris); }
+}
+
+}  // namespace fj

@@ -8,6 +8,8 @@
 #include "fjgpu.h"
 #include "fj_bvh.h"
 #include "fj_kernels.cuh"
+#include "fj_extend.cuh"
+#include "fj_extend_quad.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -30,11 +32,11 @@ struct DevBuf {
 };
 
 struct MeshRec {
-  DevBuf nodes, nodes4, tri, N, idx, group;
+  DevBuf nodes, nodes4, nodes4q, nodesq, tri, N, idx, group;
   fj::DMesh d;
   double bmin[3], bmax[3];      // exact FP64 bounds of the mesh (Mesh::ComputeBounds, fj_mesh.cc:235-244)
-  int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0, max_depth4 = 0, nnodes4 = 0;
-  void release() { nodes.release(); nodes4.release(); tri.release(); N.release(); idx.release(); group.release(); }
+  int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0, max_depth4 = 0, nnodes4 = 0, stack_need4 = 0;
+  void release() { nodes.release(); nodes4.release(); nodes4q.release(); nodesq.release(); tri.release(); N.release(); idx.release(); group.release(); }
 };
 
 }  // namespace
@@ -58,11 +60,13 @@ struct fjgpu_context {
 
   // device scene
   DevBuf d_meshes, d_inst, d_groups, d_shaders, d_lights;
-  std::vector<DevBuf> d_group_nodes, d_group_nodes4, d_group_order, d_dome;
+  std::vector<DevBuf> d_group_nodes, d_group_nodes4, d_group_nodes4q, d_group_nodesq, d_group_order, d_dome;
   fj::DScene sc;
   std::vector<int> mesh_slot_of_id;   // dense slot per mesh id (map order)
   uint64_t tlas_nodes = 0;
   int tlas_depth4 = 0;
+  bool quant_ok = true;        // every tree of the committed scene has a quantised (NodeQ64) copy
+  int stack_need = 0;          // worst-case traversal stack of k_extend3 for the committed scene (entries)
   double build_seconds = 0;
 
   // frame resources
@@ -178,12 +182,19 @@ int commit_scene(fjgpu_context *ctx) {
   const int ngroups = (int)ctx->group_off.size() - 1;
   for (auto &b : ctx->d_group_nodes) b.release();
   for (auto &b : ctx->d_group_nodes4) b.release();
+  for (auto &b : ctx->d_group_nodes4q) b.release();
+  for (auto &b : ctx->d_group_nodesq) b.release();
   for (auto &b : ctx->d_group_order) b.release();
+  ctx->d_group_nodes4q.assign(std::max(ngroups, 0), DevBuf());
+  ctx->d_group_nodesq.assign(std::max(ngroups, 0), DevBuf());
+  ctx->quant_ok = true;
+  for (auto &kv : ctx->meshes) ctx->quant_ok = ctx->quant_ok && kv.second.d.nodesq != nullptr;
   ctx->d_group_nodes.assign(std::max(ngroups, 0), DevBuf());
   ctx->d_group_nodes4.assign(std::max(ngroups, 0), DevBuf());
   ctx->d_group_order.assign(std::max(ngroups, 0), DevBuf());
   std::vector<fj::DGroup> dg(std::max(ngroups, 0));
   ctx->tlas_nodes = 0;
+  int tlas_need = 0;
   for (int g = 0; g < ngroups; g++) {
     const int b = ctx->group_off[g], e = ctx->group_off[g + 1];
     std::vector<fjb::Aabb> boxes; std::vector<int32_t> ids;
@@ -201,6 +212,19 @@ int commit_scene(fjgpu_context *ctx) {
     if (int rc = dev_upload(ctx, ctx->d_group_order[g], order.data(), order.size() * sizeof(int32_t), true)) return rc;
     if (int rc = dev_upload(ctx, ctx->d_group_nodes4[g], br.nodes4.data(), br.nodes4.size() * sizeof(fjb::Node128), true)) return rc;
     dg[g].nodes4 = (const float4 *)ctx->d_group_nodes4[g].p;
+    {
+      std::vector<fjb::Node4Q> q(br.nodes4.size());
+      fjb::to_quad_layout(br.nodes4.data(), br.nodes4.size(), q.data());
+      if (int rc = dev_upload(ctx, ctx->d_group_nodes4q[g], q.data(), q.size() * sizeof(fjb::Node4Q), true)) return rc;
+      dg[g].nodes4q = (const float4 *)ctx->d_group_nodes4q[g].p;
+      tlas_need = std::max(tlas_need, br.stack_need4);
+      std::vector<fjb::NodeQ64> nq(br.nodes4.size());
+      float bq = 0;
+      if (fjb::quantize_nodes(br.nodes4.data(), br.nodes4.size(), nq.data(), &bq)) {
+        if (int rc = dev_upload(ctx, ctx->d_group_nodesq[g], nq.data(), nq.size() * sizeof(fjb::NodeQ64), true)) return rc;
+        dg[g].nodesq = (const float4 *)ctx->d_group_nodesq[g].p; dg[g].bmagq = bq;
+      } else { dg[g].nodesq = nullptr; dg[g].bmagq = 0; ctx->quant_ok = false; }
+    }
     ctx->tlas_depth4 = std::max(ctx->tlas_depth4, br.max_depth4);
     dg[g].nodes = (const float4 *)ctx->d_group_nodes[g].p;
     dg[g].order = (const int32_t *)ctx->d_group_order[g].p;
@@ -209,6 +233,8 @@ int commit_scene(fjgpu_context *ctx) {
     ctx->tlas_nodes += br.nodes.size();
   }
   if (int rc = dev_upload(ctx, ctx->d_groups, dg.data(), dg.size() * sizeof(fj::DGroup), true)) return rc;
+  // instance tree + the other instances of a TLAS leaf (<= 7) + the BLAS sentinel + the deepest BLAS
+  { int blas_need = 0; for (auto &kv : ctx->meshes) blas_need = std::max(blas_need, kv.second.stack_need4); ctx->stack_need = tlas_need + 7 + 1 + blas_need + 2; }
 
   std::vector<fj::DShader> ds(ctx->shaders.size());
   for (size_t i = 0; i < ds.size(); i++) {
@@ -353,10 +379,67 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
 
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
+template <int MINB, bool QUANT>
+void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
+  // shared-memory carveout: MINB CTAs x (static shared memory + 1 KB the driver reserves per CTA), the rest stays L1
+  static bool configured = false;
+  if (!configured) {
+    const int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * (sizeof(fj::ExtShared) + 1024) / (228.0 * 1024)));
+    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    configured = true;
+  }
+  fj::k_extend2<MINB, true, QUANT><<<blocks, FJ_XT, 0, ctx->stream>>>(a);
+}
+
+template <int MINB>
+void launch_extend3(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks, int stride) {
+  const size_t dyn = (size_t)FJ_QR * stride * sizeof(int);
+  static size_t configured = 0;
+  if (configured < dyn + 1) {
+    const int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * (sizeof(fj::QuadShared) + dyn + 1024) / (228.0 * 1024)));
+    cudaFuncSetAttribute(fj::k_extend3<MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(fj::k_extend3<MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    configured = dyn + 1;
+  }
+  fj::k_extend3<MINB, true><<<blocks, FJ_QT, dyn, ctx->stream>>>(a, stride);
+}
+
+// The closest-hit kernel of one wavefront round.  FJGPU_EXTEND=1 selects the register-resident first version (kept as
+// a cross-check), 2 the shared-memory-state version, 3 (default) the quad-per-ray version; FJGPU_EXTEND_MINBLOCKS = resident CTAs per SM.
 void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
   a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
   a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 12)));
   a.park = env_int("FJGPU_PARK", 1);
+  int version = env_int("FJGPU_EXTEND", 2);
+  const int stride = std::max(15, ctx->stack_need) | 1;             // odd: the ray stacks start in different banks
+  if (version >= 3 && (size_t)FJ_QR * stride * sizeof(int) > 40 * 1024) version = 2;     // tree too deep for the shared-memory stacks
+  if (version >= 3) {
+    const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 8);
+    const int cap = std::max(1, grid / 4 * minb);
+    if (minb >= 12) launch_extend3<12>(ctx, a, cap, stride);
+    else if (minb >= 10) launch_extend3<10>(ctx, a, cap, stride);
+    else if (minb >= 8) launch_extend3<8>(ctx, a, cap, stride);
+    else launch_extend3<6>(ctx, a, cap, stride);
+    return;
+  }
+  if (version >= 2) {
+    const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 7);
+    const int sms = std::max(1, grid / 4);
+    const int cap = std::max(1, grid / 4 * minb);      // `grid` is 4 CTAs per SM worth of work (or fewer for small probes)
+    (void)sms;
+    const bool quant = ctx->quant_ok && env_int("FJGPU_QUANT", 1) != 0;
+    if (quant) {
+      if (minb >= 8) launch_extend2<8, true>(ctx, a, cap);
+      else if (minb == 7) launch_extend2<7, true>(ctx, a, cap);
+      else launch_extend2<6, true>(ctx, a, cap);
+    } else {
+      if (minb >= 8) launch_extend2<8, false>(ctx, a, cap);
+      else if (minb == 7) launch_extend2<7, false>(ctx, a, cap);
+      else if (minb == 6) launch_extend2<6, false>(ctx, a, cap);
+      else launch_extend2<5, false>(ctx, a, cap);
+    }
+    return;
+  }
   const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 5);
   const int g = std::max(1, (grid * minb + 3) / 4);
   if (minb >= 8) fj::k_extend<8><<<g, 128, 0, ctx->stream>>>(a);
@@ -586,6 +669,8 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &kv : ctx->meshes) kv.second.release();
   for (auto &b : ctx->d_group_nodes) b.release();
   for (auto &b : ctx->d_group_nodes4) b.release();
+  for (auto &b : ctx->d_group_nodes4q) b.release();
+  for (auto &b : ctx->d_group_nodesq) b.release();
   for (auto &b : ctx->d_group_order) b.release();
   for (auto &b : ctx->d_dome) b.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
@@ -630,10 +715,24 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
   if (br.max_depth + 8 > FJ_STACK || 3 * br.max_depth4 + 16 > FJ_STACK4) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
   if (int rc = dev_upload(ctx, m.nodes, br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64), true)) return rc;
   if (int rc = dev_upload(ctx, m.nodes4, br.nodes4.data(), br.nodes4.size() * sizeof(fjb::Node128), true)) return rc;
-  m.max_depth4 = br.max_depth4; m.nnodes4 = (int32_t)br.nodes4.size();
+  m.max_depth4 = br.max_depth4; m.nnodes4 = (int32_t)br.nodes4.size(); m.stack_need4 = br.stack_need4;
+  {
+    std::vector<fjb::Node4Q> q(br.nodes4.size());
+    fjb::to_quad_layout(br.nodes4.data(), br.nodes4.size(), q.data());
+    if (int rc = dev_upload(ctx, m.nodes4q, q.data(), q.size() * sizeof(fjb::Node4Q), true)) return rc;
+  }
   memset(&m.d, 0, sizeof m.d);
   m.d.nodes = (const float4 *)m.nodes.p;
   m.d.nodes4 = (const float4 *)m.nodes4.p;
+  m.d.nodes4q = (const float4 *)m.nodes4q.p;
+  {
+    std::vector<fjb::NodeQ64> nq(br.nodes4.size());
+    float bq = 0;
+    if (fjb::quantize_nodes(br.nodes4.data(), br.nodes4.size(), nq.data(), &bq)) {
+      if (int rc = dev_upload(ctx, m.nodesq, nq.data(), nq.size() * sizeof(fjb::NodeQ64), true)) return rc;
+      m.d.nodesq = (const float4 *)m.nodesq.p; m.d.bmagq = bq;
+    }
+  }
   const size_t nt = br.order.size();
   if (f32ok) {
     std::vector<float> tri(std::max<size_t>(nt, 1) * 12, 0.f);
@@ -821,7 +920,7 @@ int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info) {
   memset(info, 0, sizeof *info);
   for (auto &kv : ctx->meshes) {
     const MeshRec &m = kv.second;
-    info->hbm_bytes += m.nodes.bytes + m.nodes4.bytes + m.tri.bytes + m.N.bytes + m.idx.bytes + m.group.bytes;
+    info->hbm_bytes += m.nodes.bytes + m.nodes4.bytes + m.nodes4q.bytes + m.nodesq.bytes + m.tri.bytes + m.N.bytes + m.idx.bytes + m.group.bytes;
     info->blas_nodes += m.nnodes; info->blas_tris += m.nfaces;
     info->blas_max_depth = std::max<uint32_t>(info->blas_max_depth, (uint32_t)m.max_depth);
   }
@@ -837,9 +936,11 @@ int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent) {
   CK(cudaSetDevice(ctx->device));
   if (int rc = commit_scene(ctx)) return rc;
   std::vector<DevBuf *> all = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights};
-  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.tri, &m.N, &m.idx, &m.group}) all.push_back(b); }
+  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.nodes4q, &m.nodesq, &m.tri, &m.N, &m.idx, &m.group}) all.push_back(b); }
   for (auto &b : ctx->d_group_nodes) all.push_back(&b);
   for (auto &b : ctx->d_group_nodes4) all.push_back(&b);
+  for (auto &b : ctx->d_group_nodes4q) all.push_back(&b);
+  for (auto &b : ctx->d_group_nodesq) all.push_back(&b);
   for (auto &b : ctx->d_group_order) all.push_back(&b);
   uint64_t total = 0;
   for (DevBuf *b : all) {
