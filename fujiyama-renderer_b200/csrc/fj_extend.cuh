@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   const char *nodes = nullptr;                  // 4-wide nodes of the tree being walked: Node128, or NodeQ64 when QUANT
   unsigned n_steps = 0, n_tris = 0;             // warp totals (every lane carries the same value)
 
+#pragma unroll 1
   for (;;) {
     // ---- refill idle lanes from the queue head
     const unsigned idle = __ballot_sync(FULL, node == IDLE);
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
     }
 
     // ---- phase A: 4-wide inner nodes, nearest hit child first
+#pragma unroll 1
     for (;;) {
       const bool want = node >= 0;
       const unsigned wm = __ballot_sync(FULL, want);
@@ -151,21 +153,23 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           const unsigned sw = __float_as_uint(A.a.w);
           const float six = __fmul_rn(__uint_as_float(sw & 0xffff0000u), br.ix), siy = __fmul_rn(__uint_as_float(sw << 16), br.iy);
           const float siz = __fmul_rn(Q.b.z, br.iz);
-          const float bx0 = fmaf(A.a.x, br.ix, br.lx), bx1 = fmaf(A.a.x, br.ix, br.hx);
-          const float by0 = fmaf(A.a.y, br.iy, br.ly), by1 = fmaf(A.a.y, br.iy, br.hy);
-          const float bz0 = fmaf(A.a.z, br.iz, br.lz), bz1 = fmaf(A.a.z, br.iz, br.hz);
+          // near / far plane by direction sign, resolved once per node on the packed words (not per child, and not by min/max:
+          // unused slots hold an inverted box that must stay a miss).  br.l* / br.h* are the constants of the lo / hi plane.
+          const bool gx = br.ix < 0.f, gy = br.iy < 0.f, gz = br.iz < 0.f;
+          const float bnx = fmaf(A.a.x, br.ix, gx ? br.hx : br.lx), bfx = fmaf(A.a.x, br.ix, gx ? br.lx : br.hx);
+          const float bny = fmaf(A.a.y, br.iy, gy ? br.hy : br.ly), bfy = fmaf(A.a.y, br.iy, gy ? br.ly : br.hy);
+          const float bnz = fmaf(A.a.z, br.iz, gz ? br.hz : br.lz), bfz = fmaf(A.a.z, br.iz, gz ? br.lz : br.hz);
           const unsigned qlx = __float_as_uint(A.b.x), qhx = __float_as_uint(A.b.y), qly = __float_as_uint(A.b.z), qhy = __float_as_uint(A.b.w);
           const unsigned qlz = __float_as_uint(Q.a.x), qhz = __float_as_uint(Q.a.y);
+          const unsigned qnx = gx ? qhx : qlx, qfx = gx ? qlx : qhx, qny = gy ? qhy : qly, qfy = gy ? qly : qhy, qnz = gz ? qhz : qlz, qfz = gz ? qlz : qhz;
           ch = make_int4(__float_as_int(Q.a.z), __float_as_int(Q.a.w), __float_as_int(Q.b.x), __float_as_int(Q.b.y));
-          // near / far plane by direction sign (not min/max: unused slots hold an inverted box that must stay a miss)
-          const bool gx = br.ix < 0.f, gy = br.iy < 0.f, gz = br.iz < 0.f;
 #define FJ_CHILD(KEY, K)                                                                                                        \
           {                                                                                                                        \
-            const float x0 = fmaf((float)((qlx >> (8 * K)) & 255u), six, bx0), x1 = fmaf((float)((qhx >> (8 * K)) & 255u), six, bx1); \
-            const float y0 = fmaf((float)((qly >> (8 * K)) & 255u), siy, by0), y1 = fmaf((float)((qhy >> (8 * K)) & 255u), siy, by1); \
-            const float z0 = fmaf((float)((qlz >> (8 * K)) & 255u), siz, bz0), z1 = fmaf((float)((qhz >> (8 * K)) & 255u), siz, bz1); \
-            const float nr = fmaxf(fmaxf(gx ? x1 : x0, gy ? y1 : y0), fmaxf(gz ? z1 : z0, tn));                                   \
-            const float fr_ = fminf(fminf(gx ? x0 : x1, gy ? y0 : y1), fminf(gz ? z0 : z1, tf));                                  \
+            const float nx_ = fmaf((float)((qnx >> (8 * K)) & 255u), six, bnx), fx_ = fmaf((float)((qfx >> (8 * K)) & 255u), six, bfx); \
+            const float ny_ = fmaf((float)((qny >> (8 * K)) & 255u), siy, bny), fy_ = fmaf((float)((qfy >> (8 * K)) & 255u), siy, bfy); \
+            const float nz_ = fmaf((float)((qnz >> (8 * K)) & 255u), siz, bnz), fz_ = fmaf((float)((qfz >> (8 * K)) & 255u), siz, bfz); \
+            const float nr = fmaxf(fmaxf(nx_, ny_), fmaxf(nz_, tn));                                                              \
+            const float fr_ = fminf(fminf(fx_, fy_), fminf(fz_, tf));                                                             \
             KEY = nr <= fr_ ? ((__float_as_uint(nr) & ~3u) | K##u) : MISS;                                                        \
           }
           FJ_CHILD(key0, 0) FJ_CHILD(key1, 1) FJ_CHILD(key2, 2) FJ_CHILD(key3, 3)
@@ -192,11 +196,19 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
         const unsigned kmin = min(min(key0, key1), min(key2, key3));
         if (kmin != MISS) {
           const unsigned w = kmin & 3u;
-          if (key0 != MISS && w != 0u) stack[sp++] = ch.x;
-          if (key1 != MISS && w != 1u) stack[sp++] = ch.y;
-          if (key2 != MISS && w != 2u) stack[sp++] = ch.z;
-          if (key3 != MISS && w != 3u) stack[sp++] = ch.w;
+          int top = -1;
+          if (key0 != MISS && w != 0u) { stack[sp++] = ch.x; top = ch.x; }
+          if (key1 != MISS && w != 1u) { stack[sp++] = ch.y; top = ch.y; }
+          if (key2 != MISS && w != 2u) { stack[sp++] = ch.z; top = ch.z; }
+          if (key3 != MISS && w != 3u) { stack[sp++] = ch.w; top = ch.w; }
           node = (w & 2u) ? ((w & 1u) ? ch.w : ch.z) : ((w & 1u) ? ch.y : ch.x);
+          // the traversal is bound by the latency of dependent node fetches: start the fetch of the node that will be popped
+          // next (the new stack top) while the nearest child is walked
+          if (a.prefetch && top >= 0) {
+            const char *pa = nodes + (QUANT ? 64 : 128) * (size_t)top;
+            if (a.prefetch == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(pa));
+            else asm volatile("prefetch.global.L2 [%0];" :: "l"(pa));
+          }
         } else node = sp > 0 ? stack[--sp] : DONE;
         // speculative traversal: park the first triangle leaf and keep descending.  Inside a BLAS the bottom stack entry is
         // SENTINEL, so a negative reference there is SENTINEL or a triangle leaf and the pop below cannot underflow.

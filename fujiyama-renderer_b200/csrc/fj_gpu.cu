@@ -408,8 +408,9 @@ void launch_extend3(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks, int
 // a cross-check), 2 the shared-memory-state version, 3 (default) the quad-per-ray version; FJGPU_EXTEND_MINBLOCKS = resident CTAs per SM.
 void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
   a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
-  a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 12)));
+  a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 16)));
   a.park = env_int("FJGPU_PARK", 1);
+  a.prefetch = env_int("FJGPU_PREFETCH", 0);
   int version = env_int("FJGPU_EXTEND", 2);
   const int stride = std::max(15, ctx->stack_need) | 1;             // odd: the ray stacks start in different banks
   if (version >= 3 && (size_t)FJ_QR * stride * sizeof(int) > 40 * 1024) version = 2;     // tree too deep for the shared-memory stacks

@@ -283,6 +283,7 @@ struct RenderArgs {
   unsigned long long *work;               // megakernel: global work counter (units of 32 slots)
   RayRec *queue[2]; HitRec *hits; QueueCtl *ctl; uint32_t capacity; int cur;     // wavefront
   int refill, phase_a_min, park;          // k_extend scheduling: refill / phase-A thresholds (lanes), speculative leaf parking
+  int prefetch;                           // k_extend2: 1 = prefetch the new stack top into L1, 2 = into L2, 0 = off
   // ray sorting between bounces: counting sort of the next queue by (direction octant | origin cell)
   unsigned int *hist;                     // sort_bins + 1 counters (null = no sorting)
   unsigned int *perm;                     // order in which k_extend walks queue[cur] (null = queue order)

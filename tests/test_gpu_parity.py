@@ -310,3 +310,107 @@ def test_big_mesh_property(sk, device):
                                   sk.dptr(rt), sk.dptr(ru), sk.dptr(rv), sk.iptr(rp), sk.iptr(ri))
     sk.oracle().fjo_scene_free(sc)
     assert np.array_equal(t[sub], rt) and np.array_equal(inst[sub], ri)
+
+
+# ---------------------------------------------------------------------------------------------- extend-kernel variants
+def instanced16(sk):
+    """BASELINE config 4 in miniature: 16 instances of one mesh on the 4x4 grid of scenes/happy_buddhas.scn
+    (translate -1.5 i, 0, -1.5 j; rotate 0, 30 k, 0; scale .6) + a floor: a TLAS with inner nodes over a shared BLAS."""
+    from fujiyama_renderer_b200 import synth
+    d = sk.SceneDesc()
+    P, idx = synth.blob(24)
+    d.mesh("blob", P, idx)
+    Pq, iq = synth.quad(12.0, -0.7)
+    d.mesh("floor", Pq, iq)
+    d.shader("s", "plastic", diffuse=(.5, .5, .5))
+    k = 0
+    for i in range(4):
+        for j in range(4):
+            d.instance("o%d" % k, "blob", "s", T=(2.25 - 1.5 * i, 0, 2.25 - 1.5 * j), R=(0, 30 * k, 0), S=(.6, .6, .6))
+            k += 1
+    d.instance("f", "floor", "s")
+    d.light(0, T=(5, 12, 5), intensity=1.0)
+    d.cam.update(T=(0, 4, 9), R=(-25, 0, 0), fov=40)
+    d.ren.update(resolution=(96, 64), pixelsamples=(2, 2))
+    return d
+
+
+def soup(sk):
+    """BASELINE config 5 in miniature: S-random triangle soup (overlapping leaf boxes, no surface coherence)."""
+    from fujiyama_renderer_b200 import synth
+    d = sk.SceneDesc()
+    P, idx = synth.random_tris(5000, seed=1234)
+    d.mesh("soup", P * np.float32(3.0), idx)
+    d.shader("s", "constant")
+    d.instance("o", "soup", "s", R=(10, 20, 30))
+    d.cam.update(T=(0, 0, 6), fov=35)
+    d.ren.update(resolution=(64, 64), pixelsamples=(1, 1))
+    return d
+
+
+EXTEND_VARIANTS = {
+    "v1_registers": {"FJGPU_EXTEND": "1"},
+    "v2_float_nodes": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "0"},
+    "v2_quantised_6": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_EXTEND_MINBLOCKS": "6"},
+    "v2_quantised_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
+    "v3_quad_per_ray": {"FJGPU_EXTEND": "3"},
+    "v3_quad_per_ray_12": {"FJGPU_EXTEND": "3", "FJGPU_EXTEND_MINBLOCKS": "12", "FJGPU_REFILL": "32", "FJGPU_PHASE_A_MIN": "32"},
+}
+
+
+@pytest.mark.parametrize("scene", ["multi", "instanced16", "soup"])
+def test_extend_variants_bit_exact(sk, device, scene, monkeypatch):
+    """Every closest-hit kernel (register-resident, shared-memory state with FP32 or 8-bit quantised nodes, quad-per-ray)
+    returns the oracle's hits bit for bit, on a multi-instance scene, a 17-instance TLAS and a triangle soup, with
+    clipped, unnormalised and axis-parallel rays."""
+    desc = {"multi": golden_scenes.SCENES["multi"], "instanced16": lambda: instanced16(sk), "soup": lambda: soup(sk)}[scene]()
+    st = desc.to_structs()
+    n = 30000
+    o, d = random_rays(n, 21, radius=5.0)
+    d[::7, 0] = 0.0                                     # axis-parallel components
+    d[::11, 1] = 0.0
+    tmin = np.full(n, 1e-3)
+    tmax = np.full(n, 1000.0)
+    tmax[::5] = 4.0
+    sc = sk.oracle_scene(st)
+    rt, ru, rv = np.zeros(n), np.zeros(n), np.zeros(n)
+    rp, ri = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    assert sk.oracle().fjo_trace_closest(sc, 0, n, sk.dptr(o), sk.dptr(d), sk.dptr(tmin), sk.dptr(tmax),
+                                         sk.dptr(rt), sk.dptr(ru), sk.dptr(rv), sk.iptr(rp), sk.iptr(ri)) == 0
+    sk.oracle().fjo_scene_free(sc)
+    assert 0.02 * n < int((ri >= 0).sum()) < 0.99 * n
+    dev = device.Device(0)
+    dev.load_structs(st)
+    try:
+        for name, env in EXTEND_VARIANTS.items():
+            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            t, u, v, p, i = dev.trace_closest(0, o, d, tmin, tmax, 0)
+            assert np.array_equal(i, ri), name
+            assert np.array_equal(t, rt), name
+            same = p == rp
+            assert same.mean() > 0.999, name
+            assert np.array_equal(u[same], ru[same]) and np.array_equal(v[same], rv[same]), name
+    finally:
+        dev.close()
+
+
+@pytest.mark.parametrize("name", ["multi", "pt_branching"])
+def test_extend_variants_same_frame(sk, device, name, monkeypatch):
+    """Whole frames (shadow rays, mirror bounces, branching path trees) are bit-identical whichever extend kernel traces
+    them, and so are the ray counts."""
+    desc = golden_scenes.SCENES[name]()
+    frames = {}
+    for vname, env in EXTEND_VARIANTS.items():
+        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        img, stats = gpu_render(device, desc)
+        frames[vname] = (img, stats.rays)
+    ref_img, ref_rays = frames["v1_registers"]
+    for vname, (img, rays) in frames.items():
+        assert rays == ref_rays, vname
+        assert np.array_equal(img, ref_img), vname
