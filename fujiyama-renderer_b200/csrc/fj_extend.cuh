@@ -19,11 +19,13 @@ namespace fj {
 
 struct ExtShared {
   double ox[FJ_XT], oy[FJ_XT], oz[FJ_XT], dx[FJ_XT], dy[FJ_XT], dz[FJ_XT];    // ray in the space being traversed (object space inside a BLAS)
-  double tmin[FJ_XT], best_t[FJ_XT], best_u[FJ_XT], best_v[FJ_XT];
+  double tmin[FJ_XT], best_t[FJ_XT];
   const void *tri[FJ_XT];                                                     // triangle packets of the current mesh (tri32 or tri64)
-  int cur_inst[FJ_XT], best_inst[FJ_XT], best_prim[FJ_XT], leaf[FJ_XT];
+  int cur_inst[FJ_XT], leaf[FJ_XT];
   unsigned ridx[FJ_XT];
 };
+// 84 B per lane = 10.75 KB per CTA: 7 (or 8) CTAs fit the 100 KB shared-memory carveout and leave 128 KB of L1.  The
+// rest of the best hit (u, v, face, instance) goes straight to the ray's HitRec in global memory whenever it improves.
 
 // 256-bit read-only global load (sm_100: LDG.E.ENL2.256.CONSTANT).  The closest-hit kernel is bound by L1 wavefronts —
 // every lane reads its own node, so each load instruction costs one wavefront per lane whatever its width; a 128-B
@@ -70,7 +72,7 @@ __device__ __forceinline__ bool tri_intersect_smem(const D3 &v0, const D3 &v1, c
 }
 
 // Lane state word: what the node loop has to know about the exact half of the state.
-enum { XS_BLAS = 1, XS_WORLD = 2, XS_TRI64 = 4, XS_LEAF = 8 };
+enum { XS_BLAS = 1, XS_WORLD = 2, XS_TRI64 = 4, XS_LEAF = 8, XS_FOUND = 16 };
 
 template <int MINB, bool STATS, bool QUANT>
 __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
@@ -111,8 +113,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           const unsigned ridx = a.perm ? a.perm[i] : i;
           const RayRec &r = rays[ridx];
           const double tmin = r.tmin, tmax = r.tmax;
-          S.ridx[tid] = ridx; S.tmin[tid] = tmin; S.best_t[tid] = tmax; S.best_u[tid] = 0; S.best_v[tid] = 0;
-          S.best_inst[tid] = -1; S.best_prim[tid] = -1; S.cur_inst[tid] = -1;
+          S.ridx[tid] = ridx; S.tmin[tid] = tmin; S.best_t[tid] = tmax; S.cur_inst[tid] = -1;
           tn = __double2float_rd(tmin); tf = __double2float_ru(tmax);
           const DGroup grp = sc.groups[r.target];
           nodes = (const char *)(QUANT ? grp.nodesq : grp.nodes4); sp = 0; node = 0;
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
       if (st & XS_LEAF) {
         const int ref = ~S.leaf[tid];
         first = ref >> 3; cnt = (ref & 7) + 1;
-        tmin = S.tmin[tid]; best_t = S.best_t[tid]; found = S.best_inst[tid] >= 0; tp_ = S.tri[tid];
+        tmin = S.tmin[tid]; best_t = S.best_t[tid]; found = (st & XS_FOUND) != 0; tp_ = S.tri[tid];
         st &= ~XS_LEAF;
       }
       for (int k = 0;; k++) {
@@ -252,13 +253,17 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           // RayInRange (src/fj_ray.h:29-32): tmin <= t <= tmax; best_t starts at tmax, so `t <= best_t` is the upper test
           if (tri_intersect_smem(v0, v1, v2, S, tid, &t, &u, &v) && tmin <= t && t <= best_t) {
             bool better = !found || t < best_t;
-            if (!better) {                         // exact tie in t: lower instance, then higher face id
-              const int ci = S.cur_inst[tid], bi = S.best_inst[tid];
-              better = ci < bi || (ci == bi && prim > S.best_prim[tid]);
+            if (!better) {                         // exact tie in t: lower instance, then higher face id (read back from the record)
+              const HitRec *cur = a.hits + S.ridx[tid];
+              const int ci = S.cur_inst[tid], bi = cur->inst;
+              better = ci < bi || (ci == bi && prim > cur->prim);
             }
             if (better) {
-              found = true; best_t = t;
-              S.best_t[tid] = t; S.best_u[tid] = u; S.best_v[tid] = v; S.best_prim[tid] = prim; S.best_inst[tid] = S.cur_inst[tid];
+              found = true; best_t = t; st |= XS_FOUND;
+              S.best_t[tid] = t;
+              HitRec hr; hr.t = t; hr.u = u; hr.v = v; hr.prim = prim; hr.inst = S.cur_inst[tid];
+              uint4 *dst = reinterpret_cast<uint4 *>(a.hits + S.ridx[tid]); const uint4 *src = reinterpret_cast<const uint4 *>(&hr);
+              dst[0] = src[0]; dst[1] = src[1];
               tf = __double2float_ru(t);
             }
           }
@@ -270,10 +275,11 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
     const bool special = node < 0 && node != IDLE;
     if (__any_sync(FULL, special)) {
       if (special) {
-        if (node == DONE) {                        // traversal finished: write the hit record
-          const int bi = S.best_inst[tid];
-          HitRec hr; hr.t = bi >= 0 ? S.best_t[tid] : FJ_REAL_MAX; hr.u = S.best_u[tid]; hr.v = S.best_v[tid]; hr.prim = S.best_prim[tid]; hr.inst = bi;
-          store_hit_cs(a.hits + S.ridx[tid], hr);
+        if (node == DONE) {                        // traversal finished: a hit is already in the ray's record, a miss is written now
+          if (!(st & XS_FOUND)) {
+            HitRec hr; hr.t = FJ_REAL_MAX; hr.u = 0; hr.v = 0; hr.prim = -1; hr.inst = -1;
+            store_hit_cs(a.hits + S.ridx[tid], hr);
+          }
           node = IDLE;
         } else if (node == SENTINEL) {             // the instance's BLAS is done: back to the instance tree (its nodes and box
           st &= ~(XS_BLAS | XS_WORLD);             // ray are fetched again only if an inner node of that tree is still to be visited)
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           nodes = (const char *)(QUANT ? m.nodesq : m.nodes4);
           const bool t64 = m.tri32 == nullptr;
           S.tri[tid] = t64 ? (const void *)m.tri64 : (const void *)m.tri32;
-          st = XS_BLAS | (t64 ? XS_TRI64 : 0);
+          st = (st & XS_FOUND) | XS_BLAS | (t64 ? XS_TRI64 : 0);
           stack[sp++] = SENTINEL;
           node = 0;
         }

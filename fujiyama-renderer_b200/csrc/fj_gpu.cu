@@ -384,7 +384,8 @@ void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   // shared-memory carveout: MINB CTAs x (static shared memory + 1 KB the driver reserves per CTA), the rest stays L1
   static bool configured = false;
   if (!configured) {
-    const int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * (sizeof(fj::ExtShared) + 1024) / (228.0 * 1024)));
+    int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * (sizeof(fj::ExtShared) + 1024) / (228.0 * 1024)));
+    pct = env_int("FJGPU_CARVEOUT_PCT", pct);
     cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     configured = true;
   }
