@@ -220,6 +220,12 @@ def own_arm(args, builder, kw, desc):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the renderer has no CPU fallback")
     torch.cuda.set_device(local)
+    # everything but the final JSON line is kept off stdout: libfjscene prints the reference's progress lines there and NCCL
+    # its version banner
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(devnull, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -234,9 +240,6 @@ def own_arm(args, builder, kw, desc):
     text = getattr(scenes, builder)(wd, "/opt/fujiyama/lib", **kw)
     res, rate = kw["res"], kw["rate"]
     s = fujiyama.Session(echo=False, device=local, rank=rank, world_size=world)
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)                     # libfjscene prints the reference's progress lines on stdout
 
     def frame():
         s.run("RenderScene ren1\n")
