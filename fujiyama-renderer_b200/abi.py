@@ -82,7 +82,8 @@ class SceneInfo(C.Structure):
     _fields_ = [("hbm_bytes", C.c_uint64), ("blas_nodes", C.c_uint64),
                 ("blas_tris", C.c_uint64), ("tlas_nodes", C.c_uint64),
                 ("instances", C.c_uint64), ("blas_max_depth", C.c_uint32),
-                ("_pad", C.c_uint32), ("build_seconds", C.c_double)]
+                ("_pad", C.c_uint32), ("build_seconds", C.c_double),
+                ("device_build_seconds", C.c_double)]
 
 
 # every symbol include/fjgpu.h declares (tests check the built library exports all of them)

@@ -1,5 +1,6 @@
 // fj_bvh.cc — binned-SAH BVH2 builder (host, multi-threaded).  See fj_bvh.h for the layout.
 #include "fj_bvh.h"
+#include "fj_quant.h"
 
 #include <algorithm>
 #include <atomic>
@@ -279,56 +280,8 @@ void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int 
 
 bool quantize_nodes(const Node128 *in, size_t n, NodeQ64 *out, float *bmag) {
   double mag = 0;
-  for (size_t i = 0; i < n; i++) {
-    const Node128 &w = in[i];
-    NodeQ64 &q = out[i];
-    memset(&q, 0, sizeof q);
-    const float *lo[3] = {w.lox, w.loy, w.loz}, *hi[3] = {w.hix, w.hiy, w.hiz};
-    bool valid[4]; int nvalid = 0;
-    for (int k = 0; k < 4; k++) { valid[k] = !(w.lox[k] > w.hix[k]) && w.lox[k] < 3e38f; nvalid += valid[k]; }
-    uint32_t sbits[3];
-    for (int a = 0; a < 3; a++) {
-      double plo = 1e300, phi = -1e300;
-      for (int k = 0; k < 4; k++) if (valid[k]) { plo = std::min(plo, (double)lo[a][k]); phi = std::max(phi, (double)hi[a][k]); }
-      if (nvalid == 0) { plo = phi = 0; }
-      const float p = (float)plo;                       // exact: plo is one of the float planes
-      // smallest power of two s with extent <= 254 s (one step of headroom for the outward rounding below)
-      const double extent = phi - plo;
-      int e = -100;
-      if (extent > 0) { int ex; std::frexp(extent / 254.0, &ex); e = ex; if (std::ldexp(1.0, e - 1) * 254.0 >= extent) e--; }
-      if (e < -60) e = -60;                             // keeps s / d inside the normal FP32 range for any direction
-      uint32_t qlo = 0, qhi = 0;
-      double sc = 0;
-      for (;; e++) {                                    // (one more step only if the outward rounding ran out of range)
-        if (e > 60) return false;
-        sc = std::ldexp(1.0, e);
-        qlo = qhi = 0;
-        bool fits = true;
-        for (int k = 0; k < 4 && fits; k++) {
-          int l = 255, h = 0;                           // unused slot: inverted box
-          if (valid[k]) {
-            l = (int)std::floor(((double)lo[a][k] - plo) / sc); h = (int)std::ceil(((double)hi[a][k] - plo) / sc);
-            if (l > 255) l = 255;
-            if (h < 0) h = 0;
-            while (l > 0 && plo + l * sc > (double)lo[a][k]) l--;
-            while (h < 255 && plo + h * sc < (double)hi[a][k]) h++;
-            if (l < 0) l = 0;
-            if (plo + h * sc < (double)hi[a][k]) fits = false;
-          }
-          qlo |= (uint32_t)l << (8 * k); qhi |= (uint32_t)h << (8 * k);
-        }
-        if (fits) break;
-      }
-      for (int k = 0; k < 4; k++) if (valid[k])
-        mag = std::max(mag, std::max(std::fabs(plo + ((qlo >> (8 * k)) & 255) * sc), std::fabs(plo + ((qhi >> (8 * k)) & 255) * sc)));
-      memcpy(&q.w[a], &p, 4);
-      const float sf = (float)sc; memcpy(&sbits[a], &sf, 4);
-      q.w[a == 0 ? 4 : (a == 1 ? 6 : 8)] = qlo; q.w[a == 0 ? 5 : (a == 1 ? 7 : 9)] = qhi;
-    }
-    q.w[3] = (sbits[0] & 0xffff0000u) | (sbits[1] >> 16);
-    q.w[14] = sbits[2] & 0xffff0000u;
-    for (int k = 0; k < 4; k++) q.w[10 + k] = (uint32_t)w.c[k];
-  }
+  for (size_t i = 0; i < n; i++)
+    if (!quantize_one(in[i], out[i], &mag)) return false;
   *bmag = round_up(mag * (1.0 + 1e-6));
   return true;
 }

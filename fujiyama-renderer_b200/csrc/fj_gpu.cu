@@ -7,6 +7,7 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
 #include "fjgpu.h"
 #include "fj_bvh.h"
+#include "fj_build.h"
 #include "fj_kernels.cuh"
 #include "fj_extend.cuh"
 #include "fj_extend_quad.cuh"
@@ -68,6 +69,7 @@ struct fjgpu_context {
   bool quant_ok = true;        // every tree of the committed scene has a quantised (NodeQ64) copy
   int stack_need = 0;          // worst-case traversal stack of k_extend3 for the committed scene (entries)
   double build_seconds = 0;
+  double device_build_seconds = 0;    // part of build_seconds spent inside fj_device_build (CUDA events)
 
   // frame resources
   DevBuf d_samples, d_tiles, d_blocks, d_jitter, d_counters, d_frame, d_queue[2], d_hits, d_ctl, d_hist, d_perm;
@@ -700,6 +702,44 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
   bool f32ok = true;
   for (size_t i = 0; i < 3 * (size_t)nverts && f32ok; i++) f32ok = ((double)(float)P[i] == P[i]);
   if (env_int("FJGPU_FORCE_TRI64", 0)) f32ok = false;
+  // ---- device build (FJGPU_BUILD=device): linear BVH in HBM, fj_build.cu.  The host builder (binned SAH, below) stays the
+  // default because its trees are walked faster; the device builder is for time-to-first-pixel on large meshes.
+  {
+    const char *bm = getenv("FJGPU_BUILD");
+    if (bm && std::string(bm) == "device" && nfaces >= env_int("FJGPU_BUILD_DEVICE_MIN", 1024)) {
+      DevBuf dP;
+      if (int rc = dev_upload(ctx, dP, P, (size_t)nverts * 24)) return rc;
+      if (int rc = dev_upload(ctx, m.idx, idx3, (size_t)nfaces * 12, true)) { dP.release(); return rc; }
+      FjDeviceBuild db; std::string berr;
+      const int brc = fj_device_build(ctx->stream, (const double *)dP.p, nverts, (const int32_t *)m.idx.p, nfaces, env_int("FJGPU_MAX_LEAF", 4),
+                                      (float)env_int("FJGPU_LEAF_COST_X10", 15) / 10.f, env_int("FJGPU_FORCE_TRI64", 0) != 0, &db, &berr);
+      dP.release();
+      if (brc == 0 && (db.max_depth + 8 > FJ_STACK || 3 * db.max_depth4 + 16 > FJ_STACK4)) {     // too deep for the traversal stacks: host build
+        for (void *q : {db.nodes, db.nodes4, db.nodes4q, db.nodesq, db.tri}) cudaFree(q);
+      } else if (brc == 0) {
+        m.nodes.p = db.nodes; m.nodes.bytes = db.nodes_bytes; m.nodes4.p = db.nodes4; m.nodes4.bytes = db.nodes4_bytes;
+        m.nodes4q.p = db.nodes4q; m.nodes4q.bytes = db.nodes4q_bytes; m.nodesq.p = db.nodesq; m.nodesq.bytes = db.nodesq_bytes;
+        m.tri.p = db.tri; m.tri.bytes = db.tri_bytes;
+        for (int a = 0; a < 3; a++) { m.bmin[a] = db.bmin[a]; m.bmax[a] = db.bmax[a]; }
+        m.nnodes = db.nnodes; m.max_depth = db.max_depth; m.max_depth4 = db.max_depth4; m.nnodes4 = db.nnodes4; m.stack_need4 = db.stack_need4;
+        memset(&m.d, 0, sizeof m.d);
+        m.d.nodes = (const float4 *)m.nodes.p; m.d.nodes4 = (const float4 *)m.nodes4.p; m.d.nodes4q = (const float4 *)m.nodes4q.p;
+        if (db.quant_ok) { m.d.nodesq = (const float4 *)m.nodesq.p; m.d.bmagq = db.bmagq; }
+        if (db.tri64) m.d.tri64 = (const double *)m.tri.p; else m.d.tri32 = (const float4 *)m.tri.p;
+        if (N) { if (int rc = dev_upload(ctx, m.N, N, (size_t)nverts * 24, true)) return rc; m.d.N = (const double *)m.N.p; }
+        m.d.idx = (const int32_t *)m.idx.p;
+        if (face_group_id) { if (int rc = dev_upload(ctx, m.group, face_group_id, (size_t)nfaces * 4, true)) return rc; m.d.group = (const int32_t *)m.group.p; }
+        { int l = 0; while ((1ll << l) < (long long)std::max(nfaces, 1)) l++; m.d.log2_tris = l; }
+        m.d.bmag = db.bmag;
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->dirty = true;
+        ctx->build_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ctx->device_build_seconds += db.seconds;
+        return FJGPU_OK;
+      }
+      // any failure falls through to the host builder
+    }
+  }
   std::vector<fjb::Aabb> boxes(nfaces);
   for (int a = 0; a < 3; a++) { m.bmin[a] = 1.7976931348623157e308; m.bmax[a] = -1.7976931348623157e308; }
   for (int f = 0; f < nfaces; f++) {
@@ -930,6 +970,7 @@ int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info) {
   for (auto &b : ctx->d_group_nodes) info->hbm_bytes += b.bytes;
   info->tlas_nodes = ctx->tlas_nodes; info->instances = ctx->inst.size();
   info->build_seconds = ctx->build_seconds;
+  info->device_build_seconds = ctx->device_build_seconds;
   return FJGPU_OK;
 }
 

@@ -230,6 +230,7 @@ typedef struct fjgpu_scene_info {
   uint64_t blas_nodes, blas_tris, tlas_nodes, instances;
   uint32_t blas_max_depth, _pad;
   double   build_seconds;   /* host time spent in BVH construction since context creation */
+  double   device_build_seconds;   /* part of it spent in the device builder (FJGPU_BUILD=device; CUDA events), 0 for host builds */
 } fjgpu_scene_info;
 int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info);
 

@@ -414,3 +414,79 @@ def test_extend_variants_same_frame(sk, device, name, monkeypatch):
     for vname, (img, rays) in frames.items():
         assert rays == ref_rays, vname
         assert np.array_equal(img, ref_img), vname
+
+
+# ---------------------------------------------------------------------------------------------- device BVH build (§8f row 2)
+@pytest.mark.parametrize("scene", ["plastic", "multi", "soup"])
+def test_device_built_bvh_gives_the_same_hits_and_frames(sk, device, scene, monkeypatch):
+    """FJGPU_BUILD=device (linear BVH built in HBM, fj_build.cu): every traversal kernel still returns the oracle's closest
+    hits bit for bit, and whole frames are bit-identical to the frames of the host-built (binned SAH) trees."""
+    desc = {"plastic": golden_scenes.SCENES["plastic"], "multi": golden_scenes.SCENES["multi"], "soup": lambda: soup(sk)}[scene]()
+    st = desc.to_structs()
+    img_host, stats_host = gpu_render(device, desc, st=st)
+    n = 20000
+    o, d = random_rays(n, 33, radius=5.0)
+    tmin = np.full(n, 1e-3)
+    tmax = np.full(n, 1000.0)
+    tmax[::4] = 4.0
+    sc = sk.oracle_scene(st)
+    rt, ru, rv = np.zeros(n), np.zeros(n), np.zeros(n)
+    rp, ri = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    assert sk.oracle().fjo_trace_closest(sc, 0, n, sk.dptr(o), sk.dptr(d), sk.dptr(tmin), sk.dptr(tmax),
+                                         sk.dptr(rt), sk.dptr(ru), sk.dptr(rv), sk.iptr(rp), sk.iptr(ri)) == 0
+    sk.oracle().fjo_scene_free(sc)
+    monkeypatch.setenv("FJGPU_BUILD", "device")
+    monkeypatch.setenv("FJGPU_BUILD_DEVICE_MIN", "2")
+    dev = device.Device(0)
+    try:
+        dev.load_structs(st)
+        assert dev.info().device_build_seconds > 0            # the device builder really ran
+        for flags in (0, 1, 2):                               # wavefront kernel, megakernel with FP64 / FP32 boxes
+            t, u, v, p, i = dev.trace_closest(0, o, d, tmin, tmax, flags)
+            assert np.array_equal(i, ri) and np.array_equal(t, rt), flags
+            same = p == rp
+            assert same.mean() > 0.999
+            assert np.array_equal(u[same], ru[same]) and np.array_equal(v[same], rv[same])
+        for name, env in EXTEND_VARIANTS.items():
+            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v_ in env.items():
+                monkeypatch.setenv(k, v_)
+            t, u, v, p, i = dev.trace_closest(0, o, d, tmin, tmax, 0)
+            assert np.array_equal(i, ri) and np.array_equal(t, rt), name
+        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN"):
+            monkeypatch.delenv(k, raising=False)
+        img_dev, stats_dev = dev.render(st["params"], desc.tiles())
+    finally:
+        dev.close()
+    assert stats_dev.rays == stats_host.rays
+    assert np.array_equal(img_dev, img_host)
+
+
+def test_device_build_of_a_million_triangles(sk, device, monkeypatch):
+    """Full-size build on the device: same hits as the host-built tree on 200 k rays, and the build itself is timed."""
+    from fujiyama_renderer_b200 import synth
+    P, idx = synth.blob(synth.BLOB_N["1M"])
+    desc = sk.SceneDesc()
+    desc.mesh("blob", P, idx)
+    desc.shader("s", "constant")
+    desc.instance("o", "blob", "s", R=(20, 30, 0))
+    st = desc.to_structs()
+    n = 200000
+    o, d = random_rays(n, 5)
+    dev = device.Device(0)
+    dev.load_structs(st)
+    a = dev.trace_closest(0, o, d, 1e-3, 1000., 0)
+    host_s = dev.info().build_seconds
+    dev.close()
+    monkeypatch.setenv("FJGPU_BUILD", "device")
+    dev = device.Device(0)
+    dev.load_structs(st)
+    b = dev.trace_closest(0, o, d, 1e-3, 1000., 0)
+    info = dev.info()
+    dev.close()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert 0 < info.device_build_seconds < host_s
+    print("BVH build of %d triangles: host %.3f s, device %.4f s (%.0fx)" % (len(idx), host_s, info.device_build_seconds,
+                                                                             host_s / info.device_build_seconds))
