@@ -13,7 +13,7 @@ LIBFJGPU = os.path.join(HERE, "csrc", "libfjgpu.so")
 LIBFJSCENE = os.path.join(HERE, "host", "libfjscene.so")
 
 FJGPU_MAX_SHADING_GROUPS = 8
-SHADER_NONE, SHADER_CONSTANT, SHADER_PLASTIC, SHADER_PATHTRACING = 0, 1, 2, 3
+SHADER_NONE, SHADER_CONSTANT, SHADER_PLASTIC, SHADER_PATHTRACING, SHADER_GLASS = 0, 1, 2, 3, 4
 LIGHT_POINT, LIGHT_GRID, LIGHT_SPHERE, LIGHT_DOME = 0, 1, 2, 3
 FLAG_FP64_BOXES, FLAG_MEGAKERNEL = 1, 2
 

@@ -293,6 +293,7 @@ void frontier(const fjgpu_context *ctx, const fjgpu_render_params *p, int *waves
   for (const fjgpu_shader &s : ctx->shaders) {
     int n = 0;
     if (s.kind == FJGPU_SHADER_PLASTIC) { if (s.do_reflect) { R = true; n = 1; } }
+    else if (s.kind == FJGPU_SHADER_GLASS) { R = true; F = true; n = 2; }          // always one mirror and one refracted child
     else if (s.kind == FJGPU_SHADER_PATHTRACING) {
       if (s.diffuse[0] > 0 || s.diffuse[1] > 0 || s.diffuse[2] > 0) { D = true; n++; }
       if (s.reflect[0] > 0 || s.reflect[1] > 0 || s.reflect[2] > 0) { R = true; n++; }
@@ -834,7 +835,7 @@ int fjgpu_groups_set(fjgpu_context *ctx, int32_t ngroups, const int32_t *group_o
 
 int fjgpu_shaders_set(fjgpu_context *ctx, int32_t n, const fjgpu_shader *shaders) {
   if (!ctx || n < 0 || (n > 0 && !shaders)) return fail(ctx, FJGPU_ERR_INVALID, "bad shader array");
-  for (int i = 0; i < n; i++) if (shaders[i].kind < FJGPU_SHADER_NONE || shaders[i].kind > FJGPU_SHADER_PATHTRACING)
+  for (int i = 0; i < n; i++) if (shaders[i].kind < FJGPU_SHADER_NONE || shaders[i].kind > FJGPU_SHADER_GLASS)
     return fail(ctx, FJGPU_ERR_UNSUPPORTED, "shader kind has no device implementation");
   ctx->shaders.assign(shaders, shaders + n); ctx->dirty = true;
   return FJGPU_OK;

@@ -222,6 +222,26 @@ struct Shading {
         c.rd = cur.rd;
       }
       Os = sh.opacity;
+    } else if (kind == 4) {                                        // GlassShader::evaluate, glass_shader.cc:88-133
+      const DShader &sh = sc.shaders[slot];
+      const double ior = ddiv(1., (double)sh.ior);
+      const double Kr = sl_fresnel(ray.d, N, ior), Kt = dsub(1., Kr);
+      if ((int)cur.rd + 1 <= fr.max_reflect) {                     // SlReflectContext + SlTrace(.0001, 1000); Cs += Kr * C_refl
+        const D3 R = normalize(sl_reflect(ray.d, N));
+        c.d[0] = R.x; c.d[1] = R.y; c.d[2] = R.z; c.tmin = .0001;
+        c.thr[0] = fmul(thr.r, (float)Kr); c.thr[1] = fmul(thr.g, (float)Kr); c.thr[2] = fmul(thr.b, (float)Kr);
+        c.node = cur.node * 4 + 2; c.target = in.reflect_target; c.type = RAY_REFLECT; c.rd = cur.rd + 1;
+        sink.spawn(c);
+        c.rd = cur.rd;
+      }
+      if ((int)cur.fd + 1 <= fr.max_refract) {                     // SlRefractContext; C_refr *= pow(filter_color, t_hit) when entering
+        const D3 Tr = normalize(sl_refract(ray.d, N, ior));
+        c.d[0] = Tr.x; c.d[1] = Tr.y; c.d[2] = Tr.z; c.tmin = .0001;
+        c.thr[0] = fmul(thr.r, (float)Kt); c.thr[1] = fmul(thr.g, (float)Kt); c.thr[2] = fmul(thr.b, (float)Kt);
+        c.filter_shader = (sh.do_color_filter && dot(ray.d, N) < 0) ? slot : -1;
+        c.node = cur.node * 4 + 3; c.target = in.refract_target; c.type = RAY_REFRACT; c.fd = cur.fd + 1;
+        sink.spawn(c);
+      }
     } else {                                                       // PathtracingShader::evaluate, pathtracing_shader.cc:125-257
       const DShader &sh = sc.shaders[slot];
       sink.add(fmul(thr.r, sh.emission[0]), fmul(thr.g, sh.emission[1]), fmul(thr.b, sh.emission[2]));

@@ -275,7 +275,7 @@ int read_ply(const std::string &path, Mesh *mesh) {
 
 // ---------------------------------------------------------------- shader property tables
 // name -> default; the first three components are used for vectors.  constant_shader.cc:29-33,
-// plastic_shader.cc:50-62, pathtracing_shader.cc:71-86.
+// plastic_shader.cc:50-62, pathtracing_shader.cc:71-86, glass_shader.cc:48-56.
 typedef std::map<std::string, std::array<double, 4>> PropMap;
 PropMap shader_defaults(int kind) {
   PropMap m;
@@ -284,6 +284,9 @@ PropMap shader_defaults(int kind) {
     m["diffuse"] = {.8, .8, .8, 0}; m["specular"] = {1, 1, 1, 0}; m["ambient"] = {1, 1, 1, 0}; m["roughness"] = {.1, 0, 0, 0};
     m["reflect"] = {1, 1, 1, 0}; m["ior"] = {1.4, 0, 0, 0}; m["opacity"] = {1, 0, 0, 0}; m["bump_amplitude"] = {1, 0, 0, 0};
     m["diffuse_map"] = {0, 0, 0, 0}; m["bump_map"] = {0, 0, 0, 0};
+  } else if (kind == FJGPU_SHADER_GLASS) {                                  // glass_shader.cc:48-56
+    m["diffuse"] = {0, 0, 0, 0}; m["specular"] = {1, 1, 1, 0}; m["ambient"] = {1, 1, 1, 0}; m["filter_color"] = {1, 1, 1, 0};
+    m["roughness"] = {.1, 0, 0, 0}; m["ior"] = {1.4, 0, 0, 0};
   } else {
     m["emission"] = {0, 0, 0, 0}; m["diffuse"] = {.8, .8, .8, 0}; m["specular"] = {0, 0, 0, 0}; m["ambient"] = {1, 1, 1, 0};
     m["transmit"] = {1, 1, 1, 0}; m["roughness"] = {.1, 0, 0, 0}; m["reflect"] = {0, 0, 0, 0}; m["refract"] = {0, 0, 0, 0};
@@ -305,6 +308,11 @@ fjgpu_shader flatten_shader(const Scene &sc, const Shader &s) {
     o.do_reflect = (o.reflect[0] > 0 || o.reflect[1] > 0 || o.reflect[2] > 0) ? 1 : 0;
     float ior = (float)P("ior")[0]; o.ior = (float)std::max(.001, (double)ior);
     float op = (float)P("opacity")[0]; o.opacity = op < 0 ? 0 : (op > 1 ? 1 : op);
+  } else if (kind == FJGPU_SHADER_GLASS) {                                  // glass_shader.cc:135-213
+    for (int k = 0; k < 3; k++) o.transmit[k] = (float)std::max(.001, P("filter_color")[k]);
+    o.do_color_filter = (o.transmit[0] == 1 && o.transmit[1] == 1 && o.transmit[2] == 1) ? 0 : 1;
+    float ior = (float)P("ior")[0]; o.ior = ior > 0 ? ior : 0;
+    o.opacity = 1;
   } else {                                                                  // pathtracing_shader.cc:305-420
     for (int k = 0; k < 3; k++) {
       o.emission[k] = clamp0(P("emission")[k]); o.diffuse[k] = clamp0(P("diffuse")[k]);
@@ -540,6 +548,7 @@ ID SiOpenPlugin(const char *filename) {
   if (base == "ConstantShader") kind = FJGPU_SHADER_CONSTANT;
   else if (base == "PlasticShader") kind = FJGPU_SHADER_PLASTIC;
   else if (base == "PathtracingShader") kind = FJGPU_SHADER_PATHTRACING;
+  else if (base == "GlassShader") kind = FJGPU_SHADER_GLASS;
   else if (base == "StanfordPlyProcedure") kind = 100;
   if (kind < 0) { last_message = "plugin '" + base + "' has no device implementation"; return bad(SI_ERR_PLUGIN_NOT_FOUND); }
   the_scene->plugins.push_back({base, kind});
@@ -618,7 +627,7 @@ ID SiNewCamera(const char *) { if (!the_scene) return bad(SI_ERR_NO_MEMORY); the
 ID SiNewShader(ID plugin) {
   int t, i;
   if (!the_scene || !decode_id(plugin, &t, &i) || t != Type_Plugin || i >= (int)the_scene->plugins.size()) return bad(SI_ERR_BADTYPE);
-  if (the_scene->plugins[i].kind > FJGPU_SHADER_PATHTRACING) return bad(SI_ERR_FAILNEW);
+  if (the_scene->plugins[i].kind > FJGPU_SHADER_GLASS) return bad(SI_ERR_FAILNEW);
   Shader s; s.plugin = i; s.props = shader_defaults(the_scene->plugins[i].kind);      // PropSetAllDefaultValues
   the_scene->shaders.push_back(s);
   si_errno = SI_ERR_NONE;

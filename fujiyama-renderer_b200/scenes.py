@@ -9,7 +9,7 @@ import os
 from . import synth
 
 PLUGINS = {"constant": ("constant_shader", "ConstantShader"), "plastic": ("plastic_shader", "PlasticShader"),
-           "pathtracing": ("pathtracing_shader", "PathtracingShader")}
+           "pathtracing": ("pathtracing_shader", "PathtracingShader"), "glass": ("glass_shader", "GlassShader")}
 
 
 def _mesh_cmds(name, ply):

@@ -92,14 +92,15 @@ int fjgpu_groups_set(fjgpu_context *ctx, int32_t ngroups,
 
 /* ---- shaders: device re-implementations keyed on plugin_name ----------------------------
  * shaders/constant_shader/constant_shader.cc:72-94, shaders/plastic_shader/plastic_shader.cc:101-179,
- * shaders/pathtracing_shader/pathtracing_shader.cc:125-257.  Values are AFTER the clamping
- * the plugin's property setters apply (Max(0,.), ior>=.001, opacity in [0,1], transmit>=.001). */
+ * shaders/pathtracing_shader/pathtracing_shader.cc:125-257, shaders/glass_shader/glass_shader.cc:88-133.  Values are
+ * AFTER the clamping the plugin's property setters apply (Max(0,.), ior>=.001, opacity in [0,1], transmit>=.001; glass:
+ * ior = Max(0, ior), filter_color >= .001 carried in `transmit`, do_color_filter = filter_color != (1,1,1)). */
 enum { FJGPU_SHADER_NONE = 0,      /* no shader: NO_SHADER_COLOR (.5,1,0), Os 1 (src/fj_shading.cc:26,555-560) */
-       FJGPU_SHADER_CONSTANT = 1, FJGPU_SHADER_PLASTIC = 2, FJGPU_SHADER_PATHTRACING = 3 };
+       FJGPU_SHADER_CONSTANT = 1, FJGPU_SHADER_PLASTIC = 2, FJGPU_SHADER_PATHTRACING = 3, FJGPU_SHADER_GLASS = 4 };
 typedef struct fjgpu_shader {
   int32_t kind;
   int32_t do_reflect;       /* plastic: any(reflect > 0)  (plastic_shader.cc:231-250)          */
-  int32_t do_color_filter;  /* pathtracing: transmit != (1,1,1) (pathtracing_shader.cc:358-378) */
+  int32_t do_color_filter;  /* pathtracing: transmit != (1,1,1) (pathtracing_shader.cc:358-378); glass: filter_color != (1,1,1) */
   int32_t _pad;
   float diffuse[3];
   float reflect[3];

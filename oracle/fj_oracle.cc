@@ -715,6 +715,27 @@ void eval_pathtracing(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, c
   *Os = 1;
 }
 
+// GlassShader::evaluate, shaders/glass_shader/glass_shader.cc:88-133
+void eval_glass(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, const SurfIn &in, Col *Cs, float *Os) {
+  *Cs = Col();
+  const double Kr = SlFresnel(in.I, in.N, 1 / sh.ior), Kt = 1 - Kr;
+  Col4 C_refl, C_refr; double t_hit = REAL_MAX;
+  Cxt rc = cxt; rc.reflect_depth++; rc.ray_context = CXT_REFLECT_RAY;          // SlReflectContext :242-252
+  rc.trace_target = rs.s->inst[in.shaded_object].reflect_target; rc.node = cxt.node * 4 + 2;
+  const V3 R = Normalize(SlReflect(in.I, in.N));
+  SlTrace(rs, rc, in.P, R, .0001, 1000, &C_refl, &t_hit);
+  Cs->r += Kr * C_refl.r; Cs->g += Kr * C_refl.g; Cs->b += Kr * C_refl.b;
+  Cxt fc = cxt; fc.refract_depth++; fc.ray_context = CXT_REFRACT_RAY;          // SlRefractContext :254-264
+  fc.trace_target = rs.s->inst[in.shaded_object].refract_target; fc.node = cxt.node * 4 + 3;
+  const V3 T = Normalize(SlRefract(in.I, in.N, 1 / sh.ior));
+  SlTrace(rs, fc, in.P, T, .0001, 1000, &C_refr, &t_hit);
+  if (sh.do_color_filter && Dot(in.I, in.N) < 0) {                              // filter_color is carried in `transmit`
+    C_refr.r *= std::pow(sh.transmit[0], t_hit); C_refr.g *= std::pow(sh.transmit[1], t_hit); C_refr.b *= std::pow(sh.transmit[2], t_hit);
+  }
+  Cs->r += Kt * C_refr.r; Cs->g += Kt * C_refr.g; Cs->b += Kt * C_refr.b;
+  *Os = 1;
+}
+
 // SlTrace + trace_surface, src/fj_shading.cc:140-179, :527-572 ; bounce gate :467-499
 int SlTrace(RenderState &rs, const Cxt &cxt, const V3 &o, const V3 &d, double tmin, double tmax, Col4 *out, double *t_hit) {
   *out = Col4();
@@ -743,6 +764,7 @@ int SlTrace(RenderState &rs, const Cxt &cxt, const V3 &o, const V3 &d, double tm
       const fjgpu_shader &sh = rs.s->shaders[slot].d;
       if (sh.kind == FJGPU_SHADER_CONSTANT) eval_constant(sh, &Cs, &Os);
       else if (sh.kind == FJGPU_SHADER_PLASTIC) eval_plastic(rs, cxt, sh, in, &Cs, &Os);
+      else if (sh.kind == FJGPU_SHADER_GLASS) eval_glass(rs, cxt, sh, in, &Cs, &Os);
       else { rs.cur_shader = slot; eval_pathtracing(rs, cxt, sh, in, &Cs, &Os); }
     }
     Os = (float)Clamp(Os, 0, 1);

@@ -133,7 +133,7 @@ def make_tiles(xres, yres, tile=32, region=None):
 
 
 SHADER_PLUGIN = {"constant": ("constant_shader", "ConstantShader"), "plastic": ("plastic_shader", "PlasticShader"),
-                 "pathtracing": ("pathtracing_shader", "PathtracingShader")}
+                 "pathtracing": ("pathtracing_shader", "PathtracingShader"), "glass": ("glass_shader", "GlassShader")}
 LIGHT_NAME = {0: "PointLight", 1: "GridLight", 2: "SphereLight", 3: "DomeLight"}
 
 
@@ -253,6 +253,13 @@ class SceneDesc:
             sh.do_reflect = 1 if any(x > 0 for x in refl) else 0
             sh.ior = max(float(f32(.001)), float(f32(props.get("ior", 1.4))))
             sh.opacity = min(1.0, max(0.0, float(f32(props.get("opacity", 1)))))
+        elif kind == "glass":
+            sh.kind = a.SHADER_GLASS
+            fc = [max(float(f32(.001)), float(f32(x))) for x in props.get("filter_color", (1, 1, 1))]
+            sh.transmit[:] = fc
+            sh.do_color_filter = 0 if all(x == 1 for x in fc) else 1
+            sh.ior = max(0.0, float(f32(props.get("ior", 1.4))))
+            sh.opacity = 1.0
         else:
             sh.kind = a.SHADER_PATHTRACING
             sh.emission[:] = [max(0.0, float(f32(x))) for x in props.get("emission", (0, 0, 0))]

@@ -62,7 +62,7 @@ def test_ids_and_errors_follow_the_reference(fuji):
                          ("NewMesh a b", "too many arguments"), ("NewMesh mesh1", "entry name already exists"),
                          ("RenderScene nope", "entry name not found"), ("SetProperty1 ren1 cast_shadow abc", "bad number arguments"),
                          ("NewLight l1 LaserLight", "bad enum arguments"),
-                         ("OpenPlugin p /x/GlassShader.so", "plugin not found"),
+                         ("OpenPlugin p /x/HairShader.so", "plugin not found"),
                          ("NewVolume v", "new entry failed"),
                          ("SetProperty1 ren1 no_such_property 1", "command failed")]:
             with pytest.raises(fuji.SceneError, match=msg):
@@ -116,7 +116,7 @@ def test_python_shim_emits_reference_grammar(fuji):
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cube_c1", "plastic", "multi", "dome_light"])
+@pytest.mark.parametrize("name", ["cube_c1", "plastic", "multi", "dome_light", "glass"])
 def test_scn_file_renders_like_the_reference(fuji, tmp_path, name):
     """The exact command text the reference's bin/scene was given for the golden .fb, fed to libfjscene."""
     from fujiyama_renderer_b200 import fbio
