@@ -80,7 +80,18 @@ struct DInstance {
   int32_t shader_of_group[FJ_MAX_SHADING_GROUPS];
   int32_t reflect_target, refract_target, shadow_target;
 };
-struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; const float4 *nodes4q; const float4 *nodesq; float bmagq, pad2; };   // TLAS leaf (first,count) -> order[first..] = instance indices
+// Everything k_extend2 needs to enter an instance, in TLAS-leaf order (leaf `first` indexes this array directly): one
+// 144-B record instead of the chain order[] -> DInstance -> DMesh (the kernel is bound by dependent-load latency).
+struct DInstRec {
+  double inv[12];           // world -> object
+  const char *nodes4, *nodesq;
+  const void *tri;          // tri32 or tri64 packets
+  float bmag, bmagq;
+  int32_t tri64, inst;      // packet format, instance index (DScene::inst)
+  int32_t pad[2];
+};
+static_assert(sizeof(DInstRec) == 144, "instance record must be 144 bytes");
+struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; const float4 *nodes4q; const float4 *nodesq; float bmagq, pad2; const DInstRec *irec; };   // TLAS leaf (first,count) -> order[first..] = instance indices
 struct DShader {
   int32_t kind, do_reflect, do_color_filter, pad;
   float diffuse[3], reflect[3], refract[3], emission[3], transmit[3];

@@ -291,17 +291,15 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           const int first = ref >> 3, cnt = (ref & 7) + 1;
           for (int k = cnt - 1; k >= 1; k--) stack[sp++] = ~(((first + k) << 3) | 0);
           const RayRec &r = rays[S.ridx[tid]];
-          const int ci = sc.groups[r.target].order[first];
-          S.cur_inst[tid] = ci;
-          const DInstance &in = sc.inst[ci];
+          const DInstRec &in = sc.groups[r.target].irec[first];          // one record: matrix, tree, packets (no order[] -> instance -> mesh chain)
+          S.cur_inst[tid] = in.inst;
           const D3 o = mat_point(in.inv, mk(r.o[0], r.o[1], r.o[2]));
           const D3 d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
           S.ox[tid] = o.x; S.oy[tid] = o.y; S.oz[tid] = o.z; S.dx[tid] = d.x; S.dy[tid] = d.y; S.dz[tid] = d.z;
-          const DMesh &m = sc.meshes[in.mesh];
-          make_box_ray_mm(o, d, QUANT ? m.bmagq : m.bmag, br);
-          nodes = (const char *)(QUANT ? m.nodesq : m.nodes4);
-          const bool t64 = m.tri32 == nullptr;
-          S.tri[tid] = t64 ? (const void *)m.tri64 : (const void *)m.tri32;
+          make_box_ray_mm(o, d, QUANT ? in.bmagq : in.bmag, br);
+          nodes = QUANT ? in.nodesq : in.nodes4;
+          const bool t64 = in.tri64 != 0;
+          S.tri[tid] = in.tri;
           st = (st & XS_FOUND) | XS_BLAS | (t64 ? XS_TRI64 : 0);
           stack[sp++] = SENTINEL;
           node = 0;

@@ -61,11 +61,12 @@ struct fjgpu_context {
 
   // device scene
   DevBuf d_meshes, d_inst, d_groups, d_shaders, d_lights;
-  std::vector<DevBuf> d_group_nodes, d_group_nodes4, d_group_nodes4q, d_group_nodesq, d_group_order, d_dome;
+  std::vector<DevBuf> d_group_nodes, d_group_nodes4, d_group_nodes4q, d_group_nodesq, d_group_order, d_group_irec, d_dome;
   fj::DScene sc;
   std::vector<int> mesh_slot_of_id;   // dense slot per mesh id (map order)
   uint64_t tlas_nodes = 0;
   int tlas_depth4 = 0;
+  size_t ctl_off = 0;             // offset of the live QueueCtl inside d_ctl
   bool quant_ok = true;        // every tree of the committed scene has a quantised (NodeQ64) copy
   int stack_need = 0;          // worst-case traversal stack of k_extend3 for the committed scene (entries)
   double build_seconds = 0;
@@ -187,6 +188,8 @@ int commit_scene(fjgpu_context *ctx) {
   for (auto &b : ctx->d_group_nodes4q) b.release();
   for (auto &b : ctx->d_group_nodesq) b.release();
   for (auto &b : ctx->d_group_order) b.release();
+  for (auto &b : ctx->d_group_irec) b.release();
+  ctx->d_group_irec.assign(std::max(ngroups, 0), DevBuf());
   ctx->d_group_nodes4q.assign(std::max(ngroups, 0), DevBuf());
   ctx->d_group_nodesq.assign(std::max(ngroups, 0), DevBuf());
   ctx->quant_ok = true;
@@ -230,6 +233,21 @@ int commit_scene(fjgpu_context *ctx) {
     ctx->tlas_depth4 = std::max(ctx->tlas_depth4, br.max_depth4);
     dg[g].nodes = (const float4 *)ctx->d_group_nodes[g].p;
     dg[g].order = (const int32_t *)ctx->d_group_order[g].p;
+    {
+      std::vector<fj::DInstRec> rec(order.size());
+      memset(rec.data(), 0, rec.size() * sizeof(fj::DInstRec));
+      for (size_t k = 0; k < br.order.size(); k++) {
+        const fj::DInstance &in = di[order[k]];
+        const fj::DMesh &me = dm[in.mesh];
+        fj::DInstRec &r = rec[k];
+        memcpy(r.inv, in.inv, sizeof r.inv);
+        r.nodes4 = (const char *)me.nodes4; r.nodesq = (const char *)me.nodesq;
+        r.tri64 = me.tri32 == nullptr; r.tri = r.tri64 ? (const void *)me.tri64 : (const void *)me.tri32;
+        r.bmag = me.bmag; r.bmagq = me.bmagq; r.inst = order[k];
+      }
+      if (int rc = dev_upload(ctx, ctx->d_group_irec[g], rec.data(), rec.size() * sizeof(fj::DInstRec), true)) return rc;
+      dg[g].irec = (const fj::DInstRec *)ctx->d_group_irec[g].p;
+    }
     dg[g].ninst = (int32_t)ids.size();
     { double b = 0; for (int a = 0; a < 3 && !boxes.empty(); a++) b = std::max(b, std::max(std::fabs((double)br.bounds.lo[a]), std::fabs((double)br.bounds.hi[a]))); dg[g].bmag = fjb::round_up(b); }
     ctx->tlas_nodes += br.nodes.size();
@@ -477,7 +495,14 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   if (int rc = dev_upload(ctx, ctx->d_tiles, tiles, (size_t)ntiles * sizeof(fjgpu_tile))) return rc;
   if (int rc = dev_alloc(ctx, ctx->d_samples, (size_t)pl.tiles_per_batch * pl.wstride * sizeof(fj::Accum))) return rc;
   if (int rc = dev_alloc(ctx, ctx->d_counters, sizeof(fj::DCounters) + 64)) return rc;
-  if (int rc = dev_alloc(ctx, ctx->d_ctl, sizeof(fj::QueueCtl))) return rc;
+  if (int rc = dev_alloc(ctx, ctx->d_ctl, (size_t)4 << 20)) return rc;      // own 2-MB pages; the live QueueCtl sits at ctl_off inside
+  // The queue counters get an allocation of their own and sit at its start.  Measured, not yet explained: k_shade, whose
+  // every warp takes its output slots with one atomicAdd on QueueCtl::count, runs the north-star frame in 61.5-62.8 ms when
+  // the counter lies in the first 2 KB of a 2-MB-aligned block and in 74.6-78.5 ms at any of 13 other offsets tried (4 KB ...
+  // 3 MB), while a kernel of nothing but those atomics is equally fast everywhere (profiles/r1_queue_counter_placement.txt).
+  // As a 16-byte allocation from the runtime's small-block pool the counter landed on either side from build to build.
+  ctx->ctl_off = ((size_t)std::max(0, env_int("FJGPU_CTL_OFFSET", 0)) & ~(size_t)255) % ((size_t)3 << 20);
+  char *const ctl_p = (char *)ctx->d_ctl.p + ctx->ctl_off;
   float4 *blocks = nullptr;
   if (mode == OUT_DEVICE_BLOCKS) {
     blocks = (float4 *)d_out_blocks;
@@ -529,11 +554,14 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         const double want = (double)nb * pl.wstride * factor;
         if (want > 4.0e9) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray tree too wide for one tile's ray queue");
         const size_t capacity = (size_t)want;
-        if (int rc = dev_alloc(ctx, ctx->d_queue[0], capacity * sizeof(fj::RayRec))) return rc;
-        if (int rc = dev_alloc(ctx, ctx->d_queue[1], capacity * sizeof(fj::RayRec))) return rc;
-        if (int rc = dev_alloc(ctx, ctx->d_hits, capacity * sizeof(fj::HitRec))) return rc;
-        a.queue[0] = (fj::RayRec *)ctx->d_queue[0].p; a.queue[1] = (fj::RayRec *)ctx->d_queue[1].p;
-        a.hits = (fj::HitRec *)ctx->d_hits.p; a.ctl = (fj::QueueCtl *)ctx->d_ctl.p; a.capacity = (uint32_t)capacity; a.cur = 0;
+        // the two ray queues and the hit records live in ONE allocation at fixed relative offsets, so that the streams k_shade
+        // reads and writes side by side keep the same relative placement whatever the scene allocated before them
+        const size_t pad = (size_t)env_int("FJGPU_ARENA_PAD_KB", 0) << 10;
+        const size_t qbytes = (capacity * sizeof(fj::RayRec) + 255) & ~(size_t)255, hbytes = (capacity * sizeof(fj::HitRec) + 255) & ~(size_t)255;
+        if (int rc = dev_alloc(ctx, ctx->d_queue[0], 2 * (qbytes + pad) + hbytes)) return rc;
+        a.queue[0] = (fj::RayRec *)ctx->d_queue[0].p; a.queue[1] = (fj::RayRec *)((char *)ctx->d_queue[0].p + qbytes + pad);
+        a.hits = (fj::HitRec *)((char *)ctx->d_queue[0].p + 2 * (qbytes + pad));
+        a.ctl = (fj::QueueCtl *)ctl_p; a.capacity = (uint32_t)capacity; a.cur = 0;
         const int sort_bits = pl.waves > 1 ? std::min(7, std::max(0, env_int("FJGPU_SORT_BITS", 0))) : 0;
         a.hist = nullptr; a.perm = nullptr; a.sort_bits = sort_bits; a.sort_bins = 8u << (3 * sort_bits);
         if (sort_bits > 0) {
@@ -545,7 +573,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
             a.sort_lo[k] = ctx->scene_lo[k]; a.sort_scale[k] = ext > 0 ? (float)(1 << sort_bits) / ext : 0.f;
           }
         }
-        CK(cudaMemsetAsync(ctx->d_ctl.p, 0, sizeof(fj::QueueCtl), ctx->stream));
+        CK(cudaMemsetAsync(ctl_p, 0, sizeof(fj::QueueCtl), ctx->stream));
         cudaEvent_t s0 = pool_event(ctx, &evn), s1 = pool_event(ctx, &evn);
         CK(cudaEventRecord(s0, ctx->stream));
         const unsigned long long total = (unsigned long long)nb * pl.wstride;
@@ -556,8 +584,8 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         ev_shade.push_back(s0); ev_shade.push_back(s1);
         for (int w = 0; w < pl.waves; w++) {
           // head of the current queue and the count of the next one start at zero
-          CK(cudaMemsetAsync((char *)ctx->d_ctl.p + offsetof(fj::QueueCtl, head), 0, 4, ctx->stream));
-          CK(cudaMemsetAsync((char *)ctx->d_ctl.p + offsetof(fj::QueueCtl, count) + 4 * (a.cur ^ 1), 0, 4, ctx->stream));
+          CK(cudaMemsetAsync(ctl_p + offsetof(fj::QueueCtl, head), 0, 4, ctx->stream));
+          CK(cudaMemsetAsync(ctl_p + offsetof(fj::QueueCtl, count) + 4 * (a.cur ^ 1), 0, 4, ctx->stream));
           cudaEvent_t e0 = pool_event(ctx, &evn), e1 = pool_event(ctx, &evn), e2 = pool_event(ctx, &evn);
           if (a.hist) CK(cudaMemsetAsync(a.hist, 0, ((size_t)a.sort_bins + 1) * 4, ctx->stream));
           CK(cudaEventRecord(e0, ctx->stream));
@@ -565,7 +593,12 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
           CK(cudaGetLastError());
           CK(cudaEventRecord(e1, ctx->stream));
           if (has_plastic) fj::k_shade<float, true><<<ctx->sm_count * 6, 128, 0, ctx->stream>>>(a);
-          else fj::k_shade<float, false><<<ctx->sm_count * 10, 128, 0, ctx->stream>>>(a);
+          else {
+            const int smb = env_int("FJGPU_SHADE_MINBLOCKS", 5), per = env_int("FJGPU_SHADE_CTAS", 2);
+            if (smb >= 8) fj::k_shade<float, false, 8><<<ctx->sm_count * 8 * per, 128, 0, ctx->stream>>>(a);
+            else if (smb >= 6) fj::k_shade<float, false, 6><<<ctx->sm_count * 6 * per, 128, 0, ctx->stream>>>(a);
+            else fj::k_shade<float, false, 5><<<ctx->sm_count * 5 * per, 128, 0, ctx->stream>>>(a);
+          }
           CK(cudaGetLastError());
           launches += 2;
           if (a.hist && w + 1 < pl.waves) {       // order the next queue for the next extend
@@ -582,7 +615,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         }
         if (factor >= pl.peak) break;           // cannot overflow
         fj::QueueCtl hctl;
-        CK(cudaMemcpyAsync(&hctl, ctx->d_ctl.p, sizeof hctl, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&hctl, ctl_p, sizeof hctl, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (!hctl.overflow) break;
         factor = std::min(pl.peak, factor * 4.0);
@@ -677,6 +710,7 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &b : ctx->d_group_nodes4q) b.release();
   for (auto &b : ctx->d_group_nodesq) b.release();
   for (auto &b : ctx->d_group_order) b.release();
+  for (auto &b : ctx->d_group_irec) b.release();
   for (auto &b : ctx->d_dome) b.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
                    &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl, &ctx->d_hist, &ctx->d_perm};
@@ -986,6 +1020,7 @@ int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent) {
   for (auto &b : ctx->d_group_nodes4q) all.push_back(&b);
   for (auto &b : ctx->d_group_nodesq) all.push_back(&b);
   for (auto &b : ctx->d_group_order) all.push_back(&b);
+  for (auto &b : ctx->d_group_irec) all.push_back(&b);
   uint64_t total = 0;
   for (DevBuf *b : all) {
     if (!b->h || !b->used) continue;

@@ -673,8 +673,8 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const RenderArgs a) {
 // compacted into queue[cur ^ 1] by warp ballot (Shader::Evaluate + the Sl*Context/SlTrace calls the plugins make).
 // PLASTIC = false drops the light loop and its inline shadow-ray traversal from the kernel (scenes without a plastic
 // shader): fewer registers, more resident warps.
-template <typename T, bool PLASTIC>
-__global__ void __launch_bounds__(128, PLASTIC ? 3 : 5) k_shade(const RenderArgs a) {
+template <typename T, bool PLASTIC, int MINB = (PLASTIC ? 3 : 5)>
+__global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
   const RayRec *rays = a.queue[a.cur];
