@@ -490,3 +490,73 @@ def test_device_build_of_a_million_triangles(sk, device, monkeypatch):
     assert 0 < info.device_build_seconds < host_s
     print("BVH build of %d triangles: host %.3f s, device %.4f s (%.0fx)" % (len(idx), host_s, info.device_build_seconds,
                                                                              host_s / info.device_build_seconds))
+
+
+# ---------------------------------------------------------------------------------------------- full-size configurations
+def test_config4_instanced_million_triangle_meshes(sk, device):
+    """BASELINE config 4 at full size: 16 instances of a ~1.09 M-triangle mesh on the 4x4 grid of scenes/happy_buddhas.scn
+    plus a floor (17.5 M instanced triangles behind a TLAS with inner nodes).  No oracle render at this size: the
+    wavefront kernel is cross-checked against the megakernel with FP64 boxes (independent traversal code, binary BVH), hit
+    points must lie on the analytic surface of the instance they report, and an oracle spot check pins a subset."""
+    from fujiyama_renderer_b200 import synth
+    P, idx = synth.blob(740)                              # 1 095 200 triangles
+    d = sk.SceneDesc()
+    d.mesh("blob", P, idx)
+    Pq, iq = synth.quad(12.0, -0.7)
+    d.mesh("floor", Pq, iq)
+    d.shader("s", "constant")
+    xf = []
+    k = 0
+    for i in range(4):
+        for j in range(4):
+            T, R, S = (2.25 - 1.5 * i, 0, 2.25 - 1.5 * j), (0, 30 * k, 0), (.6, .6, .6)
+            d.instance("o%d" % k, "blob", "s", T=T, R=R, S=S)
+            xf.append(T)
+            k += 1
+    d.instance("f", "floor", "s")
+    st = d.to_structs()
+    n = 200000
+    o, dr = random_rays(n, 9, radius=6.0)
+    dev = device.Device(0)
+    dev.load_structs(st)
+    a = dev.trace_closest(0, o, dr, 1e-3, 1000., 0)
+    b = dev.trace_closest(0, o, dr, 1e-3, 1000., 1)
+    info = dev.info()
+    dev.close()
+    assert info.instances == 17 and info.blas_tris == len(idx) + 2
+    t, u, v, prim, inst = a
+    assert np.array_equal(t, b[0]) and np.array_equal(inst, b[4])
+    same = prim == b[3]
+    assert same.mean() > 0.999 and np.array_equal(u[same], b[1][same])
+    hit = (inst >= 0) & (inst < 16)
+    assert hit.sum() > 0.2 * n
+    Ph = o[hit] + t[hit, None] * dr[hit]
+    r = np.linalg.norm(Ph - np.asarray(xf)[inst[hit]], axis=1) / 0.6
+    assert r.min() > 0.85 and r.max() < 1.15              # radius 1 +- .11 bumps around the reported instance's centre
+
+
+def test_config5_ten_million_triangle_soup(sk, device, monkeypatch):
+    """BASELINE config 5's mesh at full size: S-random with 10 M triangles, BVH built on the device (host build: ~10 s).
+    Wavefront kernel (8-bit quantised 4-wide nodes) against the megakernel with FP64 boxes on the binary tree."""
+    from fujiyama_renderer_b200 import synth
+    P, idx = synth.random_tris(10_000_000, seed=1234)
+    d = sk.SceneDesc()
+    d.mesh("soup", P, idx)
+    d.shader("s", "constant")
+    d.instance("o", "soup", "s")
+    st = d.to_structs()
+    monkeypatch.setenv("FJGPU_BUILD", "device")
+    n = 100000
+    o, dr = random_rays(n, 13, radius=2.0)
+    dev = device.Device(0)
+    dev.load_structs(st)
+    a = dev.trace_closest(0, o, dr, 1e-3, 1000., 0)
+    b = dev.trace_closest(0, o, dr, 1e-3, 1000., 1)
+    info = dev.info()
+    dev.close()
+    assert info.blas_tris == 10_000_000 and info.device_build_seconds > 0
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[4], b[4])
+    same = a[3] == b[3]
+    assert same.mean() > 0.999 and np.array_equal(a[1][same], b[1][same]) and np.array_equal(a[2][same], b[2][same])
+    assert 0.3 < (a[4] >= 0).mean() <= 1.0
+    print("10 M triangles: device build %.3f s, scene %.2f GB in HBM" % (info.device_build_seconds, info.hbm_bytes / 1e9))
