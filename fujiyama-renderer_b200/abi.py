@@ -28,10 +28,15 @@ class Instance(C.Structure):
 
 class Shader(C.Structure):
     _fields_ = [("kind", C.c_int32), ("do_reflect", C.c_int32),
-                ("do_color_filter", C.c_int32), ("_pad", C.c_int32),
+                ("do_color_filter", C.c_int32), ("texture", C.c_int32),
                 ("diffuse", C.c_float * 3), ("reflect", C.c_float * 3),
                 ("refract", C.c_float * 3), ("emission", C.c_float * 3),
                 ("transmit", C.c_float * 3), ("ior", C.c_float), ("opacity", C.c_float)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("nchannels", C.c_int32), ("tilesize", C.c_int32),
+                ("tiles", C.POINTER(C.c_float))]
 
 
 class Light(C.Structure):
@@ -92,7 +97,7 @@ FJGPU_SYMBOLS = [
     "fjgpu_mesh_upload", "fjgpu_instances_set", "fjgpu_groups_set", "fjgpu_shaders_set",
     "fjgpu_lights_set", "fjgpu_camera_set", "fjgpu_render_tiles", "fjgpu_render_tiles_device",
     "fjgpu_render_tiles_resident", "fjgpu_trace_closest", "fjgpu_render_tile_samples",
-    "fjgpu_scene_info_get", "fjgpu_scene_resend",
+    "fjgpu_scene_info_get", "fjgpu_scene_resend", "fjgpu_textures_set", "fjgpu_mesh_set_uv",
 ]
 
 _P = C.POINTER

@@ -72,6 +72,7 @@ struct DMesh {
   const float4 *nodes4q;    // the 4-wide tree in child-major layout (fj_bvh.h Node4Q) for the quad-per-ray k_extend3
   const float4 *nodesq;     // the 4-wide tree with 8-bit quantised child boxes (fj_bvh.h NodeQ64), null if not representable
   float bmagq, pad2;        // bound magnitude of the decoded planes
+  const float *uv;          // per-vertex texture coordinates, 2 floats per vertex (null: uv = 0, fj_mesh.cc:292-297)
 };
 struct DInstance {
   double inv[12];           // rows 0..2 of MatInverse(matrix): world -> object (fj_object_instance.cc:222-225)
@@ -93,7 +94,7 @@ struct DInstRec {
 static_assert(sizeof(DInstRec) == 144, "instance record must be 144 bytes");
 struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; const float4 *nodes4q; const float4 *nodesq; float bmagq, pad2; const DInstRec *irec; };   // TLAS leaf (first,count) -> order[first..] = instance indices
 struct DShader {
-  int32_t kind, do_reflect, do_color_filter, pad;
+  int32_t kind, do_reflect, do_color_filter, texture;     // texture: 1 + index into DScene::textures, 0 = none
   float diffuse[3], reflect[3], refract[3], emission[3], transmit[3];
   float ior, opacity;
 };
@@ -104,7 +105,10 @@ struct DLight {
   double fwd[12];
   const double *dome_dirs; const float *dome_colors;
 };
+// One `.mip` texture in HBM: the file's tiles in file order (src/fj_mipmap.cc:156-180).
+struct DTexture { const float *tiles; int32_t width, height, nch, tilesize, xnt, ynt; };
 struct DScene {
+  const DTexture *textures;
   const DMesh *meshes; const DInstance *inst; const DGroup *groups; const DShader *shaders; const DLight *lights;
   int32_t nmeshes, ninst, ngroups, nshaders, nlights, pad;
 };
@@ -393,6 +397,35 @@ __device__ __forceinline__ void hit_surface(const DScene &sc, const RayD &ray, c
   int slot = (gid < 0 || gid >= FJ_MAX_SHADING_GROUPS) ? in.shader_of_group[0] : in.shader_of_group[gid];
   if (slot < 0) slot = in.shader_of_group[0];
   *shader_slot = slot;
+}
+
+// Texture coordinates of a hit: UV = (1-u-v) UV0 + u UV1 + v UV2 with the reference's mixed precision (`const float t =
+// 1 - u - v`, float * float for the first term, double for the others, one rounding to float at the end;
+// Mesh::ray_intersect, src/fj_mesh.cc:280-291).  Instances do not transform uv.
+__device__ __forceinline__ void hit_uv(const DScene &sc, const Hit &h, float *tu, float *tv) {
+  const DMesh &m = sc.meshes[sc.inst[h.inst].mesh];
+  if (!m.uv) { *tu = 0.f; *tv = 0.f; return; }
+  const int i0 = m.idx[3 * (size_t)h.prim], i1 = m.idx[3 * (size_t)h.prim + 1], i2 = m.idx[3 * (size_t)h.prim + 2];
+  const float t = (float)dsub(dsub(1., h.u), h.v);
+  const float2 a = reinterpret_cast<const float2 *>(m.uv)[i0], b = reinterpret_cast<const float2 *>(m.uv)[i1], c = reinterpret_cast<const float2 *>(m.uv)[i2];
+  *tu = (float)dadd(dadd((double)fmul(t, a.x), dmul(h.u, (double)b.x)), dmul(h.v, (double)c.x));
+  *tv = (float)dadd(dadd((double)fmul(t, a.y), dmul(h.u, (double)b.y)), dmul(h.v, (double)c.y));
+}
+
+// TextureCache::LookupTexture, src/fj_texture.cc:51-78: wrap to [0,1), flip v, tile = floor(coordinate * tile count) clamped
+// as MipInput::ReadTile does (src/fj_mipmap.cc:163-165), texel = (int)(fraction * 64) inside the tile; all in float as the
+// reference compiles it.  Colour as FrameBuffer::GetColor (src/fj_framebuffer.cc:84-101).
+__device__ __forceinline__ float4 tex_lookup(const DTexture &tx, float u, float v) {
+  const float tsu = __fsub_rn(u, floorf(u)), tsv = __fsub_rn(v, floorf(v));
+  const float tlu = fmul(tsu, (float)tx.xnt), tlv = fmul(__fsub_rn(1.f, tsv), (float)tx.ynt);
+  const int xtile = (int)floorf(tlu), ytile = (int)floorf(tlv);
+  const int xpxl = (int)fmul(__fsub_rn(tlu, floorf(tlu)), 64.f), ypxl = (int)fmul(__fsub_rn(tlv, floorf(tlv)), 64.f);
+  const int tx_ = min(max(xtile, 0), tx.xnt - 1), ty_ = min(max(ytile, 0), tx.ynt - 1);
+  const float *px = tx.tiles + ((size_t)(ty_ * tx.xnt + tx_) * tx.tilesize * tx.tilesize + (size_t)ypxl * tx.tilesize + xpxl) * tx.nch;
+  if (tx.nch == 1) return make_float4(px[0], px[0], px[0], 1.f);
+  if (tx.nch == 3) return make_float4(px[0], px[1], px[2], 1.f);
+  if (tx.nch == 4) return make_float4(px[0], px[1], px[2], px[3]);
+  return make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Opacity the shader of an occluder returns to a shadow ray (Os of evaluate(); the colour is unused and

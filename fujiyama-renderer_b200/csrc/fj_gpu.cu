@@ -33,11 +33,11 @@ struct DevBuf {
 };
 
 struct MeshRec {
-  DevBuf nodes, nodes4, nodes4q, nodesq, tri, N, idx, group;
+  DevBuf nodes, nodes4, nodes4q, nodesq, tri, N, idx, group, uv;
   fj::DMesh d;
   double bmin[3], bmax[3];      // exact FP64 bounds of the mesh (Mesh::ComputeBounds, fj_mesh.cc:235-244)
   int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0, max_depth4 = 0, nnodes4 = 0, stack_need4 = 0;
-  void release() { nodes.release(); nodes4.release(); nodes4q.release(); nodesq.release(); tri.release(); N.release(); idx.release(); group.release(); }
+  void release() { uv.release(); nodes.release(); nodes4.release(); nodes4q.release(); nodesq.release(); tri.release(); N.release(); idx.release(); group.release(); }
 };
 
 }  // namespace
@@ -54,6 +54,7 @@ struct fjgpu_context {
   std::vector<int32_t> group_off, group_ids;
   std::vector<fjgpu_shader> shaders;
   std::vector<fjgpu_light> lights;
+  std::vector<fjgpu_texture> textures; std::vector<DevBuf> d_tex_tiles; DevBuf d_textures;
   std::vector<std::vector<double>> dome_dirs;
   std::vector<std::vector<float>> dome_cols;
   fjgpu_camera cam;
@@ -259,7 +260,8 @@ int commit_scene(fjgpu_context *ctx) {
   std::vector<fj::DShader> ds(ctx->shaders.size());
   for (size_t i = 0; i < ds.size(); i++) {
     const fjgpu_shader &s = ctx->shaders[i]; fj::DShader &d = ds[i];
-    d.kind = s.kind; d.do_reflect = s.do_reflect; d.do_color_filter = s.do_color_filter; d.pad = 0;
+    d.kind = s.kind; d.do_reflect = s.do_reflect; d.do_color_filter = s.do_color_filter; d.texture = s.texture;
+    if (s.texture < 0 || s.texture > (int)ctx->textures.size()) return fail(ctx, FJGPU_ERR_INVALID, "shader refers to an unknown texture");
     memcpy(d.diffuse, s.diffuse, 12); memcpy(d.reflect, s.reflect, 12); memcpy(d.refract, s.refract, 12);
     memcpy(d.emission, s.emission, 12); memcpy(d.transmit, s.transmit, 12);
     d.ior = s.ior; d.opacity = s.opacity;
@@ -286,6 +288,17 @@ int commit_scene(fjgpu_context *ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
 
   fj::DScene &sc = ctx->sc;
+  {
+    std::vector<fj::DTexture> dt(ctx->textures.size());
+    for (size_t i = 0; i < dt.size(); i++) {
+      const fjgpu_texture &t = ctx->textures[i];
+      dt[i].tiles = (const float *)ctx->d_tex_tiles[i].p; dt[i].width = t.width; dt[i].height = t.height; dt[i].nch = t.nchannels;
+      dt[i].tilesize = t.tilesize; dt[i].xnt = t.width / t.tilesize; dt[i].ynt = t.height / t.tilesize;
+    }
+    if (int rc = dev_upload(ctx, ctx->d_textures, dt.data(), dt.size() * sizeof(fj::DTexture), true)) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    sc.textures = (const fj::DTexture *)ctx->d_textures.p;
+  }
   sc.meshes = (const fj::DMesh *)ctx->d_meshes.p; sc.inst = (const fj::DInstance *)ctx->d_inst.p;
   sc.groups = (const fj::DGroup *)ctx->d_groups.p; sc.shaders = (const fj::DShader *)ctx->d_shaders.p;
   sc.lights = (const fj::DLight *)ctx->d_lights.p;
@@ -712,6 +725,8 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &b : ctx->d_group_order) b.release();
   for (auto &b : ctx->d_group_irec) b.release();
   for (auto &b : ctx->d_dome) b.release();
+  for (auto &b : ctx->d_tex_tiles) b.release();
+  ctx->d_textures.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
                    &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl, &ctx->d_hist, &ctx->d_perm};
   for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -893,6 +908,45 @@ int fjgpu_lights_set(fjgpu_context *ctx, int32_t n, const fjgpu_light *lights) {
   return FJGPU_OK;
 }
 
+int fjgpu_textures_set(fjgpu_context *ctx, int32_t n, const fjgpu_texture *textures) {
+  if (!ctx || n < 0 || (n > 0 && !textures)) return fail(ctx, FJGPU_ERR_INVALID, "bad texture array");
+  CK(cudaSetDevice(ctx->device));
+  for (int i = 0; i < n; i++) {
+    const fjgpu_texture &t = textures[i];
+    if (t.width <= 0 || t.height <= 0 || t.tilesize <= 0 || !t.tiles || (t.nchannels != 1 && t.nchannels != 3 && t.nchannels != 4))
+      return fail(ctx, FJGPU_ERR_INVALID, "bad texture description");
+    if (t.tilesize < 64 || t.width / t.tilesize < 1 || t.height / t.tilesize < 1)
+      return fail(ctx, FJGPU_ERR_UNSUPPORTED, "texture tiles must be at least 64 texels wide (TextureCache::LookupTexture assumes 64) and the image at least one tile");
+  }
+  for (auto &b : ctx->d_tex_tiles) b.release();
+  ctx->d_tex_tiles.assign(n, DevBuf());
+  ctx->textures.assign(textures, textures + n);
+  for (int i = 0; i < n; i++) {
+    const fjgpu_texture &t = textures[i];
+    const size_t floats = (size_t)(t.width / t.tilesize) * (t.height / t.tilesize) * t.tilesize * t.tilesize * t.nchannels;
+    if (int rc = dev_upload(ctx, ctx->d_tex_tiles[i], t.tiles, floats * sizeof(float), true)) return rc;
+    ctx->textures[i].tiles = nullptr;      // the caller's buffer is not kept
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->dirty = true;
+  return FJGPU_OK;
+}
+
+int fjgpu_mesh_set_uv(fjgpu_context *ctx, int32_t mesh_id, const float *uv2, int32_t nverts) {
+  if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
+  auto it = ctx->meshes.find(mesh_id);
+  if (it == ctx->meshes.end()) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_mesh_set_uv: unknown mesh_id");
+  MeshRec &m = it->second;
+  CK(cudaSetDevice(ctx->device));
+  if (!uv2) { m.uv.release(); m.d.uv = nullptr; ctx->dirty = true; return FJGPU_OK; }
+  if (nverts != m.nverts) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_mesh_set_uv: vertex count differs from the uploaded mesh");
+  if (int rc = dev_upload(ctx, m.uv, uv2, (size_t)nverts * 8, true)) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  m.d.uv = (const float *)m.uv.p;
+  ctx->dirty = true;
+  return FJGPU_OK;
+}
+
 int fjgpu_camera_set(fjgpu_context *ctx, const fjgpu_camera *cam) {
   if (!ctx || !cam) return fail(ctx, FJGPU_ERR_INVALID, "null camera");
   ctx->cam = *cam; ctx->have_cam = true;
@@ -1014,7 +1068,9 @@ int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent) {
   CK(cudaSetDevice(ctx->device));
   if (int rc = commit_scene(ctx)) return rc;
   std::vector<DevBuf *> all = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights};
-  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.nodes4q, &m.nodesq, &m.tri, &m.N, &m.idx, &m.group}) all.push_back(b); }
+  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.nodes4q, &m.nodesq, &m.tri, &m.N, &m.idx, &m.group, &m.uv}) all.push_back(b); }
+  for (auto &b : ctx->d_tex_tiles) all.push_back(&b);
+  all.push_back(&ctx->d_textures);
   for (auto &b : ctx->d_group_nodes) all.push_back(&b);
   for (auto &b : ctx->d_group_nodes4) all.push_back(&b);
   for (auto &b : ctx->d_group_nodes4q) all.push_back(&b);

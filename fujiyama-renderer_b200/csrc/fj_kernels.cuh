@@ -205,12 +205,19 @@ struct Shading {
       sink.add(fmul(thr.r, .5f), thr.g, 0.f);
     } else if (kind == 1) {                                        // ConstantShader::evaluate, constant_shader.cc:72-94
       const DShader &sh = sc.shaders[slot];
+      if (sh.texture) {                                            // C_tex = texture->Lookup(uv) * diffuse
+        float tu, tv; hit_uv(sc, h, &tu, &tv);
+        const float4 ct = tex_lookup(sc.textures[sh.texture - 1], tu, tv);
+        sink.add(fmul(thr.r, fmul(ct.x, sh.diffuse[0])), fmul(thr.g, fmul(ct.y, sh.diffuse[1])), fmul(thr.b, fmul(ct.z, sh.diffuse[2])));
+      } else
       sink.add(fmul(thr.r, sh.diffuse[0]), fmul(thr.g, sh.diffuse[1]), fmul(thr.b, sh.diffuse[2]));
     } else if (PLASTIC && kind == 2) {                             // PlasticShader::evaluate, plastic_shader.cc:101-179
       const DShader &sh = sc.shaders[slot];
       const D3 Nf = sl_faceforward(ray.d, N);
       const C3 diff = gather_lights(P, Nf, h.inst, cur.node);
-      sink.add(fmul(thr.r, fmul(diff.r, sh.diffuse[0])), fmul(thr.g, fmul(diff.g, sh.diffuse[1])), fmul(thr.b, fmul(diff.b, sh.diffuse[2])));
+      float4 dm = make_float4(1.f, 1.f, 1.f, 1.f);                 // diffuse_map, plastic_shader.cc:148-156: Cs = diff * diffuse * diff_map
+      if (sh.texture) { float tu, tv; hit_uv(sc, h, &tu, &tv); dm = tex_lookup(sc.textures[sh.texture - 1], tu, tv); }
+      sink.add(fmul(thr.r, fmul(fmul(diff.r, sh.diffuse[0]), dm.x)), fmul(thr.g, fmul(fmul(diff.g, sh.diffuse[1]), dm.y)), fmul(thr.b, fmul(fmul(diff.b, sh.diffuse[2]), dm.z)));
       if (sh.do_reflect && (int)cur.rd + 1 <= fr.max_reflect) {    // SlReflectContext :242-252, gate :467-499
         const double Kr = sl_fresnel(ray.d, Nf, ddiv(1., (double)sh.ior));
         const D3 R = normalize(sl_reflect(ray.d, Nf));
@@ -255,7 +262,13 @@ struct Shading {
         const D3 D = normalize(((u * cos(r1)) * r2s + (v * sin(r1)) * r2s) + w * __dsqrt_rn(dsub(1., r2)));
         const float Kd = (float)dot(N, D);
         c.d[0] = D.x; c.d[1] = D.y; c.d[2] = D.z; c.tmin = .001;
+        if (sh.texture) {                            // diffuse_map scales Cd (pathtracing_shader.cc:132-135): L = Cd * Kd * diffuse * C
+          float tu, tv; hit_uv(sc, h, &tu, &tv);
+          const float4 cd = tex_lookup(sc.textures[sh.texture - 1], tu, tv);
+          c.thr[0] = fmul(thr.r, fmul(fmul(cd.x, Kd), sh.diffuse[0])); c.thr[1] = fmul(thr.g, fmul(fmul(cd.y, Kd), sh.diffuse[1])); c.thr[2] = fmul(thr.b, fmul(fmul(cd.z, Kd), sh.diffuse[2]));
+        } else {
         c.thr[0] = fmul(thr.r, fmul(Kd, sh.diffuse[0])); c.thr[1] = fmul(thr.g, fmul(Kd, sh.diffuse[1])); c.thr[2] = fmul(thr.b, fmul(Kd, sh.diffuse[2]));
+        }
         c.node = cur.node * 4 + 1; c.target = in.reflect_target; c.type = RAY_DIFFUSE; c.dd = cur.dd + 1;
         sink.spawn(c);
         c.dd = cur.dd;

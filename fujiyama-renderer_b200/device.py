@@ -77,6 +77,11 @@ class Device:
         """`st`: the flat struct dict (meshes, instances, group_offsets/ids, shaders, lights, camera)."""
         for mid, P, N, idx in st["meshes"]:
             self.mesh(mid, P, N, idx)
+        for mid, uv in st.get("mesh_uv", {}).items():
+            uv = np.ascontiguousarray(uv, np.float32)
+            self._ck(self.lib.fjgpu_mesh_set_uv(self.ctx, mid, uv.ctypes.data_as(C.POINTER(C.c_float)), len(uv)))
+        if "textures" in st:
+            self._ck(self.lib.fjgpu_textures_set(self.ctx, st["ntextures"], st["textures"]))
         self._ck(self.lib.fjgpu_shaders_set(self.ctx, st["nshaders"], st["shaders"]))
         off = np.ascontiguousarray(st["group_offsets"], np.int32)
         ids = np.ascontiguousarray(st["group_ids"], np.int32)

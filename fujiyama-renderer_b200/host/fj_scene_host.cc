@@ -132,8 +132,9 @@ struct Xform {
 };
 
 struct Plugin { std::string name; int kind; };   // kind: FJGPU_SHADER_* for shaders, 100 = StanfordPlyProcedure
-struct Mesh { std::vector<double> P, N; std::vector<int32_t> idx; bool dirty = true; };
-struct Shader { int plugin; std::map<std::string, std::array<double, 4>> props; };
+struct Mesh { std::vector<double> P, N; std::vector<int32_t> idx; std::vector<float> uv; bool dirty = true; };
+struct Texture { int width = 0, height = 0, nch = 0, tilesize = 0; std::vector<float> tiles; };   // a `.mip` file's header and tiles (src/fj_mipmap.cc:124-180)
+struct Shader { int plugin; std::map<std::string, std::array<double, 4>> props; ID texture = SI_BADID; };   // texture: the `texture` / `diffuse_map` property
 struct Procedure { int plugin; ID mesh = SI_BADID; std::string filepath, io_mode; };
 struct Instance { ID mesh; Xform x; std::map<std::string, ID> shaders; ID reflect = SI_BADID, refract = SI_BADID, shadow = SI_BADID; };
 struct Group { std::vector<int> members; };
@@ -150,6 +151,7 @@ struct Renderer {
 };
 
 struct Scene {
+  std::vector<Texture> textures; bool textures_dirty = true;
   std::vector<Plugin> plugins; std::vector<Mesh> meshes; std::vector<Shader> shaders; std::vector<Procedure> procedures;
   std::vector<Instance> instances; std::vector<Group> groups; std::vector<Light> lights; std::vector<Camera> cameras;
   std::vector<FrameBuf> framebuffers; std::vector<Renderer> renderers;
@@ -242,15 +244,18 @@ int read_ply(const std::string &path, Mesh *mesh) {
   if (!ascii && !swap && fmt != "binary_little_endian") return -1;
   const unsigned char *p = (const unsigned char *)data.data() + body, *end = (const unsigned char *)data.data() + data.size();
   std::istringstream as; if (ascii) as.str(data.substr(body));
-  mesh->P.clear(); mesh->idx.clear();
+  mesh->P.clear(); mesh->idx.clear(); mesh->uv.clear();
+  bool has_uv = false;
+  for (const Elem &e : elems) if (e.name == "vertex") for (const PlyProp &pr : e.props) has_uv = has_uv || pr.name == "uv1" || pr.name == "uv2";
   for (const Elem &e : elems) {
     for (long i = 0; i < e.count; i++) {
-      double xyz[3] = {0, 0, 0}; std::vector<int32_t> poly;
+      double xyz[3] = {0, 0, 0}, tuv[2] = {0, 0}; std::vector<int32_t> poly;
       for (const PlyProp &pr : e.props) {
         if (!pr.list) {
           double v;
           if (ascii) { if (!(as >> v)) return -1; } else { const int n = ply_size(pr.type); if (!n || p + n > end) return -1; v = ply_scalar(p, pr.type, swap); p += n; }
           if (pr.name == "x") xyz[0] = v; else if (pr.name == "y") xyz[1] = v; else if (pr.name == "z") xyz[2] = v;
+          else if (pr.name == "uv1") tuv[0] = v; else if (pr.name == "uv2") tuv[1] = v;     // ply2mesh.cc:42-43,91-98
         } else {
           long cnt;
           if (ascii) { double c; if (!(as >> c)) return -1; cnt = (long)c; } else { const int n = ply_size(pr.ctype); if (!n || p + n > end) return -1; cnt = (long)ply_scalar(p, pr.ctype, swap); p += n; }
@@ -261,7 +266,7 @@ int read_ply(const std::string &path, Mesh *mesh) {
           }
         }
       }
-      if (e.name == "vertex") { mesh->P.push_back(xyz[0]); mesh->P.push_back(xyz[1]); mesh->P.push_back(xyz[2]); }
+      if (e.name == "vertex") { mesh->P.push_back(xyz[0]); mesh->P.push_back(xyz[1]); mesh->P.push_back(xyz[2]); if (has_uv) { mesh->uv.push_back((float)tuv[0]); mesh->uv.push_back((float)tuv[1]); } }
       else if (e.name == "face")          // fan triangulation, ply2mesh.cc:129-136
         for (size_t k = 0; k + 2 < poly.size(); k++) { mesh->idx.push_back(poly[0]); mesh->idx.push_back(poly[k + 1]); mesh->idx.push_back(poly[k + 2]); }
     }
@@ -301,6 +306,7 @@ fjgpu_shader flatten_shader(const Scene &sc, const Shader &s) {
   const int kind = sc.plugins[s.plugin].kind;
   o.kind = kind;
   auto P = [&](const char *n) { return s.props.find(n)->second; };
+  { int tt, ti; if (s.texture != SI_BADID && decode_id(s.texture, &tt, &ti) && tt == Type_Texture && kind != FJGPU_SHADER_GLASS) o.texture = ti + 1; }
   if (kind == FJGPU_SHADER_CONSTANT) {                                      // constant_shader.cc:96-107
     for (int k = 0; k < 3; k++) o.diffuse[k] = clamp0(P("diffuse")[k]);
   } else if (kind == FJGPU_SHADER_PLASTIC) {                                // plastic_shader.cc:183-273
@@ -488,7 +494,15 @@ Status render(Scene &sc, Renderer &r) {
     if (!m.dirty) continue;
     if (fjgpu_mesh_upload(sc.gpu, (int32_t)i, m.P.data(), m.N.empty() ? nullptr : m.N.data(), (int32_t)(m.P.size() / 3), m.idx.data(), nullptr,
                           (int32_t)(m.idx.size() / 3)) != FJGPU_OK) return failmsg(std::string("fjgpu_mesh_upload: ") + fjgpu_last_error(sc.gpu));
+    if (!m.uv.empty() && fjgpu_mesh_set_uv(sc.gpu, (int32_t)i, m.uv.data(), (int32_t)(m.uv.size() / 2)) != FJGPU_OK)
+      return failmsg(std::string("fjgpu_mesh_set_uv: ") + fjgpu_last_error(sc.gpu));
     m.dirty = false;
+  }
+  if (sc.textures_dirty) {
+    std::vector<fjgpu_texture> ft(sc.textures.size());
+    for (size_t i = 0; i < ft.size(); i++) { const Texture &t = sc.textures[i]; ft[i].width = t.width; ft[i].height = t.height; ft[i].nchannels = t.nch; ft[i].tilesize = t.tilesize; ft[i].tiles = t.tiles.data(); }
+    if (fjgpu_textures_set(sc.gpu, (int32_t)ft.size(), ft.data()) != FJGPU_OK) return failmsg(std::string("fjgpu_textures_set: ") + fjgpu_last_error(sc.gpu));
+    sc.textures_dirty = false;
   }
   int rc = fjgpu_shaders_set(sc.gpu, (int32_t)f.shaders.size(), f.shaders.data());
   if (!rc) rc = fjgpu_groups_set(sc.gpu, (int32_t)f.goff.size() - 1, f.goff.data(), f.gids.data());
@@ -610,7 +624,29 @@ ID SiNewFrameBuffer(const char *) { if (!the_scene) return bad(SI_ERR_NO_MEMORY)
 ID SiNewObjectGroup(void) { if (!the_scene) return bad(SI_ERR_NO_MEMORY); the_scene->groups.push_back(Group()); si_errno = SI_ERR_NONE; return encode_id(Type_ObjectGroup, (int)the_scene->groups.size() - 1); }
 ID SiNewPointCloud(void) { return bad(SI_ERR_FAILNEW); }
 ID SiNewTurbulence(void) { return bad(SI_ERR_FAILNEW); }
-ID SiNewTexture(const char *) { return bad(SI_ERR_FAILNEW); }
+// SiNewTexture, src/fj_scene_interface.cc:529-545 -> Texture::LoadFile -> MipInput::ReadHeader (src/fj_mipmap.cc:124-154)
+ID SiNewTexture(const char *filename) {
+  if (!the_scene) return bad(SI_ERR_NO_MEMORY);
+  Texture t;
+  FILE *f = filename ? fopen(filename, "rb") : nullptr;
+  if (!f) return bad(SI_ERR_FAILLOAD);
+  char magic[4]; int32_t hdr[5];
+  bool good = fread(magic, 1, 4, f) == 4 && memcmp(magic, "MIPM", 4) == 0 && fread(hdr, 4, 5, f) == 5 && hdr[0] == 1;
+  if (good) {
+    t.width = hdr[1]; t.height = hdr[2]; t.nch = hdr[3]; t.tilesize = hdr[4];
+    good = t.width > 0 && t.height > 0 && t.tilesize > 0 && (t.nch == 1 || t.nch == 3 || t.nch == 4) && t.width / t.tilesize > 0 && t.height / t.tilesize > 0;
+  }
+  if (good) {
+    const size_t n = (size_t)(t.width / t.tilesize) * (t.height / t.tilesize) * t.tilesize * t.tilesize * t.nch;
+    t.tiles.resize(n);
+    good = fread(t.tiles.data(), sizeof(float), n, f) == n;
+  }
+  fclose(f);
+  if (!good) return bad(SI_ERR_FAILLOAD);
+  the_scene->textures.push_back(std::move(t)); the_scene->textures_dirty = true;
+  si_errno = SI_ERR_NONE;
+  return encode_id(Type_Texture, (int)the_scene->textures.size() - 1);
+}
 ID SiNewVolume(void) { return bad(SI_ERR_FAILNEW); }
 ID SiNewCurve(void) { return bad(SI_ERR_FAILNEW); }
 ID SiNewProcedure(ID plugin) {
@@ -662,7 +698,18 @@ Status SiAssignObjectGroup(ID id, const char *name, ID group) {
 }
 Status SiAssignPointCloud(ID, const char *, ID) { return SI_FAIL; }
 Status SiAssignTurbulence(ID, const char *, ID) { return SI_FAIL; }
-Status SiAssignTexture(ID, const char *, ID) { return SI_FAIL; }
+// SiAssignTexture, src/fj_scene_interface.cc:786-805: the PropTexture properties of the device shaders
+// (constant_shader `texture`, plastic_shader / pathtracing_shader `diffuse_map`; bump maps have no device implementation)
+Status SiAssignTexture(ID id, const char *name, ID texture) {
+  Shader *sh = the_scene ? get(the_scene->shaders, id, Type_Shader) : nullptr;
+  if (!sh || !name || !get(the_scene->textures, texture, Type_Texture)) return SI_FAIL;
+  const int kind = the_scene->plugins[sh->plugin].kind;
+  const std::string n(name);
+  const bool okname = (kind == FJGPU_SHADER_CONSTANT && n == "texture") || ((kind == FJGPU_SHADER_PLASTIC || kind == FJGPU_SHADER_PATHTRACING) && n == "diffuse_map");
+  if (!okname) return failmsg("AssignTexture " + n + ": no device implementation of this texture property");
+  sh->texture = texture;
+  return ok();
+}
 Status SiAssignVolume(ID, const char *, ID) { return SI_FAIL; }
 Status SiAssignCurve(ID, const char *, ID) { return SI_FAIL; }
 Status SiAssignShader(ID object, const char *shading_group, ID shader) {

@@ -64,19 +64,48 @@ def cube(size=1.0):
     return np.asarray(P, np.float32), np.asarray(idx, np.int32)
 
 
-def write_ply(path, P, idx):
+def write_ply(path, P, idx, uv=None):
+    """Binary PLY the reference's StanfordPlyProcedure reads (ply2mesh.cc:32-49); `uv` [V,2] adds the float properties
+    uv1 / uv2 it maps to Mesh::SetPointTexture (ply2mesh.cc:42-43,156-161)."""
     P = np.ascontiguousarray(P, dtype="<f4")
     idx = np.ascontiguousarray(idx, dtype="<i4")
+    uvp = "property float uv1\nproperty float uv2\n" if uv is not None else ""
     hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
-           "property float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n"
-           % (len(P), len(idx)))
+           "property float z\n%selement face %d\nproperty list uchar int vertex_indices\nend_header\n"
+           % (len(P), uvp, len(idx)))
     rec = np.empty(len(idx), dtype=[("n", "u1"), ("v", "<i4", 3)])
     rec["n"] = 3
     rec["v"] = idx
+    vert = P if uv is None else np.concatenate([P, np.ascontiguousarray(uv, dtype="<f4")], axis=1)
     with open(path, "wb") as f:
         f.write(hdr.encode("ascii"))
-        f.write(P.tobytes())
+        f.write(np.ascontiguousarray(vert, dtype="<f4").tobytes())
         f.write(rec.tobytes())
+
+
+def write_mip(path, img, tilesize=64):
+    """Writes the reference's `.mip` texture format (src/fj_mipmap.cc:124-180, 270-320): "MIPM", int32 version 1, width,
+    height, nchannels, tilesize, then the row-major tiles of tilesize x tilesize x nchannels float32.  `img` is
+    [H, W, C] with H and W multiples of `tilesize`, row 0 = top of the image.  Returns the tile array [ny, nx, ts, ts, C]."""
+    img = np.ascontiguousarray(img, np.float32)
+    h, w, c = img.shape
+    assert h % tilesize == 0 and w % tilesize == 0 and c in (1, 3, 4)
+    tiles = img.reshape(h // tilesize, tilesize, w // tilesize, tilesize, c).transpose(0, 2, 1, 3, 4)
+    tiles = np.ascontiguousarray(tiles)
+    with open(path, "wb") as f:
+        f.write(b"MIPM")
+        f.write(np.array([1, w, h, c, tilesize], "<i4").tobytes())
+        f.write(tiles.astype("<f4").tobytes())
+    return tiles
+
+
+def sphere_uv(P):
+    """Longitude / latitude texture coordinates of points around the origin (seam at -x)."""
+    P = np.asarray(P, np.float64)
+    r = np.linalg.norm(P, axis=1) + 1e-30
+    u = np.arctan2(P[:, 2], P[:, 0]) / (2 * np.pi) + .5
+    v = np.arccos(np.clip(P[:, 1] / r, -1, 1)) / np.pi
+    return np.stack([u, 1 - v], -1).astype(np.float32)
 
 
 def read_ply(path):

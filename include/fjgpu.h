@@ -101,7 +101,7 @@ typedef struct fjgpu_shader {
   int32_t kind;
   int32_t do_reflect;       /* plastic: any(reflect > 0)  (plastic_shader.cc:231-250)          */
   int32_t do_color_filter;  /* pathtracing: transmit != (1,1,1) (pathtracing_shader.cc:358-378); glass: filter_color != (1,1,1) */
-  int32_t _pad;
+  int32_t texture;          /* constant: `texture`, plastic: `diffuse_map` — 1 + index into fjgpu_textures_set, 0 = none */
   float diffuse[3];
   float reflect[3];
   float refract[3];
@@ -234,6 +234,20 @@ typedef struct fjgpu_scene_info {
   double   device_build_seconds;   /* part of it spent in the device builder (FJGPU_BUILD=device; CUDA events), 0 for host builds */
 } fjgpu_scene_info;
 int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info);
+
+/* ---- textures ------------------------------------------------------------
+ * Replaces Texture / TextureCache (src/fj_texture.cc:51-78) over a `.mip` file (src/fj_mipmap.cc:124-180: "MIPM", version,
+ * width, height, nchannels, tilesize, then (width/tilesize) x (height/tilesize) row-major tiles of tilesize x tilesize x
+ * nchannels floats).  `tiles` is the file's tile data in file order; the lookup is the reference's nearest-texel tile
+ * arithmetic (64 texels per tile side).  nchannels 1, 3 or 4 (FrameBuffer::GetColor, src/fj_framebuffer.cc:84-101). */
+typedef struct fjgpu_texture {
+  int32_t width, height, nchannels, tilesize;
+  const float *tiles;
+} fjgpu_texture;
+int fjgpu_textures_set(fjgpu_context *ctx, int32_t n, const fjgpu_texture *textures);
+/* Per-vertex texture coordinates of an uploaded mesh (Mesh::AddPointTexture, src/fj_mesh.h; interpolated as
+ * Mesh::ray_intersect does, src/fj_mesh.cc:280-291).  uv2 = nverts x 2 floats; NULL removes them. */
+int fjgpu_mesh_set_uv(fjgpu_context *ctx, int32_t mesh_id, const float *uv2, int32_t nverts);
 
 /* Re-sends the retained pinned host copy of every scene array (BVH nodes, triangle packets, normals, indices,
  * instance / group / shader / light tables) host -> device and reports the bytes copied: what a host that

@@ -268,11 +268,13 @@ inline bool RayInRange(const Ray &r, Real t) { return r.tmin <= t && t <= r.tmax
 
 struct Isect {                       // src/fj_intersection.h:21-55
   V3 P, N; int object, prim_id, shading_group_id; Real t_hit; Real u, v;
-  Isect() : object(-1), prim_id(0), shading_group_id(0), t_hit(REAL_MAX), u(0), v(0) {}
+  float tu, tv;                      // TexCoord uv
+  Isect() : object(-1), prim_id(0), shading_group_id(0), t_hit(REAL_MAX), u(0), v(0), tu(0), tv(0) {}
 };
 
 struct Mesh {                        // src/fj_mesh.h:200-216 (subset on the path)
   std::vector<V3> P, N; std::vector<int32_t> idx; std::vector<int32_t> group; int nfaces;
+  std::vector<float> uv;             // 2 floats per vertex (empty: no point texture)
   Box bounds;                        // Mesh::ComputeBounds, src/fj_mesh.cc:235-244
   // GridAccelerator state, src/fj_grid_accelerator.h
   Box acc_bounds;                    // Accelerator::bounds_ (padded), src/fj_accelerator.cc:60-64
@@ -299,7 +301,7 @@ void compute_normals(Mesh &m) {
   for (int i = 0; i < nv; i++) m.N[i] = Normalize(m.N[i]);
 }
 
-// Mesh::ray_intersect, src/fj_mesh.cc:246-308 (no velocity, no uv) wrapped by
+// Mesh::ray_intersect, src/fj_mesh.cc:246-308 (no velocity) wrapped by
 // PrimitiveSet::RayIntersect, src/fj_primitive_set.cc:10-26
 bool mesh_ray_intersect(const Mesh &m, int prim, const Ray &ray, Isect *is) {
   V3 P0, P1, P2; m.tri(prim, P0, P1, P2);
@@ -309,6 +311,12 @@ bool mesh_ray_intersect(const Mesh &m, int prim, const Ray &ray, Isect *is) {
     const V3 N0 = m.N[m.idx[3 * prim]], N1 = m.N[m.idx[3 * prim + 1]], N2 = m.N[m.idx[3 * prim + 2]];
     is->N = (1 - u - v) * N0 + u * N1 + v * N2;        // TriComputeNormal, fj_triangle.cc:44-49
   } else is->N = V3(0, 0, 0);
+  if (!m.uv.empty()) {                                   // UV = (1-u-v) UV0 + u UV1 + v UV2, fj_mesh.cc:280-291
+    const int i0 = m.idx[3 * prim], i1 = m.idx[3 * prim + 1], i2 = m.idx[3 * prim + 2];
+    const float tt = 1 - u - v;
+    is->tu = tt * m.uv[2 * i0] + u * m.uv[2 * i1] + v * m.uv[2 * i2];
+    is->tv = tt * m.uv[2 * i0 + 1] + u * m.uv[2 * i1 + 1] + v * m.uv[2 * i2 + 1];
+  } else { is->tu = 0; is->tv = 0; }
   is->P = RayPointAt(ray, t);
   is->object = -1; is->prim_id = prim;
   is->shading_group_id = m.group.empty() ? 0 : m.group[prim];
@@ -446,7 +454,10 @@ int build_bvh(Group &g, BvhPrim **p, int begin, int end, int axis) {    // :253-
 struct Shader { fjgpu_shader d; };
 struct Light { fjgpu_light d; Mat fwd; std::vector<V3> dome_dir; std::vector<Col> dome_col; XorShift rng; };
 
+// Texture over a `.mip` file's tiles (src/fj_texture.cc, src/fj_mipmap.cc:124-180)
+struct Tex { int width, height, nch, tilesize, xnt, ynt; std::vector<float> tiles; };
 struct Scene {
+  std::vector<Tex> textures;
   std::map<int, Mesh> meshes; std::vector<Instance> inst; std::vector<Group> groups;
   std::vector<Shader> shaders; std::vector<Light> lights; fjgpu_camera cam; bool built;
   Scene() : built(false) { memset(&cam, 0, sizeof cam); }
@@ -631,12 +642,35 @@ int SlIlluminance(RenderState &rs, const Cxt &cxt, const LightSample &sample, co
   return 1;
 }
 
-struct SurfIn { V3 P, N, I; Col Cd; int shaded_object; };
+struct SurfIn { V3 P, N, I; Col Cd; int shaded_object; float tu, tv; };
 
-// ConstantShader::evaluate, shaders/constant_shader/constant_shader.cc:72-94 (no texture)
-void eval_constant(const fjgpu_shader &sh, Col *Cs, float *Os) { *Cs = Col(sh.diffuse[0], sh.diffuse[1], sh.diffuse[2]); *Os = 1; }
+// TextureCache::LookupTexture, src/fj_texture.cc:51-78 (float arithmetic, as compiled) + MipInput::ReadTile's clamp
+// (src/fj_mipmap.cc:163-165) + FrameBuffer::GetColor (src/fj_framebuffer.cc:84-101)
+Col4 tex_lookup(const Tex &tx, float u, float v) {
+  const float tsu = u - std::floor(u), tsv = v - std::floor(v);
+  const float tlu = tsu * tx.xnt, tlv = (1 - tsv) * tx.ynt;
+  const int xtile = (int)std::floor(tlu), ytile = (int)std::floor(tlv);
+  const int xpxl = (int)((tlu - std::floor(tlu)) * 64), ypxl = (int)((tlv - std::floor(tlv)) * 64);
+  const int x = Clamp(xtile, 0, tx.xnt - 1), y = Clamp(ytile, 0, tx.ynt - 1);
+  const float *px = &tx.tiles[((size_t)(y * tx.xnt + x) * tx.tilesize * tx.tilesize + (size_t)ypxl * tx.tilesize + xpxl) * tx.nch];
+  Col4 c;
+  if (tx.nch == 1) { c.r = c.g = c.b = px[0]; c.a = 1; }
+  else if (tx.nch == 3) { c.r = px[0]; c.g = px[1]; c.b = px[2]; c.a = 1; }
+  else if (tx.nch == 4) { c.r = px[0]; c.g = px[1]; c.b = px[2]; c.a = px[3]; }
+  return c;
+}
 
-// PlasticShader::evaluate, shaders/plastic_shader/plastic_shader.cc:101-179 (no maps)
+// ConstantShader::evaluate, shaders/constant_shader/constant_shader.cc:72-94
+void eval_constant(const Scene &s, const fjgpu_shader &sh, const SurfIn &in, Col *Cs, float *Os) {
+  if (sh.texture) {
+    Col4 C_tex = tex_lookup(s.textures[sh.texture - 1], in.tu, in.tv);
+    C_tex.r *= sh.diffuse[0]; C_tex.g *= sh.diffuse[1]; C_tex.b *= sh.diffuse[2];
+    *Cs = Col(C_tex.r, C_tex.g, C_tex.b);
+  } else *Cs = Col(sh.diffuse[0], sh.diffuse[1], sh.diffuse[2]);
+  *Os = 1;
+}
+
+// PlasticShader::evaluate, shaders/plastic_shader/plastic_shader.cc:101-179 (diffuse_map; no bump map)
 void eval_plastic(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, const SurfIn &in, Col *Cs, float *Os) {
   Col diff, spec;
   const V3 Nf = SlFaceforward(in.I, in.N);
@@ -648,9 +682,11 @@ void eval_plastic(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, const
     Kd = Max(0, Kd);
     diff.r += Kd * Lout.Cl.r; diff.g += Kd * Lout.Cl.g; diff.b += Kd * Lout.Cl.b;
   }
-  Cs->r = diff.r * sh.diffuse[0] * 1.f + spec.r;
-  Cs->g = diff.g * sh.diffuse[1] * 1.f + spec.g;
-  Cs->b = diff.b * sh.diffuse[2] * 1.f + spec.b;
+  Col4 diff_map; diff_map.r = diff_map.g = diff_map.b = diff_map.a = 1;
+  if (sh.texture) diff_map = tex_lookup(rs.s->textures[sh.texture - 1], in.tu, in.tv);
+  Cs->r = diff.r * sh.diffuse[0] * diff_map.r + spec.r;
+  Cs->g = diff.g * sh.diffuse[1] * diff_map.g + spec.g;
+  Cs->b = diff.b * sh.diffuse[2] * diff_map.b + spec.b;
   if (sh.do_reflect) {
     Col4 C_refl; double t_hit = REAL_MAX;
     Cxt rc = cxt; rc.reflect_depth++; rc.ray_context = CXT_REFLECT_RAY;          // SlReflectContext :242-252
@@ -672,6 +708,8 @@ void eval_pathtracing(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, c
   const Col refract(sh.refract[0], sh.refract[1], sh.refract[2]);
   const Col Le(sh.emission[0], sh.emission[1], sh.emission[2]);
   Col L_diffuse, L_reflect, L_refract;
+  Col Cd = in.Cd;
+  if (sh.texture) { const Col4 m = tex_lookup(rs.s->textures[sh.texture - 1], in.tu, in.tv); Cd = Cd * Col(m.r, m.g, m.b); }    // diffuse_map :132-135
   if (Luminance(diffuse) > 0.) {                                        // integrate_diffuse :176-208
     V3 u, v, w = in.N;
     u = std::abs(w.x) > .001 ? V3(0, 1, 0) : V3(1, 0, 0);
@@ -687,7 +725,7 @@ void eval_pathtracing(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, c
     Cxt dc = cxt; dc.diffuse_depth++; dc.ray_context = CXT_DIFFUSE_RAY;          // SlDiffuseContext :230-240
     dc.trace_target = rs.s->inst[in.shaded_object].reflect_target; dc.node = cxt.node * 4 + 1;
     SlTrace(rs, dc, in.P, D, .001, 1000, &C, &t_hit);
-    L_diffuse = in.Cd * (float)Kd * diffuse * Col(C.r, C.g, C.b);
+    L_diffuse = Cd * (float)Kd * diffuse * Col(C.r, C.g, C.b);
   }
   if (Luminance(reflect) > 0.) {                                        // integrate_reflect :210-229
     const V3 R = Normalize(SlReflect(in.I, in.N));
@@ -754,6 +792,7 @@ int SlTrace(RenderState &rs, const Cxt &cxt, const V3 &o, const V3 &d, double tm
   Col4 surf;
   if (hit) {
     SurfIn in; in.shaded_object = isect.object; in.P = isect.P; in.N = isect.N; in.Cd = Col(1, 1, 1); in.I = ray.dir;
+    in.tu = isect.tu; in.tv = isect.tv;
     const Instance &inst = rs.s->inst[isect.object];
     int g = isect.shading_group_id;                                  // ObjectInstance::GetShader :177-191
     int slot = (g < 0 || g >= FJGPU_MAX_SHADING_GROUPS) ? inst.shader_of_group[0] : inst.shader_of_group[g];
@@ -762,7 +801,7 @@ int SlTrace(RenderState &rs, const Cxt &cxt, const V3 &o, const V3 &d, double tm
     if (slot < 0 || rs.s->shaders[slot].d.kind == FJGPU_SHADER_NONE) { Cs = Col(.5, 1., 0.); Os = 1; }
     else {
       const fjgpu_shader &sh = rs.s->shaders[slot].d;
-      if (sh.kind == FJGPU_SHADER_CONSTANT) eval_constant(sh, &Cs, &Os);
+      if (sh.kind == FJGPU_SHADER_CONSTANT) eval_constant(*rs.s, sh, in, &Cs, &Os);
       else if (sh.kind == FJGPU_SHADER_PLASTIC) eval_plastic(rs, cxt, sh, in, &Cs, &Os);
       else if (sh.kind == FJGPU_SHADER_GLASS) eval_glass(rs, cxt, sh, in, &Cs, &Os);
       else { rs.cur_shader = slot; eval_pathtracing(rs, cxt, sh, in, &Cs, &Os); }
@@ -872,6 +911,22 @@ int fjo_mesh(fjo_scene *sc, int mesh_id, const double *P, const double *N, int n
   m.bounds.ReverseInfinite();
   for (int i = 0; i < nfaces; i++) { Box b; m.prim_bounds(i, &b); m.bounds.AddBox(b); }
   sc->s.built = false;
+  return 0;
+}
+int fjo_mesh_set_uv(fjo_scene *sc, int mesh_id, const float *uv2, int nverts) {
+  auto it = sc->s.meshes.find(mesh_id);
+  if (it == sc->s.meshes.end() || (uv2 && nverts != (int)it->second.P.size())) return -1;
+  if (uv2) it->second.uv.assign(uv2, uv2 + 2 * (size_t)nverts); else it->second.uv.clear();
+  return 0;
+}
+int fjo_textures(fjo_scene *sc, int n, const fjgpu_texture *t) {
+  sc->s.textures.resize(n);
+  for (int i = 0; i < n; i++) {
+    Tex &x = sc->s.textures[i];
+    x.width = t[i].width; x.height = t[i].height; x.nch = t[i].nchannels; x.tilesize = t[i].tilesize;
+    x.xnt = x.width / x.tilesize; x.ynt = x.height / x.tilesize;
+    x.tiles.assign(t[i].tiles, t[i].tiles + (size_t)x.xnt * x.ynt * x.tilesize * x.tilesize * x.nch);
+  }
   return 0;
 }
 // Mesh::ComputeNormals restatement exposed for the host-side parity test

@@ -71,6 +71,8 @@ def oracle():
     lib.fjo_instances.argtypes = [vp, i32, P(a.Instance)]
     lib.fjo_groups.argtypes = [vp, i32, i32p, i32p]
     lib.fjo_shaders.argtypes = [vp, i32, P(a.Shader)]
+    lib.fjo_mesh_set_uv.argtypes = [vp, i32, P(C.c_float), i32]
+    lib.fjo_textures.argtypes = [vp, i32, P(a.Texture)]
     lib.fjo_lights.argtypes = [vp, i32, P(a.Light)]
     lib.fjo_camera.argtypes = [vp, P(a.Camera)]
     lib.fjo_build.argtypes = [vp]
@@ -142,6 +144,9 @@ class SceneDesc:
 
     def __init__(self):
         self.meshes = []      # (name, P float32 [V,3], idx int32 [F,3], ply_path or None)
+        self.mesh_uv = {}     # name -> uv float32 [V,2] (PLY properties uv1 / uv2)
+        self.textures = []    # (name, image float32 [H,W,C]) written as .mip; shaders refer to them by name in the
+                              # `texture` (constant) / `diffuse_map` (plastic, pathtracing) property
         self.shaders = []     # (name, kind str, props dict)
         self.instances = []   # dict(name, mesh, T, R, S, shader)
         self.lights = []      # dict(kind, T, R, S, intensity, color, sample_count, double_sided)
@@ -151,8 +156,13 @@ class SceneDesc:
                         seed=1)
 
     # ---- construction
-    def mesh(self, name, P, idx, ply_path=None):
+    def mesh(self, name, P, idx, ply_path=None, uv=None):
         self.meshes.append((name, np.ascontiguousarray(P, np.float32), np.ascontiguousarray(idx, np.int32), ply_path))
+        if uv is not None:
+            self.mesh_uv[name] = np.ascontiguousarray(uv, np.float32)
+
+    def texture(self, name, img):
+        self.textures.append((name, np.ascontiguousarray(img, np.float32)))
 
     def shader(self, name, kind, **props):
         self.shaders.append((name, kind, props))
@@ -191,10 +201,17 @@ class SceneDesc:
             L.append("SetProperty3 %s color %r %r %r" % ((n,) + tuple(float(x) for x in lt["color"])))
             L.append("SetProperty1 %s sample_count %d" % (n, lt["sample_count"]))
             L.append("SetProperty1 %s double_sided %d" % (n, lt["double_sided"]))
+        from fujiyama_renderer_b200 import synth
+        for tname, img in self.textures:
+            mip = os.path.join(workdir, tname + ".mip")
+            synth.write_mip(mip, img)
+            L.append("NewTexture %s %s" % (tname, mip))
         for name, kind, props in self.shaders:
             L.append("NewShader %s %s" % (name, SHADER_PLUGIN[kind][0]))
             for k, v in props.items():
-                if np.isscalar(v):
+                if isinstance(v, str):
+                    L.append("AssignTexture %s %s %s" % (name, k, v))
+                elif np.isscalar(v):
                     L.append("SetProperty1 %s %s %r" % (name, k, float(v)))
                 else:
                     L.append("SetProperty3 %s %s %r %r %r" % ((name, k) + tuple(float(x) for x in v)))
@@ -202,7 +219,7 @@ class SceneDesc:
         for name, P, idx, ply in self.meshes:
             if ply is None:
                 ply = os.path.join(workdir, name + ".ply")
-                synth.write_ply(ply, P, idx)
+                synth.write_ply(ply, P, idx, self.mesh_uv.get(name))
             L.append("NewMesh %s" % name)
             L.append("NewProcedure %s_proc stanfordply_procedure" % name)
             L.append("AssignMesh %s_proc mesh %s" % (name, name))
@@ -288,11 +305,28 @@ class SceneDesc:
             o.fjo_compute_normals(dptr(P64), len(P64), iptr(idx), len(idx) // 3, dptr(N64))
             meshes.append((mid, P64, N64, idx))
         out["meshes"] = meshes
+        out["mesh_uv"] = {mesh_ids[n]: uv for n, uv in self.mesh_uv.items()}
+        # textures: the tile arrays a .mip file of the image holds (synth.write_mip), as fjgpu_texture structs
+        tex_ids = {}
+        texs = (a.Texture * max(1, len(self.textures)))()
+        for i, (tname, img) in enumerate(self.textures):
+            tex_ids[tname] = i
+            h, w, c = img.shape
+            tiles = np.ascontiguousarray(img.reshape(h // 64, 64, w // 64, 64, c).transpose(0, 2, 1, 3, 4), np.float32)
+            out.setdefault("_keep", []).append(tiles)
+            texs[i].width, texs[i].height, texs[i].nchannels, texs[i].tilesize = w, h, c, 64
+            texs[i].tiles = fptr(tiles)
+        out["textures"] = texs
+        out["ntextures"] = len(self.textures)
         sh_ids = {}
         shs = (a.Shader * max(1, len(self.shaders)))()
         for i, (name, kind, props) in enumerate(self.shaders):
             sh_ids[name] = i
-            shs[i] = self.shader_struct(kind, props)
+            shs[i] = self.shader_struct(kind, {k: v for k, v in props.items() if not isinstance(v, str)})
+            for k, v in props.items():
+                if isinstance(v, str):
+                    assert (kind, k) in (("constant", "texture"), ("plastic", "diffuse_map"), ("pathtracing", "diffuse_map"))
+                    shs[i].texture = tex_ids[v] + 1
         out["shaders"] = shs
         out["nshaders"] = len(self.shaders)
         ins = (a.Instance * max(1, len(self.instances)))()
@@ -365,6 +399,9 @@ def oracle_scene(st):
     sc = o.fjo_scene_new()
     for mid, P, N, idx in st["meshes"]:
         o.fjo_mesh(sc, mid, dptr(P), dptr(N), len(P), iptr(idx), None, len(idx) // 3)
+    for mid, uv in st.get("mesh_uv", {}).items():
+        assert o.fjo_mesh_set_uv(sc, mid, fptr(uv), len(uv)) == 0
+    o.fjo_textures(sc, st.get("ntextures", 0), st.get("textures"))
     o.fjo_instances(sc, st["ninstances"], st["instances"])
     o.fjo_groups(sc, 1, iptr(st["group_offsets"]), iptr(st["group_ids"]))
     o.fjo_shaders(sc, st["nshaders"], st["shaders"])
