@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x;
   const RayRec *rays = a.queue[a.cur];
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->count[a.cur ^ 1] = 0;      // the queue k_shade fills next: nobody touches it during this kernel
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
   const DScene &sc = a.sc;
   int stack[FJ_STACK4];

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(FJ_QT, MINB) k_extend3(const RenderArgs a, con
   const int tid = threadIdx.x, lane = tid & 31, s = tid & 3, rs = tid >> 2, qbase = lane & 28;
   int *const stack = stack_mem + rs * stack_stride;
   const RayRec *rays = a.queue[a.cur];
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->count[a.cur ^ 1] = 0;      // the queue k_shade fills next
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
   const DScene &sc = a.sc;
   const int SENTINEL = (int)0x80000000, DONE = (int)0x80000001, IDLE = (int)0x80000002;

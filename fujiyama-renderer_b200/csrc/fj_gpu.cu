@@ -597,8 +597,10 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         ev_shade.push_back(s0); ev_shade.push_back(s1);
         for (int w = 0; w < pl.waves; w++) {
           // head of the current queue and the count of the next one start at zero
-          CK(cudaMemsetAsync(ctl_p + offsetof(fj::QueueCtl, head), 0, 4, ctx->stream));
-          CK(cudaMemsetAsync(ctl_p + offsetof(fj::QueueCtl, count) + 4 * (a.cur ^ 1), 0, 4, ctx->stream));
+          if (env_int("FJGPU_CTL_MEMSET", 0)) {     // (the kernels reset the counters themselves: k_extend* the next queue's count, k_shade the head)
+            CK(cudaMemsetAsync(ctl_p + offsetof(fj::QueueCtl, head), 0, 4, ctx->stream));
+            CK(cudaMemsetAsync(ctl_p + offsetof(fj::QueueCtl, count) + 4 * (a.cur ^ 1), 0, 4, ctx->stream));
+          }
           cudaEvent_t e0 = pool_event(ctx, &evn), e1 = pool_event(ctx, &evn), e2 = pool_event(ctx, &evn);
           if (a.hist) CK(cudaMemsetAsync(a.hist, 0, ((size_t)a.sort_bins + 1) * 4, ctx->stream));
           CK(cudaEventRecord(e0, ctx->stream));

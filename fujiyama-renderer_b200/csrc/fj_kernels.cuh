@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const RayRec *rays = a.queue[a.cur];
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->count[a.cur ^ 1] = 0;      // the queue k_shade fills next
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
   const DScene &sc = a.sc;
   int stack[FJ_STACK4];
@@ -690,6 +691,7 @@ template <typename T, bool PLASTIC, int MINB = (PLASTIC ? 3 : 5)>
 __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->head = 0;                  // the next k_extend starts at the queue head
   const RayRec *rays = a.queue[a.cur];
   ShadeCounters cnt; memset(&cnt, 0, sizeof cnt);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
