@@ -407,7 +407,9 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
   const size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 4096) << 20;
   const size_t per_slot = sizeof(fj::Accum) + (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec));
   long per = (long)(cap / ((size_t)pl->wstride * per_slot));
-  pl->tiles_per_batch = (int)std::max(1l, std::min<long>(per, std::max(ntiles, 1)));
+  per = std::max(1l, std::min<long>(per, std::max(ntiles, 1)));
+  const long nbatches = (std::max(ntiles, 1) + per - 1) / per;             // equal batches: no short last batch with long tails
+  pl->tiles_per_batch = (int)((std::max(ntiles, 1) + nbatches - 1) / nbatches);
   return 0;
 }
 
