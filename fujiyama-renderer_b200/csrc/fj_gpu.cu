@@ -1,9 +1,10 @@
 // fj_gpu.cu — libfjgpu.so: the extern "C" ABI of include/fjgpu.h over the sm_100a kernels.
 //
 // Host side of the device path: keeps the scene description the caller hands over (meshes, instances,
-// object groups, shaders, lights, camera), builds the two BVH levels (fj_bvh.cc), lays everything out in
-// HBM (DESIGN.md "Data layout"), and runs the frame: batches of tiles -> k_render_samples ->
-// k_resolve_tiles -> packed tile blocks -> host frame / device frame / caller's device buffer.
+// object groups, shaders, textures, lights, camera), builds the two BVH levels (fj_bvh.cc on the host or
+// fj_build.cu on the device), lays everything out in HBM (DESIGN.md "Data layout"), and runs the frame:
+// batches of tiles -> k_generate -> (k_extend2 -> k_shade) x rounds -> k_resolve_tiles -> packed tile blocks ->
+// host frame / device frame / caller's device buffer.
 // There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
 #include "fjgpu.h"
 #include "fj_bvh.h"
