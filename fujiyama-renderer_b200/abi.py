@@ -31,7 +31,8 @@ class Shader(C.Structure):
                 ("do_color_filter", C.c_int32), ("texture", C.c_int32),
                 ("diffuse", C.c_float * 3), ("reflect", C.c_float * 3),
                 ("refract", C.c_float * 3), ("emission", C.c_float * 3),
-                ("transmit", C.c_float * 3), ("ior", C.c_float), ("opacity", C.c_float)]
+                ("transmit", C.c_float * 3), ("ior", C.c_float), ("opacity", C.c_float),
+                ("bump_texture", C.c_int32), ("bump_amplitude", C.c_float)]
 
 
 class Texture(C.Structure):

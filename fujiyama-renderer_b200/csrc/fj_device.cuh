@@ -73,6 +73,7 @@ struct DMesh {
   const float4 *nodesq;     // the 4-wide tree with 8-bit quantised child boxes (fj_bvh.h NodeQ64), null if not representable
   float bmagq, pad2;        // bound magnitude of the decoded planes
   const float *uv;          // per-vertex texture coordinates, 2 floats per vertex (null: uv = 0, fj_mesh.cc:292-297)
+  const double *P;          // vertex positions by vertex index (FP64 as given), kept only for meshes with uv: dPdu / dPdv of bump maps
 };
 struct DInstance {
   double inv[12];           // rows 0..2 of MatInverse(matrix): world -> object (fj_object_instance.cc:222-225)
@@ -97,6 +98,7 @@ struct DShader {
   int32_t kind, do_reflect, do_color_filter, texture;     // texture: 1 + index into DScene::textures, 0 = none
   float diffuse[3], reflect[3], refract[3], emission[3], transmit[3];
   float ior, opacity;
+  int32_t bump_texture; float bump_amplitude;
 };
 struct DLight {
   int32_t kind, sample_count, double_sided, dome_count;
@@ -412,6 +414,29 @@ __device__ __forceinline__ void hit_uv(const DScene &sc, const Hit &h, float *tu
   *tv = (float)dadd(dadd((double)fmul(t, a.y), dmul(h.u, (double)b.y)), dmul(h.v, (double)c.y));
 }
 
+// dPdu, dPdv of a hit in world space: TriComputeDerivatives (src/fj_triangle.cc:51-74: float uv differences and determinant,
+// `const float invdet = 1. / determinant`, FP64 edges) inside Mesh::ray_intersect (fj_mesh.cc:287-290), then the instance's
+// forward matrix (XfmTransformVector, fj_object_instance.cc:237-238).  Zero without uv or with a degenerate uv triangle.
+__device__ __forceinline__ void hit_derivatives(const DScene &sc, const Hit &h, D3 *dPdu, D3 *dPdv) {
+  const DInstance &in = sc.inst[h.inst];
+  const DMesh &m = sc.meshes[in.mesh];
+  *dPdu = mk(0, 0, 0); *dPdv = mk(0, 0, 0);
+  if (!m.uv || !m.P) return;
+  const int i0 = m.idx[3 * (size_t)h.prim], i1 = m.idx[3 * (size_t)h.prim + 1], i2 = m.idx[3 * (size_t)h.prim + 2];
+  const D3 P0 = mk(m.P[3 * (size_t)i0], m.P[3 * (size_t)i0 + 1], m.P[3 * (size_t)i0 + 2]);
+  const D3 P1 = mk(m.P[3 * (size_t)i1], m.P[3 * (size_t)i1 + 1], m.P[3 * (size_t)i1 + 2]);
+  const D3 P2 = mk(m.P[3 * (size_t)i2], m.P[3 * (size_t)i2 + 1], m.P[3 * (size_t)i2 + 2]);
+  const float2 t0 = reinterpret_cast<const float2 *>(m.uv)[i0], t1 = reinterpret_cast<const float2 *>(m.uv)[i1], t2 = reinterpret_cast<const float2 *>(m.uv)[i2];
+  const D3 dP1 = P1 - P0, dP2 = P2 - P0;
+  const float du1 = __fsub_rn(t1.x, t0.x), du2 = __fsub_rn(t2.x, t0.x), dv1 = __fsub_rn(t1.y, t0.y), dv2 = __fsub_rn(t2.y, t0.y);
+  const float det = __fsub_rn(fmul(du1, dv2), fmul(dv1, du2));
+  if (det == 0.f) return;
+  const float invdet = (float)ddiv(1., (double)det);
+  const D3 a = ((double)dv2 * dP1 - (double)dv1 * dP2) * (double)invdet;
+  const D3 b = ((double)(-du2) * dP1 + (double)du1 * dP2) * (double)invdet;
+  *dPdu = mat_vector(in.fwd, a); *dPdv = mat_vector(in.fwd, b);
+}
+
 // TextureCache::LookupTexture, src/fj_texture.cc:51-78: wrap to [0,1), flip v, tile = floor(coordinate * tile count) clamped
 // as MipInput::ReadTile does (src/fj_mipmap.cc:163-165), texel = (int)(fraction * 64) inside the tile; all in float as the
 // reference compiles it.  Colour as FrameBuffer::GetColor (src/fj_framebuffer.cc:84-101).
@@ -426,6 +451,24 @@ __device__ __forceinline__ float4 tex_lookup(const DTexture &tx, float u, float 
   if (tx.nch == 3) return make_float4(px[0], px[1], px[2], 1.f);
   if (tx.nch == 4) return make_float4(px[0], px[1], px[2], px[3]);
   return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__device__ __forceinline__ float luminance4(const float4 &c) {       // Luminance4, fj_color.h:280-283
+  return (float)dadd(dadd(dmul(.298912, (double)c.x), dmul(.586611, (double)c.y)), dmul(.114478, (double)c.z));
+}
+// SlBumpMapping, src/fj_shading.cc:418-465 (both cross products are scaled by du, as the reference does)
+__device__ __forceinline__ D3 sl_bump_mapping(const DTexture &tx, const D3 &dPdu, const D3 &dPdv, float tu, float tv, double amplitude, const D3 &N) {
+  if (tx.width == 0 || tx.height == 0) return N;
+  const float du = (float)ddiv(1., (double)tx.width), dv = (float)ddiv(1., (double)tx.height);
+  float val0 = luminance4(tex_lookup(tx, __fsub_rn(tu, du), tv)), val1 = luminance4(tex_lookup(tx, fadd(tu, du), tv));
+  const float Bu = __fdiv_rn(__fsub_rn(val0, val1), fmul(2.f, du));
+  val0 = luminance4(tex_lookup(tx, tu, __fsub_rn(tv, dv))); val1 = luminance4(tex_lookup(tx, tu, fadd(tv, dv)));
+  const float Bv = __fdiv_rn(__fsub_rn(val0, val1), fmul(2.f, dv));
+  const D3 NdPdu = cross(N, dPdu) * (double)du, NdPdv = cross(N, dPdv) * (double)du;
+  const D3 nb = mk(dadd(N.x, dmul(amplitude, dsub(dmul((double)Bv, NdPdu.x), dmul((double)Bu, NdPdv.x)))),
+                   dadd(N.y, dmul(amplitude, dsub(dmul((double)Bv, NdPdu.y), dmul((double)Bu, NdPdv.y)))),
+                   dadd(N.z, dmul(amplitude, dsub(dmul((double)Bv, NdPdu.z), dmul((double)Bu, NdPdv.z)))));
+  return normalize(nb);
 }
 
 // Opacity the shader of an occluder returns to a shadow ray (Os of evaluate(); the colour is unused and

@@ -34,11 +34,12 @@ struct DevBuf {
 };
 
 struct MeshRec {
-  DevBuf nodes, nodes4, nodes4q, nodesq, tri, N, idx, group, uv;
+  DevBuf nodes, nodes4, nodes4q, nodesq, tri, N, idx, group, uv, P;
+  std::vector<double> hostP;     // vertex positions kept until fjgpu_mesh_set_uv decides whether the device needs them
   fj::DMesh d;
   double bmin[3], bmax[3];      // exact FP64 bounds of the mesh (Mesh::ComputeBounds, fj_mesh.cc:235-244)
   int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0, max_depth4 = 0, nnodes4 = 0, stack_need4 = 0;
-  void release() { uv.release(); nodes.release(); nodes4.release(); nodes4q.release(); nodesq.release(); tri.release(); N.release(); idx.release(); group.release(); }
+  void release() { uv.release(); P.release(); nodes.release(); nodes4.release(); nodes4q.release(); nodesq.release(); tri.release(); N.release(); idx.release(); group.release(); }
 };
 
 }  // namespace
@@ -261,7 +262,8 @@ int commit_scene(fjgpu_context *ctx) {
   std::vector<fj::DShader> ds(ctx->shaders.size());
   for (size_t i = 0; i < ds.size(); i++) {
     const fjgpu_shader &s = ctx->shaders[i]; fj::DShader &d = ds[i];
-    d.kind = s.kind; d.do_reflect = s.do_reflect; d.do_color_filter = s.do_color_filter; d.texture = s.texture;
+    d.kind = s.kind; d.do_reflect = s.do_reflect; d.do_color_filter = s.do_color_filter; d.texture = s.texture; d.bump_texture = s.bump_texture; d.bump_amplitude = s.bump_amplitude;
+    if (s.bump_texture < 0 || s.bump_texture > (int)ctx->textures.size()) return fail(ctx, FJGPU_ERR_INVALID, "shader refers to an unknown bump texture");
     if (s.texture < 0 || s.texture > (int)ctx->textures.size()) return fail(ctx, FJGPU_ERR_INVALID, "shader refers to an unknown texture");
     memcpy(d.diffuse, s.diffuse, 12); memcpy(d.reflect, s.reflect, 12); memcpy(d.refract, s.refract, 12);
     memcpy(d.emission, s.emission, 12); memcpy(d.transmit, s.transmit, 12);
@@ -754,6 +756,7 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
   MeshRec &m = ctx->meshes[mesh_id];
   m.release();
   m.nfaces = nfaces; m.nverts = nverts;
+  m.hostP.assign(P, P + 3 * (size_t)nverts);
   bool f32ok = true;
   for (size_t i = 0; i < 3 * (size_t)nverts && f32ok; i++) f32ok = ((double)(float)P[i] == P[i]);
   if (env_int("FJGPU_FORCE_TRI64", 0)) f32ok = false;
@@ -943,11 +946,13 @@ int fjgpu_mesh_set_uv(fjgpu_context *ctx, int32_t mesh_id, const float *uv2, int
   if (it == ctx->meshes.end()) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_mesh_set_uv: unknown mesh_id");
   MeshRec &m = it->second;
   CK(cudaSetDevice(ctx->device));
-  if (!uv2) { m.uv.release(); m.d.uv = nullptr; ctx->dirty = true; return FJGPU_OK; }
+  if (!uv2) { m.uv.release(); m.P.release(); m.d.uv = nullptr; m.d.P = nullptr; ctx->dirty = true; return FJGPU_OK; }
   if (nverts != m.nverts) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_mesh_set_uv: vertex count differs from the uploaded mesh");
   if (int rc = dev_upload(ctx, m.uv, uv2, (size_t)nverts * 8, true)) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
-  m.d.uv = (const float *)m.uv.p;
+  if (int rc = dev_upload(ctx, m.P, m.hostP.data(), m.hostP.size() * 8, true)) return rc;       // dPdu / dPdv of bump maps need the vertices by index
+  CK(cudaStreamSynchronize(ctx->stream));
+  m.d.uv = (const float *)m.uv.p; m.d.P = (const double *)m.P.p;
   ctx->dirty = true;
   return FJGPU_OK;
 }
@@ -1073,7 +1078,7 @@ int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent) {
   CK(cudaSetDevice(ctx->device));
   if (int rc = commit_scene(ctx)) return rc;
   std::vector<DevBuf *> all = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights};
-  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.nodes4q, &m.nodesq, &m.tri, &m.N, &m.idx, &m.group, &m.uv}) all.push_back(b); }
+  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.nodes4q, &m.nodesq, &m.tri, &m.N, &m.idx, &m.group, &m.uv, &m.P}) all.push_back(b); }
   for (auto &b : ctx->d_tex_tiles) all.push_back(&b);
   all.push_back(&ctx->d_textures);
   for (auto &b : ctx->d_group_nodes) all.push_back(&b);

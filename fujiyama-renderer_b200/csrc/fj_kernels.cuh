@@ -213,7 +213,12 @@ struct Shading {
       sink.add(fmul(thr.r, sh.diffuse[0]), fmul(thr.g, sh.diffuse[1]), fmul(thr.b, sh.diffuse[2]));
     } else if (PLASTIC && kind == 2) {                             // PlasticShader::evaluate, plastic_shader.cc:101-179
       const DShader &sh = sc.shaders[slot];
-      const D3 Nf = sl_faceforward(ray.d, N);
+      D3 Nf = sl_faceforward(ray.d, N);
+      if (sh.bump_texture) {                                       // plastic_shader.cc:115-123
+        float tu, tv; hit_uv(sc, h, &tu, &tv);
+        D3 dPdu, dPdv; hit_derivatives(sc, h, &dPdu, &dPdv);
+        Nf = sl_bump_mapping(sc.textures[sh.bump_texture - 1], dPdu, dPdv, tu, tv, (double)sh.bump_amplitude, Nf);
+      }
       const C3 diff = gather_lights(P, Nf, h.inst, cur.node);
       float4 dm = make_float4(1.f, 1.f, 1.f, 1.f);                 // diffuse_map, plastic_shader.cc:148-156: Cs = diff * diffuse * diff_map
       if (sh.texture) { float tu, tv; hit_uv(sc, h, &tu, &tv); dm = tex_lookup(sc.textures[sh.texture - 1], tu, tv); }

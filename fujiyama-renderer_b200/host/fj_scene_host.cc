@@ -134,7 +134,7 @@ struct Xform {
 struct Plugin { std::string name; int kind; };   // kind: FJGPU_SHADER_* for shaders, 100 = StanfordPlyProcedure
 struct Mesh { std::vector<double> P, N; std::vector<int32_t> idx; std::vector<float> uv; bool dirty = true; };
 struct Texture { int width = 0, height = 0, nch = 0, tilesize = 0; std::vector<float> tiles; };   // a `.mip` file's header and tiles (src/fj_mipmap.cc:124-180)
-struct Shader { int plugin; std::map<std::string, std::array<double, 4>> props; ID texture = SI_BADID; };   // texture: the `texture` / `diffuse_map` property
+struct Shader { int plugin; std::map<std::string, std::array<double, 4>> props; ID texture = SI_BADID, bump = SI_BADID; };   // texture: the `texture` / `diffuse_map` property
 struct Procedure { int plugin; ID mesh = SI_BADID; std::string filepath, io_mode; };
 struct Instance { ID mesh; Xform x; std::map<std::string, ID> shaders; ID reflect = SI_BADID, refract = SI_BADID, shadow = SI_BADID; };
 struct Group { std::vector<int> members; };
@@ -307,6 +307,7 @@ fjgpu_shader flatten_shader(const Scene &sc, const Shader &s) {
   o.kind = kind;
   auto P = [&](const char *n) { return s.props.find(n)->second; };
   { int tt, ti; if (s.texture != SI_BADID && decode_id(s.texture, &tt, &ti) && tt == Type_Texture && kind != FJGPU_SHADER_GLASS) o.texture = ti + 1; }
+  { int tt, ti; if (s.bump != SI_BADID && decode_id(s.bump, &tt, &ti) && tt == Type_Texture && kind == FJGPU_SHADER_PLASTIC) { o.bump_texture = ti + 1; o.bump_amplitude = (float)P("bump_amplitude")[0]; } }
   if (kind == FJGPU_SHADER_CONSTANT) {                                      // constant_shader.cc:96-107
     for (int k = 0; k < 3; k++) o.diffuse[k] = clamp0(P("diffuse")[k]);
   } else if (kind == FJGPU_SHADER_PLASTIC) {                                // plastic_shader.cc:183-273
@@ -699,13 +700,14 @@ Status SiAssignObjectGroup(ID id, const char *name, ID group) {
 Status SiAssignPointCloud(ID, const char *, ID) { return SI_FAIL; }
 Status SiAssignTurbulence(ID, const char *, ID) { return SI_FAIL; }
 // SiAssignTexture, src/fj_scene_interface.cc:786-805: the PropTexture properties of the device shaders
-// (constant_shader `texture`, plastic_shader / pathtracing_shader `diffuse_map`; bump maps have no device implementation)
+// (constant_shader `texture`, plastic_shader / pathtracing_shader `diffuse_map`, plastic_shader `bump_map`)
 Status SiAssignTexture(ID id, const char *name, ID texture) {
   Shader *sh = the_scene ? get(the_scene->shaders, id, Type_Shader) : nullptr;
   if (!sh || !name || !get(the_scene->textures, texture, Type_Texture)) return SI_FAIL;
   const int kind = the_scene->plugins[sh->plugin].kind;
   const std::string n(name);
   const bool okname = (kind == FJGPU_SHADER_CONSTANT && n == "texture") || ((kind == FJGPU_SHADER_PLASTIC || kind == FJGPU_SHADER_PATHTRACING) && n == "diffuse_map");
+  if (kind == FJGPU_SHADER_PLASTIC && n == "bump_map") { sh->bump = texture; return ok(); }      // SlBumpMapping, src/fj_shading.cc:418-465
   if (!okname) return failmsg("AssignTexture " + n + ": no device implementation of this texture property");
   sh->texture = texture;
   return ok();

@@ -269,6 +269,7 @@ inline bool RayInRange(const Ray &r, Real t) { return r.tmin <= t && t <= r.tmax
 struct Isect {                       // src/fj_intersection.h:21-55
   V3 P, N; int object, prim_id, shading_group_id; Real t_hit; Real u, v;
   float tu, tv;                      // TexCoord uv
+  V3 dPdu, dPdv;
   Isect() : object(-1), prim_id(0), shading_group_id(0), t_hit(REAL_MAX), u(0), v(0), tu(0), tv(0) {}
 };
 
@@ -316,7 +317,18 @@ bool mesh_ray_intersect(const Mesh &m, int prim, const Ray &ray, Isect *is) {
     const float tt = 1 - u - v;
     is->tu = tt * m.uv[2 * i0] + u * m.uv[2 * i1] + v * m.uv[2 * i2];
     is->tv = tt * m.uv[2 * i0 + 1] + u * m.uv[2 * i1 + 1] + v * m.uv[2 * i2 + 1];
-  } else { is->tu = 0; is->tv = 0; }
+    // TriComputeDerivatives, src/fj_triangle.cc:51-74
+    const V3 dP1 = P1 - P0, dP2 = P2 - P0;
+    const float du1 = m.uv[2 * i1] - m.uv[2 * i0], du2 = m.uv[2 * i2] - m.uv[2 * i0];
+    const float dv1 = m.uv[2 * i1 + 1] - m.uv[2 * i0 + 1], dv2 = m.uv[2 * i2 + 1] - m.uv[2 * i0 + 1];
+    const float determinant = du1 * dv2 - dv1 * du2;
+    if (determinant == 0) { is->dPdu = V3(0, 0, 0); is->dPdv = V3(0, 0, 0); }
+    else {
+      const float invdet = 1. / determinant;
+      is->dPdu = (dv2 * dP1 - dv1 * dP2) * invdet;
+      is->dPdv = (-du2 * dP1 + du1 * dP2) * invdet;
+    }
+  } else { is->tu = 0; is->tv = 0; is->dPdu = V3(0, 0, 0); is->dPdv = V3(0, 0, 0); }
   is->P = RayPointAt(ray, t);
   is->object = -1; is->prim_id = prim;
   is->shading_group_id = m.group.empty() ? 0 : m.group[prim];
@@ -474,6 +486,7 @@ bool instance_ray_intersect(const Scene &s, int iid, const Ray &ray, Isect *isec
   if (!grid_intersect(m, ro, isect)) return false;
   isect->P = MatPoint(in.fwd, isect->P);
   isect->N = Normalize(MatVector(in.fwd, isect->N));
+  isect->dPdu = MatVector(in.fwd, isect->dPdu); isect->dPdv = MatVector(in.fwd, isect->dPdv);     // fj_object_instance.cc:237-238
   isect->object = iid;
   return true;
 }
@@ -642,7 +655,7 @@ int SlIlluminance(RenderState &rs, const Cxt &cxt, const LightSample &sample, co
   return 1;
 }
 
-struct SurfIn { V3 P, N, I; Col Cd; int shaded_object; float tu, tv; };
+struct SurfIn { V3 P, N, I; Col Cd; int shaded_object; float tu, tv; V3 dPdu, dPdv; };
 
 // TextureCache::LookupTexture, src/fj_texture.cc:51-78 (float arithmetic, as compiled) + MipInput::ReadTile's clamp
 // (src/fj_mipmap.cc:163-165) + FrameBuffer::GetColor (src/fj_framebuffer.cc:84-101)
@@ -660,6 +673,25 @@ Col4 tex_lookup(const Tex &tx, float u, float v) {
   return c;
 }
 
+inline float Luminance4(const Col4 &A) { return .298912 * A.r + .586611 * A.g + .114478 * A.b; }     // fj_color.h:280-283
+// SlBumpMapping, src/fj_shading.cc:418-465
+V3 SlBumpMapping(const Tex &bump, const V3 &dPdu, const V3 &dPdv, float tu, float tv, double amplitude, const V3 &N) {
+  if (bump.width == 0 || bump.height == 0) return N;
+  const float du = 1. / bump.width, dv = 1. / bump.height;
+  float val0 = Luminance4(tex_lookup(bump, tu - du, tv)), val1 = Luminance4(tex_lookup(bump, tu + du, tv));
+  const float Bu = (val0 - val1) / (2 * du);
+  val0 = Luminance4(tex_lookup(bump, tu, tv - dv)); val1 = Luminance4(tex_lookup(bump, tu, tv + dv));
+  const float Bv = (val0 - val1) / (2 * dv);
+  V3 N_dPdu = Cross(N, dPdu), N_dPdv = Cross(N, dPdv);
+  N_dPdu.x *= du; N_dPdu.y *= du; N_dPdu.z *= du;
+  N_dPdv.x *= du; N_dPdv.y *= du; N_dPdv.z *= du;          // (du, not dv: as the reference)
+  V3 Nb;
+  Nb.x = N.x + amplitude * (Bv * N_dPdu.x - Bu * N_dPdv.x);
+  Nb.y = N.y + amplitude * (Bv * N_dPdu.y - Bu * N_dPdv.y);
+  Nb.z = N.z + amplitude * (Bv * N_dPdu.z - Bu * N_dPdv.z);
+  return Normalize(Nb);
+}
+
 // ConstantShader::evaluate, shaders/constant_shader/constant_shader.cc:72-94
 void eval_constant(const Scene &s, const fjgpu_shader &sh, const SurfIn &in, Col *Cs, float *Os) {
   if (sh.texture) {
@@ -673,7 +705,8 @@ void eval_constant(const Scene &s, const fjgpu_shader &sh, const SurfIn &in, Col
 // PlasticShader::evaluate, shaders/plastic_shader/plastic_shader.cc:101-179 (diffuse_map; no bump map)
 void eval_plastic(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, const SurfIn &in, Col *Cs, float *Os) {
   Col diff, spec;
-  const V3 Nf = SlFaceforward(in.I, in.N);
+  V3 Nf = SlFaceforward(in.I, in.N);
+  if (sh.bump_texture) Nf = SlBumpMapping(rs.s->textures[sh.bump_texture - 1], in.dPdu, in.dPdv, in.tu, in.tv, sh.bump_amplitude, Nf);   // :115-123
   std::vector<LightSample> samples; new_light_samples(rs, cxt, samples);
   for (size_t i = 0; i < samples.size(); i++) {
     LightOut Lout; Lout.Ln = V3(); Lout.distance = 0;
@@ -792,7 +825,7 @@ int SlTrace(RenderState &rs, const Cxt &cxt, const V3 &o, const V3 &d, double tm
   Col4 surf;
   if (hit) {
     SurfIn in; in.shaded_object = isect.object; in.P = isect.P; in.N = isect.N; in.Cd = Col(1, 1, 1); in.I = ray.dir;
-    in.tu = isect.tu; in.tv = isect.tv;
+    in.tu = isect.tu; in.tv = isect.tv; in.dPdu = isect.dPdu; in.dPdv = isect.dPdv;
     const Instance &inst = rs.s->inst[isect.object];
     int g = isect.shading_group_id;                                  // ObjectInstance::GetShader :177-191
     int slot = (g < 0 || g >= FJGPU_MAX_SHADING_GROUPS) ? inst.shader_of_group[0] : inst.shader_of_group[g];

@@ -270,6 +270,7 @@ class SceneDesc:
             sh.do_reflect = 1 if any(x > 0 for x in refl) else 0
             sh.ior = max(float(f32(.001)), float(f32(props.get("ior", 1.4))))
             sh.opacity = min(1.0, max(0.0, float(f32(props.get("opacity", 1)))))
+            sh.bump_amplitude = float(f32(props.get("bump_amplitude", 1)))
         elif kind == "glass":
             sh.kind = a.SHADER_GLASS
             fc = [max(float(f32(.001)), float(f32(x))) for x in props.get("filter_color", (1, 1, 1))]
@@ -325,8 +326,12 @@ class SceneDesc:
             shs[i] = self.shader_struct(kind, {k: v for k, v in props.items() if not isinstance(v, str)})
             for k, v in props.items():
                 if isinstance(v, str):
-                    assert (kind, k) in (("constant", "texture"), ("plastic", "diffuse_map"), ("pathtracing", "diffuse_map"))
-                    shs[i].texture = tex_ids[v] + 1
+                    assert (kind, k) in (("constant", "texture"), ("plastic", "diffuse_map"), ("pathtracing", "diffuse_map"),
+                                         ("plastic", "bump_map"))
+                    if k == "bump_map":
+                        shs[i].bump_texture = tex_ids[v] + 1
+                    else:
+                        shs[i].texture = tex_ids[v] + 1
         out["shaders"] = shs
         out["nshaders"] = len(self.shaders)
         ins = (a.Instance * max(1, len(self.instances)))()
