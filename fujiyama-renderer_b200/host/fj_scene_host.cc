@@ -138,7 +138,7 @@ struct Shader { int plugin; std::map<std::string, std::array<double, 4>> props; 
 struct Procedure { int plugin; ID mesh = SI_BADID; std::string filepath, io_mode; };
 struct Instance { ID mesh; Xform x; std::map<std::string, ID> shaders; ID reflect = SI_BADID, refract = SI_BADID, shadow = SI_BADID; };
 struct Group { std::vector<int> members; };
-struct Light { int type; Xform x; double intensity = 1; double color[3] = {1, 1, 1}; int sample_count = 16; int double_sided = 0; };
+struct Light { int type; Xform x; double intensity = 1; double color[3] = {1, 1, 1}; int sample_count = 16; int double_sided = 0; ID envmap = SI_BADID; };
 struct Camera { Xform x; double fov = 30, znear = .01, zfar = 1000; };
 struct FrameBuf { int w = 0, h = 0, c = 4; std::vector<float> px; };
 struct Renderer {
@@ -276,6 +276,52 @@ int read_ply(const std::string &path, Mesh *mesh) {
   compute_normals(*mesh);
   mesh->dirty = true;
   return 0;
+}
+
+// ---------------------------------------------------------------- environment-map dome lights (host side of Light::Preprocess)
+// TextureCache::LookupTexture (src/fj_texture.cc:51-78) on the tiles SiNewTexture read: float arithmetic as compiled.
+void host_tex_lookup(const Texture &t, float u, float v, float rgba[4]) {
+  const int xnt = t.width / t.tilesize, ynt = t.height / t.tilesize;
+  const float tsu = u - std::floor(u), tsv = v - std::floor(v);
+  const float tlu = tsu * xnt, tlv = (1 - tsv) * ynt;
+  int xtile = (int)std::floor(tlu), ytile = (int)std::floor(tlv);
+  const int xpxl = (int)((tlu - std::floor(tlu)) * 64), ypxl = (int)((tlv - std::floor(tlv)) * 64);
+  xtile = std::min(std::max(xtile, 0), xnt - 1); ytile = std::min(std::max(ytile, 0), ynt - 1);      // MipInput::ReadTile :163-165
+  const float *px = &t.tiles[((size_t)(ytile * xnt + xtile) * t.tilesize * t.tilesize + (size_t)ypxl * t.tilesize + xpxl) * t.nch];
+  if (t.nch == 1) { rgba[0] = rgba[1] = rgba[2] = px[0]; rgba[3] = 1; }
+  else if (t.nch == 3) { rgba[0] = px[0]; rgba[1] = px[1]; rgba[2] = px[2]; rgba[3] = 1; }
+  else { rgba[0] = px[0]; rgba[1] = px[1]; rgba[2] = px[2]; rgba[3] = px[3]; }
+}
+// DomeLight::preprocess with an environment map (src/fj_dome_light.cc:78-96) -> StratifiedImportanceSampling
+// (src/fj_importance_sampling.cc:102-150, helpers :222-277): the map sampled at 1/8 of its resolution, one pick per stratum.
+bool dome_samples_from_envmap(const Texture &t, int nsamples, std::vector<double> *dirs, std::vector<float> *cols) {
+  const int xres = t.width / 8, yres = t.height / 8, npixels = xres * yres;
+  if (npixels <= 0 || t.tilesize < 64) return false;
+  const double PI = 3.14159265358979323846;
+  auto index_to_uv = [&](int index, float *u, float *v) { const int x = index % xres, y = index / xres; *u = (.5 + x) / xres; *v = 1. - ((.5 + y) / yres); };
+  std::vector<double> hist(npixels);
+  double sum = 0;
+  for (int i = 0; i < npixels; i++) {
+    float u, v, c[4]; index_to_uv(i, &u, &v); host_tex_lookup(t, u, v, c);
+    sum += (float)(.298912 * c[0] + .586611 * c[1] + .114478 * c[2]);
+    hist[i] = sum;
+  }
+  uint32_t s[4] = {123456789u, 362436069u, 521288629u, 88675123u};                                      // XorShift, src/fj_random.cc:10-43
+  dirs->clear(); cols->clear();
+  for (int i = 0; i < nsamples; i++) {
+    const uint32_t tt = s[0] ^ (s[0] << 11);
+    s[0] = s[1]; s[1] = s[2]; s[2] = s[3]; s[3] = (s[3] ^ (s[3] >> 19)) ^ (tt ^ (tt >> 8));
+    const double f01 = (double)s[3] / 4294967295.0;
+    const double rnd = sum * ((i + f01) / nsamples);
+    int index = -1;
+    for (int k = 0; k < npixels; k++) if (rnd < hist[k]) { index = k; break; }
+    float u, v, c[4]; index_to_uv(index, &u, &v);
+    const double phi = 2 * PI * u, theta = PI * (v - .5), r = std::cos(theta);
+    dirs->insert(dirs->end(), {r * std::sin(phi), std::sin(theta), r * std::cos(phi)});
+    host_tex_lookup(t, u, v, c);
+    cols->insert(cols->end(), {c[0], c[1], c[2]});
+  }
+  return true;
 }
 
 // ---------------------------------------------------------------- shader property tables
@@ -448,7 +494,11 @@ Status flatten(Scene &sc, const Renderer &r, Flat *f) {
     for (int k = 0; k < 3; k++) { d.color[k] = (float)l.color[k]; d.translate[k] = l.x.T.s[0].second[k]; }
     d.intensity = (float)l.intensity;
     const M4 m = l.x.matrix(); memcpy(d.fwd, m.e, sizeof m.e);
-    if (l.type == SI_DOME_LIGHT) {          // DomeLight::preprocess without an environment map, src/fj_dome_light.cc:58-76
+    int et, ei;
+    if (l.type == SI_DOME_LIGHT && l.envmap != SI_BADID && decode_id(l.envmap, &et, &ei) && et == Type_Texture && ei < (int)sc.textures.size()) {
+      if (!dome_samples_from_envmap(sc.textures[ei], l.sample_count, &f->dome_dirs[i], &f->dome_cols[i])) return failmsg("environment map too small to sample");
+      d.dome_sample_count = l.sample_count;
+    } else if (l.type == SI_DOME_LIGHT) {   // DomeLight::preprocess without an environment map, src/fj_dome_light.cc:58-76
       const int n = l.sample_count; const double a = 1. / n;
       const double len = std::sqrt(a * a + 1. * 1. + a * a), inv = 1. / len;
       for (int k = 0; k < n; k++) { f->dome_dirs[i].insert(f->dome_dirs[i].end(), {a * inv, 1. * inv, a * inv}); f->dome_cols[i].insert(f->dome_cols[i].end(), {1.f, .63f, .63f}); }
@@ -702,6 +752,11 @@ Status SiAssignTurbulence(ID, const char *, ID) { return SI_FAIL; }
 // SiAssignTexture, src/fj_scene_interface.cc:786-805: the PropTexture properties of the device shaders
 // (constant_shader `texture`, plastic_shader / pathtracing_shader `diffuse_map`, plastic_shader `bump_map`)
 Status SiAssignTexture(ID id, const char *name, ID texture) {
+  if (Light *lt = the_scene ? get(the_scene->lights, id, Type_Light) : nullptr) {       // Light::SetEnvironmentMap, src/fj_light.cc:54-57
+    if (!name || std::string(name) != "environment_map" || !get(the_scene->textures, texture, Type_Texture)) return SI_FAIL;
+    lt->envmap = texture;
+    return ok();
+  }
   Shader *sh = the_scene ? get(the_scene->shaders, id, Type_Shader) : nullptr;
   if (!sh || !name || !get(the_scene->textures, texture, Type_Texture)) return SI_FAIL;
   const int kind = the_scene->plugins[sh->plugin].kind;

@@ -962,6 +962,41 @@ int fjo_textures(fjo_scene *sc, int n, const fjgpu_texture *t) {
   }
   return 0;
 }
+// DomeLight::preprocess with an environment map (src/fj_dome_light.cc:78-96: the map sampled at 1/8 of its resolution)
+// -> StratifiedImportanceSampling (src/fj_importance_sampling.cc:102-150) with make_histgram / lookup_histgram /
+// index_to_uv / uv_to_dir (:222-277).  Writes `nsamples` directions (3 doubles) and colours (3 floats).
+int fjo_dome_samples(const fjgpu_texture *t, int nsamples, double *dirs3, float *cols3) {
+  Tex tx; tx.width = t->width; tx.height = t->height; tx.nch = t->nchannels; tx.tilesize = t->tilesize;
+  tx.xnt = tx.width / tx.tilesize; tx.ynt = tx.height / tx.tilesize;
+  tx.tiles.assign(t->tiles, t->tiles + (size_t)tx.xnt * tx.ynt * tx.tilesize * tx.tilesize * tx.nch);
+  const int xres = tx.width / 8, yres = tx.height / 8, NPIXELS = xres * yres;
+  if (NPIXELS <= 0) return -1;
+  auto index_to_uv = [&](int index, float *u, float *v) {
+    const int x = index % xres, y = index / xres;
+    *u = (.5 + x) / xres; *v = 1. - ((.5 + y) / yres);
+  };
+  std::vector<double> hist(NPIXELS);
+  double sum = 0;
+  for (int i = 0; i < NPIXELS; i++) {
+    float u, v; index_to_uv(i, &u, &v);
+    const Col4 c = tex_lookup(tx, u, v);
+    sum += (float)(.298912 * c.r + .586611 * c.g + .114478 * c.b);      // Luminance4 returns float
+    hist[i] = sum;
+  }
+  sum = hist[NPIXELS - 1];
+  XorShift rng;
+  for (int i = 0; i < nsamples; i++) {
+    const double rnd = sum * ((i + rng.NextFloat01()) / nsamples);
+    int index = -1;
+    for (int k = 0; k < NPIXELS; k++) if (rnd < hist[k]) { index = k; break; }
+    float u, v; index_to_uv(index, &u, &v);
+    const double phi = 2 * PI * u, theta = PI * (v - .5), r = std::cos(theta);
+    dirs3[3 * i] = r * std::sin(phi); dirs3[3 * i + 1] = std::sin(theta); dirs3[3 * i + 2] = r * std::cos(phi);
+    const Col4 c = tex_lookup(tx, u, v);
+    cols3[3 * i] = c.r; cols3[3 * i + 1] = c.g; cols3[3 * i + 2] = c.b;
+  }
+  return 0;
+}
 // Mesh::ComputeNormals restatement exposed for the host-side parity test
 void fjo_compute_normals(const double *P, int nverts, const int32_t *idx, int nfaces, double *N_out) {
   Mesh m; m.P.resize(nverts); for (int i = 0; i < nverts; i++) m.P[i] = V3(P[3 * i], P[3 * i + 1], P[3 * i + 2]);

@@ -73,6 +73,7 @@ def oracle():
     lib.fjo_shaders.argtypes = [vp, i32, P(a.Shader)]
     lib.fjo_mesh_set_uv.argtypes = [vp, i32, P(C.c_float), i32]
     lib.fjo_textures.argtypes = [vp, i32, P(a.Texture)]
+    lib.fjo_dome_samples.argtypes = [P(a.Texture), i32, f64p, P(C.c_float)]
     lib.fjo_lights.argtypes = [vp, i32, P(a.Light)]
     lib.fjo_camera.argtypes = [vp, P(a.Camera)]
     lib.fjo_build.argtypes = [vp]
@@ -171,9 +172,9 @@ class SceneDesc:
         self.instances.append(dict(name=name, mesh=mesh, shader=shader, T=T, R=R, S=S))
 
     def light(self, kind=0, T=(0, 0, 0), R=(0, 0, 0), S=(1, 1, 1), intensity=1.0, color=(1, 1, 1), sample_count=16,
-              double_sided=0):
+              double_sided=0, environment_map=None):
         self.lights.append(dict(kind=kind, T=T, R=R, S=S, intensity=intensity, color=color,
-                                sample_count=sample_count, double_sided=double_sided))
+                                sample_count=sample_count, double_sided=double_sided, environment_map=environment_map))
 
     def tiles(self, region=None):
         return make_tiles(self.ren["resolution"][0], self.ren["resolution"][1], self.ren["tilesize"], region)
@@ -191,6 +192,7 @@ class SceneDesc:
         L.append("SetProperty3 cam1 translate %r %r %r" % tuple(float(x) for x in self.cam["T"]))
         L.append("SetProperty3 cam1 rotate %r %r %r" % tuple(float(x) for x in self.cam["R"]))
         L.append("SetProperty1 cam1 fov %r" % float(self.cam["fov"]))
+        env_assign = []
         for i, lt in enumerate(self.lights):
             n = "light%d" % i
             L.append("NewLight %s %s" % (n, LIGHT_NAME[lt["kind"]]))
@@ -201,11 +203,14 @@ class SceneDesc:
             L.append("SetProperty3 %s color %r %r %r" % ((n,) + tuple(float(x) for x in lt["color"])))
             L.append("SetProperty1 %s sample_count %d" % (n, lt["sample_count"]))
             L.append("SetProperty1 %s double_sided %d" % (n, lt["double_sided"]))
+            if lt.get("environment_map"):
+                env_assign.append("AssignTexture %s environment_map %s" % (n, lt["environment_map"]))
         from fujiyama_renderer_b200 import synth
         for tname, img in self.textures:
             mip = os.path.join(workdir, tname + ".mip")
             synth.write_mip(mip, img)
             L.append("NewTexture %s %s" % (tname, mip))
+        L += env_assign
         for name, kind, props in self.shaders:
             L.append("NewShader %s %s" % (name, SHADER_PLUGIN[kind][0]))
             for k, v in props.items():
@@ -358,7 +363,16 @@ class SceneDesc:
             lts[i].intensity = float(d["intensity"])
             lts[i].translate[:] = [float(x) for x in d["T"]]
             lts[i].fwd[:] = list(fwd)
-            if d["kind"] == a.LIGHT_DOME:   # DomeLight::preprocess without an environment map (fj_dome_light.cc:64-76)
+            if d["kind"] == a.LIGHT_DOME and d.get("environment_map"):   # DomeLight::preprocess with an environment map (:78-96)
+                n = lts[i].sample_count
+                dirs = np.zeros((n, 3), np.float64)
+                cols = np.zeros((n, 3), np.float32)
+                assert o.fjo_dome_samples(C.byref(texs[tex_ids[d["environment_map"]]]), n, dptr(dirs), fptr(cols)) == 0
+                out.setdefault("_keep", []).extend([dirs, cols])
+                lts[i].dome_sample_count = n
+                lts[i].dome_dirs = dptr(dirs)
+                lts[i].dome_colors = fptr(cols)
+            elif d["kind"] == a.LIGHT_DOME:   # DomeLight::preprocess without an environment map (fj_dome_light.cc:64-76)
                 n = lts[i].sample_count
                 v = np.array([1. / n, 1., 1. / n])
                 inv_len = 1. / np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
