@@ -316,13 +316,14 @@ struct FramePlan {
   fj::DFrame fr; fj::DCamera cam;
   uint32_t wstride = 0; int bw = 0, bh = 0;
   int tiles_per_batch = 0;
-  int waves = 1; double peak = 1;     // wavefront: number of extend/shade rounds, worst-case rays per camera sample in one round
+  int waves = 1; double peak = 1;     // wavefront: number of extend/shade rounds, worst-case queue records per camera sample in one round
+  double factor0 = 1;                 // queue capacity per sample slot the first attempt allocates
 };
 
 // Worst-case width of the ray tree per camera sample (rays alive in one wavefront round) and the number of rounds,
 // from the lobes the scene's shaders can spawn and the per-type bounce limits (has_reached_bounce_limit,
 // src/fj_shading.cc:467-499).
-void frontier(const fjgpu_context *ctx, const fjgpu_render_params *p, int *waves, double *peak) {
+void frontier(const fjgpu_context *ctx, const fjgpu_render_params *p, int *waves, double *peak, double *block_out, bool mega_for_plan = false) {
   bool D = false, R = false, F = false; int b = 0;
   for (const fjgpu_shader &s : ctx->shaders) {
     int n = 0;
@@ -338,7 +339,21 @@ void frontier(const fjgpu_context *ctx, const fjgpu_render_params *p, int *waves
   const int md = D ? p->max_diffuse_depth : 0, mr = R ? p->max_reflect_depth : 0, mf = F ? p->max_refract_depth : 0;
   *waves = 1 + md + mr + mf;
   *peak = 1;
-  if (b <= 1) return;
+  // wavefront shadow rays: every plastic hit writes a block of 1 header + one record per light sample into the next queue
+  // (fj_kernels.cuh, Shading), and the blocks of the last bounce need one more extend / shade round
+  double block = 0;
+  {
+    bool plastic = false;
+    for (const fjgpu_shader &s : ctx->shaders) plastic = plastic || s.kind == FJGPU_SHADER_PLASTIC;
+    long samples = 0;
+    for (size_t i = 0; i < ctx->lights.size(); i++) {
+      const fjgpu_light &l = ctx->lights[i];
+      samples += l.kind == FJGPU_LIGHT_POINT ? 1 : (l.kind == FJGPU_LIGHT_DOME ? std::min<long>(l.sample_count, (long)(ctx->dome_dirs[i].size() / 3)) : l.sample_count);
+    }
+    if (plastic && p->cast_shadow && samples > 0 && !mega_for_plan) { block = 1.0 + (double)samples; *waves += 1; }
+  }
+  *block_out = block;
+  if (b <= 1) { *peak = 1 + block; return; }
   std::vector<double> fact(md + mr + mf + 1, 1.);
   for (size_t i = 1; i < fact.size(); i++) fact[i] = fact[i - 1] * (double)i;
   for (int w = 1; w <= md + mr + mf; w++) {
@@ -346,6 +361,7 @@ void frontier(const fjgpu_context *ctx, const fjgpu_render_params *p, int *waves
     for (int nd = 0; nd <= md; nd++) for (int nr = 0; nr <= mr; nr++) { const int nf = w - nd - nr; if (nf < 0 || nf > mf) continue; width += fact[w] / (fact[nd] * fact[nr] * fact[nf]); }
     *peak = std::max(*peak, std::min(width, std::pow((double)b, w)));
   }
+  *peak *= 1 + block;
 }
 
 int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_tile *tiles, int ntiles, FramePlan *pl) {
@@ -406,9 +422,13 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
   pl->cam.uvx = pl->cam.uvy * aspect;
   rows12(ctx->cam.fwd, pl->cam.fwd); pl->cam.znear = ctx->cam.znear; pl->cam.zfar = ctx->cam.zfar;
   // batch so the per-batch buffers (accumulators + two ray queues + hit records) stay bounded
-  frontier(ctx, p, &pl->waves, &pl->peak);
+  double block = 0;
+  frontier(ctx, p, &pl->waves, &pl->peak, &block);
+  if (block > 254) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "more than 253 light samples per shading point");
+  // ray trees that can branch start optimistic (grown on overflow); shadow-ray blocks are sized for the worst case at once
+  pl->factor0 = block > 0 ? pl->peak : std::min(pl->peak, 2.0);
   const size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 4096) << 20;
-  const size_t per_slot = sizeof(fj::Accum) + (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec));
+  const size_t per_slot = sizeof(fj::Accum) + (size_t)std::ceil(pl->factor0 * (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec)));
   long per = (long)(cap / ((size_t)pl->wstride * per_slot));
   per = std::max(1l, std::min<long>(per, std::max(ntiles, 1)));
   const long nbatches = (std::max(ntiles, 1) + per - 1) / per;             // equal batches: no short last batch with long tails
@@ -546,7 +566,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   size_t evn = 0;
   std::vector<cudaEvent_t> ev_extend, ev_shade, ev_resolve;     // (start, stop) pairs read after the final sync
   // ray-queue capacity: optimistic when the ray tree can branch, grown on overflow up to the worst case
-  double factor = std::min(pl.peak, 2.0);
+  double factor = pl.factor0;
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   for (int b0 = 0; b0 < ntiles; b0 += pl.tiles_per_batch) {
     const int nb = std::min(pl.tiles_per_batch, ntiles - b0);

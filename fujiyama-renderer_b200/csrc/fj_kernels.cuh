@@ -106,44 +106,43 @@ struct ShadeCounters { unsigned int rays[5]; unsigned int hits, levels; };
 
 // Shades one traced ray: adds its radiance (times the ray's throughput) to the sample through `sink.add`, and hands the
 // secondary rays it spawns to `sink.spawn` (SlTrace -> trace_surface -> Shader::evaluate, src/fj_shading.cc:140-179,
-// 527-572).  Shadow rays are traced inline (SlIlluminance needs the occluder's opacity before the light sample is
-// weighted).  Sink: add(r,g,b) in float, alpha(a) for camera rays, spawn(const RayRec&).
-template <typename T, bool PLASTIC = true>
+// 527-572).  Sink: add(r,g,b) in float, alpha(a) for camera rays, spawn(const RayRec&).
+//
+// Shadow rays (SlIlluminance, src/fj_shading.cc:296-359): `Cl *= 1 - alpha_occluder` has to precede the Lambert weight and
+// the float sum over the light samples runs in sample order, so the diffuse term of a plastic hit cannot be split into
+// independent rays.  DEFER = false (megakernel): they are traced inline, on the binary BVH.  DEFER = true (wavefront): the
+// hit writes ONE CONTIGUOUS BLOCK into the next queue — a header record (RAY_SHADOW_HEAD: parent throughput, shader slot,
+// diffuse-map texel, sample count; tmin > tmax so k_extend retires it at the root) followed by one RAY_SHADOW record per
+// light sample that passed the cone and intensity tests (ray, unshadowed Cl in `thr`, Lambert weight in `pad2`) — the
+// block is traced by k_extend with everything else, and the next k_shade finishes the sum from the block in sample
+// order (finish_shadow_block): the same float operations in the same order as the inline path, bit for bit.
+template <typename T, bool PLASTIC = true, bool DEFER = false>
 struct Shading {
   const DScene &sc; const DFrame &fr; PathKey key; ShadeCounters &cnt;
   __device__ Shading(const DScene &s, const DFrame &f, PathKey k, ShadeCounters &c) : sc(s), fr(f), key(k), cnt(c) {}
   __device__ __forceinline__ double rnd(unsigned long long node, uint32_t dim) const { return ctr_rand(key.seed, key.tile, key.sample, node, dim); }
 
-  // SlIlluminance (src/fj_shading.cc:296-359) for one light sample.
-  __device__ __forceinline__ bool illuminance(const DLight &lt, const LightSample &ls, const D3 &Ps, const D3 &axis,
-                                              int shaded_object, C3 *Cl, D3 *Ln_out) {
+  // SlIlluminance up to the shadow ray: direction and distance to the light sample, cone test, Light::Illuminate, the
+  // 1e-4 intensity cut (src/fj_shading.cc:296-336).
+  __device__ __forceinline__ bool light_sample_reaches(const DLight &lt, const LightSample &ls, const D3 &Ps, const D3 &axis,
+                                                       C3 *Cl, D3 *Ln_out, double *dist) {
     D3 Ln = ls.P - Ps;
     const double distance = length(Ln);
     if (distance > 0) { const double inv = ddiv(1., distance); Ln = Ln * inv; }
-    *Ln_out = Ln;
+    *Ln_out = Ln; *dist = distance;
     const D3 nml_axis = normalize(axis);
     const double cosangle = dot(nml_axis, Ln);
     if (cosangle < 6.123233995736766e-17) return false;          // cos(PI/2) in FP64
-    C3 lc = light_illuminate(lt, ls, Ps);
+    const C3 lc = light_illuminate(lt, ls, Ps);
     if ((double)lc.r < .0001 && (double)lc.g < .0001 && (double)lc.b < .0001) return false;
-    if (fr.cast_shadow) {                                        // SlShadowContext :266-279
-      RayD sr; sr.o = Ps; sr.d = Ln; sr.tmin = .0001; sr.tmax = distance;
-      Hit h;
-      cnt.rays[RAY_SHADOW]++;
-      if (trace_closest<T>(sc, sc.inst[shaded_object].shadow_target, sr, &h)) {
-        cnt.hits++; cnt.levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
-        const float ac = fadd(1.f, -occluder_opacity(sc, h));
-        lc.r = fmul(lc.r, ac); lc.g = fmul(lc.g, ac); lc.b = fmul(lc.b, ac);
-      }
-    }
     *Cl = lc;
     return true;
   }
 
-  // diff = sum over all light samples of max(0, Nf.Ln) * Cl — the loop of PlasticShader::evaluate
-  // (plastic_shader.cc:117-137) over SlNewLightSamples (fj_shading.cc:380-404; Light::GetSamples).
-  __device__ C3 gather_lights(const D3 &P, const D3 &Nf, int shaded_object, unsigned long long node) {
-    C3 diff = c3(0, 0, 0);
+  // The light samples of one shading point in the reference's order (SlNewLightSamples, fj_shading.cc:380-404;
+  // Light::GetSamples of the four light types): f(light, sample) for every one of them.
+  template <typename F>
+  __device__ __forceinline__ void for_each_light_sample(unsigned long long node, F f) {
     uint32_t dim = 16;
     for (int li = 0; li < sc.nlights; li++) {
       const DLight &lt = sc.lights[li];
@@ -172,14 +171,63 @@ struct Shading {
           ls.N = mat_vector(lt.fwd, -1. * dir);
           ls.color = c3(lt.dome_colors[3 * i], lt.dome_colors[3 * i + 1], lt.dome_colors[3 * i + 2]);
         }
-        C3 Cl; D3 Ln;
-        if (!illuminance(lt, ls, P, Nf, shaded_object, &Cl, &Ln)) continue;
-        float Kd = (float)dot(Nf, Ln);
-        Kd = Kd > 0.f ? Kd : 0.f;
-        diff.r = fadd(diff.r, fmul(Kd, Cl.r)); diff.g = fadd(diff.g, fmul(Kd, Cl.g)); diff.b = fadd(diff.b, fmul(Kd, Cl.b));
+        f(lt, ls);
       }
     }
+  }
+
+  // diff = sum over all light samples of max(0, Nf.Ln) * Cl — the loop of PlasticShader::evaluate (plastic_shader.cc:117-137),
+  // shadow rays traced inline (SlShadowContext :266-279).
+  __device__ C3 gather_lights(const D3 &P, const D3 &Nf, int shaded_object, unsigned long long node) {
+    C3 diff = c3(0, 0, 0);
+    for_each_light_sample(node, [&](const DLight &lt, const LightSample &ls) {
+      C3 lc; D3 Ln; double distance;
+      if (!light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) return;
+      if (fr.cast_shadow) {
+        RayD sr; sr.o = P; sr.d = Ln; sr.tmin = .0001; sr.tmax = distance;
+        Hit h;
+        cnt.rays[RAY_SHADOW]++;
+        if (trace_closest<T>(sc, sc.inst[shaded_object].shadow_target, sr, &h)) {
+          cnt.hits++; cnt.levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
+          const float ac = fadd(1.f, -occluder_opacity(sc, h));
+          lc.r = fmul(lc.r, ac); lc.g = fmul(lc.g, ac); lc.b = fmul(lc.b, ac);
+        }
+      }
+      float Kd = (float)dot(Nf, Ln);
+      Kd = Kd > 0.f ? Kd : 0.f;
+      diff.r = fadd(diff.r, fmul(Kd, lc.r)); diff.g = fadd(diff.g, fmul(Kd, lc.g)); diff.b = fadd(diff.b, fmul(Kd, lc.b));
+    });
     return diff;
+  }
+
+  // The wavefront's version: writes the block described above through `sink` and returns; the sum is finished one round later.
+  template <typename Sink>
+  __device__ void defer_lights(const RayRec &cur, const C3 &thr, const D3 &P, const D3 &Nf, int shaded_object, int slot, const float4 &dm, Sink &sink) {
+    int n = 0;
+    for_each_light_sample(cur.node, [&](const DLight &lt, const LightSample &ls) {
+      C3 lc; D3 Ln; double distance;
+      if (light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) n++;
+    });
+    if (n == 0) return;                                            // diff = 0: the diffuse term adds nothing
+    unsigned at = sink.reserve((unsigned)n + 1u);
+    RayRec c; memset(&c, 0, sizeof c);
+    c.d[2] = 1.; c.tmin = 1.; c.tmax = 0.;                         // never enters a box: retired at the root of the instance tree
+    c.thr[0] = thr.r; c.thr[1] = thr.g; c.thr[2] = thr.b; c.slot = cur.slot;
+    c.node = (unsigned long long)(unsigned)n | ((unsigned long long)__float_as_uint(dm.x) << 32);
+    c.pad2 = __float_as_int(dm.y); c.pad3 = __float_as_int(dm.z);
+    c.target = sc.inst[shaded_object].shadow_target; c.type = RAY_SHADOW_HEAD; c.filter_shader = slot;
+    sink.put(at++, c);
+    for_each_light_sample(cur.node, [&](const DLight &lt, const LightSample &ls) {
+      C3 lc; D3 Ln; double distance;
+      if (!light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) return;
+      float Kd = (float)dot(Nf, Ln);
+      Kd = Kd > 0.f ? Kd : 0.f;
+      RayRec r; memset(&r, 0, sizeof r);
+      r.o[0] = P.x; r.o[1] = P.y; r.o[2] = P.z; r.d[0] = Ln.x; r.d[1] = Ln.y; r.d[2] = Ln.z; r.tmin = .0001; r.tmax = distance;
+      r.thr[0] = lc.r; r.thr[1] = lc.g; r.thr[2] = lc.b; r.slot = cur.slot; r.pad2 = __float_as_int(Kd);
+      r.target = sc.inst[shaded_object].shadow_target; r.type = RAY_SHADOW; r.filter_shader = -1;
+      sink.put(at++, r);
+    });
   }
 
   template <typename Sink>
@@ -219,10 +267,13 @@ struct Shading {
         D3 dPdu, dPdv; hit_derivatives(sc, h, &dPdu, &dPdv);
         Nf = sl_bump_mapping(sc.textures[sh.bump_texture - 1], dPdu, dPdv, tu, tv, (double)sh.bump_amplitude, Nf);
       }
-      const C3 diff = gather_lights(P, Nf, h.inst, cur.node);
       float4 dm = make_float4(1.f, 1.f, 1.f, 1.f);                 // diffuse_map, plastic_shader.cc:148-156: Cs = diff * diffuse * diff_map
       if (sh.texture) { float tu, tv; hit_uv(sc, h, &tu, &tv); dm = tex_lookup(sc.textures[sh.texture - 1], tu, tv); }
-      sink.add(fmul(thr.r, fmul(fmul(diff.r, sh.diffuse[0]), dm.x)), fmul(thr.g, fmul(fmul(diff.g, sh.diffuse[1]), dm.y)), fmul(thr.b, fmul(fmul(diff.b, sh.diffuse[2]), dm.z)));
+      if (DEFER && fr.cast_shadow) defer_lights(cur, thr, P, Nf, h.inst, slot, dm, sink);
+      else {
+        const C3 diff = gather_lights(P, Nf, h.inst, cur.node);
+        sink.add(fmul(thr.r, fmul(fmul(diff.r, sh.diffuse[0]), dm.x)), fmul(thr.g, fmul(fmul(diff.g, sh.diffuse[1]), dm.y)), fmul(thr.b, fmul(fmul(diff.b, sh.diffuse[2]), dm.z)));
+      }
       if (sh.do_reflect && (int)cur.rd + 1 <= fr.max_reflect) {    // SlReflectContext :242-252, gate :467-499
         const double Kr = sl_fresnel(ray.d, Nf, ddiv(1., (double)sh.ior));
         const D3 R = normalize(sl_reflect(ray.d, Nf));
@@ -346,6 +397,8 @@ struct StackSink {
   __device__ __forceinline__ void add(float r, float g, float b) { acc.r = fadd(acc.r, r); acc.g = fadd(acc.g, g); acc.b = fadd(acc.b, b); }
   __device__ __forceinline__ void alpha(float v) { a = v; }
   __device__ __forceinline__ void spawn(const RayRec &c) { if (sp < FJ_PENDING) stack[sp++] = c; }
+  __device__ __forceinline__ unsigned reserve(unsigned) { return 0u; }      // (the megakernel traces shadow rays inline)
+  __device__ __forceinline__ void put(unsigned, const RayRec &) {}
 };
 
 template <typename T>
@@ -637,14 +690,8 @@ struct QueueSink {
   long long r, g, b; bool has_alpha; float av;
   __device__ __forceinline__ void add(float x, float y, float z) { r += to_fix(x); g += to_fix(y); b += to_fix(z); }
   __device__ __forceinline__ void alpha(float v) { has_alpha = true; av = v; }
-  // the warp may be diverged here: aggregate over whichever lanes arrive together
-  __device__ __forceinline__ void spawn(const RayRec &c) {
-    const unsigned m = __activemask();
-    const int leader = __ffs(m) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(&a.ctl->count[a.cur ^ 1], (unsigned)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    const unsigned i = base + __popc(m & ((1u << lane) - 1));
+  // writes record `c` into slot i of the next queue (and files it under its sort key when rays are sorted between bounces)
+  __device__ __forceinline__ void put(unsigned i, const RayRec &c) {
     if (i < a.capacity) {
       store_ray_cs(next + i, c);
       if (a.hist) {       // sort key: rays leaving the same cell of the scene in the same octant walk the same part of the BVH
@@ -660,6 +707,30 @@ struct QueueSink {
         atomicAdd(&a.hist[key], 1u);
       }
     } else a.ctl->overflow = 1;
+  }
+  // the warp may be diverged here: aggregate over whichever lanes arrive together
+  __device__ __forceinline__ void spawn(const RayRec &c) {
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&a.ctl->count[a.cur ^ 1], (unsigned)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    put(base + __popc(m & ((1u << lane) - 1)), c);
+  }
+  // `n` (<= 255) contiguous slots for this lane; one atomic for the lanes that arrive together (prefix sums by bit plane)
+  __device__ __forceinline__ unsigned reserve(unsigned n) {
+    const unsigned m = __activemask(), lt = (1u << lane) - 1u;
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const unsigned plane = __ballot_sync(m, (n >> b) & 1u);
+      before += (unsigned)__popc(plane & lt) << b; total += (unsigned)__popc(plane) << b;
+    }
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&a.ctl->count[a.cur ^ 1], total);
+    base = __shfl_sync(m, base, leader);
+    return base + before;
   }
 };
 
@@ -692,6 +763,36 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const RenderArgs a) {
 // compacted into queue[cur ^ 1] by warp ballot (Shader::Evaluate + the Sl*Context/SlTrace calls the plugins make).
 // PLASTIC = false drops the light loop and its inline shadow-ray traversal from the kernel (scenes without a plastic
 // shader): fewer registers, more resident warps.
+// Finishes the diffuse term of a plastic hit from its block of traced shadow rays (see Shading): records i+1 .. i+n of the
+// queue and their hit records, in light-sample order; exactly the float operations of Shading::gather_lights.
+__device__ __forceinline__ void finish_shadow_block(const RenderArgs &a, const RayRec *rays, unsigned i, const RayRec &head, ShadeCounters &cnt) {
+  const int n = (int)(unsigned)(head.node & 0xffffffffull);
+  C3 diff = c3(0, 0, 0);
+  for (int k = 1; k <= n; k++) {
+    const RayRec *rr = rays + i + k;
+    const float4 w = __ldcs(reinterpret_cast<const float4 *>(rr) + 4);        // thr[3], slot
+    const int kdbits = __ldcs(reinterpret_cast<const int *>(rr) + 26);         // pad2
+    HitRec hr; load_hit_cs(&hr, a.hits + i + k);
+    C3 lc = c3(w.x, w.y, w.z);
+    if (hr.inst >= 0) {
+      Hit h; h.t = hr.t; h.u = hr.u; h.v = hr.v; h.prim = hr.prim; h.inst = hr.inst;
+      const float ac = fadd(1.f, -occluder_opacity(a.sc, h));
+      lc.r = fmul(lc.r, ac); lc.g = fmul(lc.g, ac); lc.b = fmul(lc.b, ac);
+    }
+    const float Kd = __int_as_float(kdbits);
+    diff.r = fadd(diff.r, fmul(Kd, lc.r)); diff.g = fadd(diff.g, fmul(Kd, lc.g)); diff.b = fadd(diff.b, fmul(Kd, lc.b));
+  }
+  const DShader &sh = a.sc.shaders[head.filter_shader];
+  const float dmx = __uint_as_float((unsigned)(head.node >> 32)), dmy = __int_as_float(head.pad2), dmz = __int_as_float(head.pad3);
+  const long long fr_ = to_fix(fmul(head.thr[0], fmul(fmul(diff.r, sh.diffuse[0]), dmx)));
+  const long long fg_ = to_fix(fmul(head.thr[1], fmul(fmul(diff.g, sh.diffuse[1]), dmy)));
+  const long long fb_ = to_fix(fmul(head.thr[2], fmul(fmul(diff.b, sh.diffuse[2]), dmz)));
+  Accum *acc = a.accum + head.slot;
+  if (fr_) atomicAdd((unsigned long long *)&acc->r, (unsigned long long)fr_);
+  if (fg_) atomicAdd((unsigned long long *)&acc->g, (unsigned long long)fg_);
+  if (fb_) atomicAdd((unsigned long long *)&acc->b, (unsigned long long)fb_);
+}
+
 template <typename T, bool PLASTIC, int MINB = (PLASTIC ? 3 : 5)>
 __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   const int lane = threadIdx.x & 31;
@@ -701,13 +802,18 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   ShadeCounters cnt; memset(&cnt, 0, sizeof cnt);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     RayRec cur; load_ray_cs(&cur, rays + i);
+    if (PLASTIC && cur.type == RAY_SHADOW_HEAD) { finish_shadow_block(a, rays, i, cur, cnt); continue; }
     HitRec hr; load_hit_cs(&hr, a.hits + i);
     cnt.rays[cur.type]++;
     if (hr.inst < 0) continue;
+    if (PLASTIC && cur.type == RAY_SHADOW) {        // traced for its block's header; counted like the inline shadow rays
+      cnt.hits++; cnt.levels += a.sc.meshes[a.sc.inst[hr.inst].mesh].log2_tris;
+      continue;
+    }
     int ti, x, y; TileGrid g;
     slot_decode(a.fr, a.tiles, a.wstride, cur.slot, &ti, &g, &x, &y);
     PathKey key; key.seed = a.fr.seed; key.tile = (uint32_t)a.tiles[ti].id; key.sample = (uint32_t)(y * g.nsx + x);
-    Shading<T, PLASTIC> sh(a.sc, a.fr, key, cnt);
+    Shading<T, PLASTIC, true> sh(a.sc, a.fr, key, cnt);
     QueueSink sink{a, a.queue[a.cur ^ 1], lane, 0, 0, 0, false, 0.f};
     Hit h; h.t = hr.t; h.u = hr.u; h.v = hr.v; h.prim = hr.prim; h.inst = hr.inst;
     sh.shade(cur, h, sink);
