@@ -34,6 +34,12 @@ WORKLOADS = {
                    "S-blob(707)=999698 tris + emissive shell, pathtracing_shader depth 3, 1920x1080, 8x8=64spp, tile 32, filter 2"),
     "config2": ("plastic_blob", dict(n=187, res=(1280, 720), rate=4),
                 "S-blob(187)=69938 tris, plastic_shader + 1 point light, 1280x720, 4x4=16spp"),
+    "config3": ("pathtracing_blob", dict(n=1871, res=(1920, 1080), rate=8, depth=3),
+                "S-blob(1871)=7.0M tris + emissive shell (dragon stand-in), pathtracing_shader depth 3, 1920x1080, 64spp"),
+    "config4": ("instanced_blobs", dict(n=740, res=(1920, 1080), rate=8),
+                "16 instances of S-blob(740)=1.09M tris + floor, plastic_shader, GridLight 16 samples, 1920x1080, 64spp"),
+    "config5": ("pathtracing_soup", dict(ntris=10_000_000, res=(3840, 2160), rate=16, depth=8),
+                "S-random 10M-triangle soup + emissive shell, pathtracing_shader depth 8, 3840x2160, 256spp"),
     "profile": ("pathtracing_blob", dict(n=707, res=(480, 270), rate=8, depth=3),
                 "north-star scene at 480x270 (1/16 of the frame) for ncu --set full captures"),
     "small": ("pathtracing_blob", dict(n=64, res=(320, 180), rate=4, depth=3),
@@ -155,6 +161,9 @@ def reference_arm(args, builder, kw, desc):
     if not os.path.exists(probe):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (needs /root/reference at build time)"}))
         return
+    if builder not in ("pathtracing_blob", "plastic_blob"):
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm is wired for the north_star / config2 / profile / small workloads"}))
+        return
     threads = min(os.cpu_count() or 1, 64)
     text = getattr(scenes, builder)(workdir(), os.path.join(ref, "lib"), threads=threads, **kw)
     res, rate = kw["res"], kw["rate"]
@@ -186,6 +195,8 @@ def reference_arm(args, builder, kw, desc):
 def cpu_baseline_leg(builder, kw):
     """Bounded sample of the same workload on the host cores (about 10-30 s of CPU work) for the own arm's line."""
     from fujiyama_renderer_b200 import scenes
+    if builder not in ("pathtracing_blob", "plastic_blob"):
+        return None                       # extra workloads (config3-5 at full size): own arm only
     ref, probe = ref_paths()
     if not os.path.exists(probe):
         return None

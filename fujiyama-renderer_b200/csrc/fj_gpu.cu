@@ -427,7 +427,7 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
   if (block > 254) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "more than 253 light samples per shading point");
   // ray trees that can branch start optimistic (grown on overflow); shadow-ray blocks are sized for the worst case at once
   pl->factor0 = block > 0 ? pl->peak : std::min(pl->peak, 2.0);
-  const size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 4096) << 20;
+  const size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 16384) << 20;
   const size_t per_slot = sizeof(fj::Accum) + (size_t)std::ceil(pl->factor0 * (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec)));
   long per = (long)(cap / ((size_t)pl->wstride * per_slot));
   per = std::max(1l, std::min<long>(per, std::max(ntiles, 1)));
@@ -667,7 +667,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
     if (mode != OUT_SAMPLES_ONLY) {
       cudaEvent_t e0 = pool_event(ctx, &evn), e1 = pool_event(ctx, &evn);
       CK(cudaEventRecord(e0, ctx->stream));
-      fj::k_resolve_tiles<<<nb, 256, 0, ctx->stream>>>(pl.fr, a.tiles, pl.wstride, a.accum, blocks + (size_t)b0 * pl.bw * pl.bh, pl.bw, pl.bh);
+      fj::k_resolve_tiles<<<nb * FJ_RESOLVE_SPLIT, 256, 0, ctx->stream>>>(pl.fr, a.tiles, pl.wstride, a.accum, blocks + (size_t)b0 * pl.bw * pl.bh, pl.bw, pl.bh);
       launches++;
       CK(cudaGetLastError());
       CK(cudaEventRecord(e1, ctx->stream));

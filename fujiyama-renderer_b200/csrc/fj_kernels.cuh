@@ -101,6 +101,7 @@ __device__ __forceinline__ C3 light_illuminate(const DLight &lt, const LightSamp
 }
 
 // ------------------------------------------------------------------------------------------ shading
+#define FJ_LIGHT_CACHE 16     // light samples a plastic hit keeps between deciding and writing its shadow-ray block
 struct PathKey { uint32_t seed, tile, sample; };
 struct ShadeCounters { unsigned int rays[5]; unsigned int hits, levels; };
 
@@ -203,10 +204,20 @@ struct Shading {
   // The wavefront's version: writes the block described above through `sink` and returns; the sum is finished one round later.
   template <typename Sink>
   __device__ void defer_lights(const RayRec &cur, const C3 &thr, const D3 &P, const D3 &Nf, int shaded_object, int slot, const float4 &dm, Sink &sink) {
+    // one pass over the light samples decides which reach the point and keeps their rays (up to FJ_LIGHT_CACHE of them; a
+    // second pass recomputes only what did not fit), then the block is reserved and written
+    struct Kept { double lx, ly, lz, dist; float r, g, b, kd; };
+    Kept kept[FJ_LIGHT_CACHE];
     int n = 0;
     for_each_light_sample(cur.node, [&](const DLight &lt, const LightSample &ls) {
       C3 lc; D3 Ln; double distance;
-      if (light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) n++;
+      if (!light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) return;
+      if (n < FJ_LIGHT_CACHE) {
+        float Kd = (float)dot(Nf, Ln);
+        Kd = Kd > 0.f ? Kd : 0.f;
+        Kept &k = kept[n]; k.lx = Ln.x; k.ly = Ln.y; k.lz = Ln.z; k.dist = distance; k.r = lc.r; k.g = lc.g; k.b = lc.b; k.kd = Kd;
+      }
+      n++;
     });
     if (n == 0) return;                                            // diff = 0: the diffuse term adds nothing
     unsigned at = sink.reserve((unsigned)n + 1u);
@@ -217,17 +228,28 @@ struct Shading {
     c.pad2 = __float_as_int(dm.y); c.pad3 = __float_as_int(dm.z);
     c.target = sc.inst[shaded_object].shadow_target; c.type = RAY_SHADOW_HEAD; c.filter_shader = slot;
     sink.put(at++, c);
-    for_each_light_sample(cur.node, [&](const DLight &lt, const LightSample &ls) {
-      C3 lc; D3 Ln; double distance;
-      if (!light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) return;
-      float Kd = (float)dot(Nf, Ln);
-      Kd = Kd > 0.f ? Kd : 0.f;
-      RayRec r; memset(&r, 0, sizeof r);
-      r.o[0] = P.x; r.o[1] = P.y; r.o[2] = P.z; r.d[0] = Ln.x; r.d[1] = Ln.y; r.d[2] = Ln.z; r.tmin = .0001; r.tmax = distance;
-      r.thr[0] = lc.r; r.thr[1] = lc.g; r.thr[2] = lc.b; r.slot = cur.slot; r.pad2 = __float_as_int(Kd);
-      r.target = sc.inst[shaded_object].shadow_target; r.type = RAY_SHADOW; r.filter_shader = -1;
+    RayRec r; memset(&r, 0, sizeof r);
+    r.o[0] = P.x; r.o[1] = P.y; r.o[2] = P.z; r.tmin = .0001; r.slot = cur.slot;
+    r.target = sc.inst[shaded_object].shadow_target; r.type = RAY_SHADOW; r.filter_shader = -1;
+    const int nc = min(n, FJ_LIGHT_CACHE);
+    for (int k = 0; k < nc; k++) {
+      r.d[0] = kept[k].lx; r.d[1] = kept[k].ly; r.d[2] = kept[k].lz; r.tmax = kept[k].dist;
+      r.thr[0] = kept[k].r; r.thr[1] = kept[k].g; r.thr[2] = kept[k].b; r.pad2 = __float_as_int(kept[k].kd);
       sink.put(at++, r);
-    });
+    }
+    if (n > FJ_LIGHT_CACHE) {
+      int seen = 0;
+      for_each_light_sample(cur.node, [&](const DLight &lt, const LightSample &ls) {
+        C3 lc; D3 Ln; double distance;
+        if (!light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) return;
+        if (seen++ < FJ_LIGHT_CACHE) return;
+        float Kd = (float)dot(Nf, Ln);
+        Kd = Kd > 0.f ? Kd : 0.f;
+        r.d[0] = Ln.x; r.d[1] = Ln.y; r.d[2] = Ln.z; r.tmax = distance;
+        r.thr[0] = lc.r; r.thr[1] = lc.g; r.thr[2] = lc.b; r.pad2 = __float_as_int(Kd);
+        sink.put(at++, r);
+      });
+    }
   }
 
   template <typename Sink>
@@ -830,15 +852,16 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
 // reconstruct_image + apply_pixel_filter (src/fj_renderer.cc:939-995), get_sampleset_in_pixel
 // (src/fj_fixed_grid_sampler.cc:97-124), Gaussian (src/fj_filter.cc:49-58).  One CTA per tile, one thread per pixel.
 // Output: packed tile blocks, block ti = bw*bh float4 (row-major inside the tile; texels outside the tile untouched).
+#define FJ_RESOLVE_SPLIT 4
 __global__ void __launch_bounds__(256) k_resolve_tiles(const DFrame fr, const DTile *tiles, uint32_t wstride,
                                                        const Accum *samples, float4 *blocks, int bw, int bh) {
-  const int ti = blockIdx.x;
+  const int ti = blockIdx.x / FJ_RESOLVE_SPLIT, part = blockIdx.x % FJ_RESOLVE_SPLIT;      // a tile is shared by FJ_RESOLVE_SPLIT CTAs
   const DTile t = tiles[ti];
   const TileGrid g = tile_grid(fr, t);
   const int w = t.xmax - t.xmin, h = t.ymax - t.ymin;
   const int npx = fr.xrate + 2 * fr.mx, npy = fr.yrate + 2 * fr.my;
   const Accum *smp = samples + (size_t)ti * wstride;
-  for (int p = threadIdx.x; p < w * h; p += blockDim.x) {
+  for (int p = part * blockDim.x + threadIdx.x; p < w * h; p += FJ_RESOLVE_SPLIT * blockDim.x) {
     const int px = p % w, py = p / w;
     const int x = t.xmin + px, y = t.ymin + py;
     float pr = 0, pg = 0, pb = 0, pa = 0, wsum = 0;
