@@ -785,36 +785,25 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const RenderArgs a) {
 // compacted into queue[cur ^ 1] by warp ballot (Shader::Evaluate + the Sl*Context/SlTrace calls the plugins make).
 // PLASTIC = false drops the light loop and its inline shadow-ray traversal from the kernel (scenes without a plastic
 // shader): fewer registers, more resident warps.
-// Finishes the diffuse term of a plastic hit from its block of traced shadow rays (see Shading): records i+1 .. i+n of the
-// queue and their hit records, in light-sample order; exactly the float operations of Shading::gather_lights.
-__device__ __forceinline__ void finish_shadow_block(const RenderArgs &a, const RayRec *rays, unsigned i, const RayRec &head, ShadeCounters &cnt) {
-  const int n = (int)(unsigned)(head.node & 0xffffffffull);
-  C3 diff = c3(0, 0, 0);
-  for (int k = 1; k <= n; k++) {
-    const RayRec *rr = rays + i + k;
-    const float4 w = __ldcs(reinterpret_cast<const float4 *>(rr) + 4);        // thr[3], slot
-    const int kdbits = __ldcs(reinterpret_cast<const int *>(rr) + 26);         // pad2
-    HitRec hr; load_hit_cs(&hr, a.hits + i + k);
-    C3 lc = c3(w.x, w.y, w.z);
-    if (hr.inst >= 0) {
-      Hit h; h.t = hr.t; h.u = hr.u; h.v = hr.v; h.prim = hr.prim; h.inst = hr.inst;
-      const float ac = fadd(1.f, -occluder_opacity(a.sc, h));
-      lc.r = fmul(lc.r, ac); lc.g = fmul(lc.g, ac); lc.b = fmul(lc.b, ac);
-    }
-    const float Kd = __int_as_float(kdbits);
-    diff.r = fadd(diff.r, fmul(Kd, lc.r)); diff.g = fadd(diff.g, fmul(Kd, lc.g)); diff.b = fadd(diff.b, fmul(Kd, lc.b));
+// The term one traced shadow ray contributes to its block's sum: Kd * (Cl * (1 - alpha_occluder)), the float operations of
+// Shading::gather_lights in the same order.
+__device__ __forceinline__ C3 shadow_term(const DScene &sc, const float thr[3], int kdbits, const HitRec &hr) {
+  C3 lc = c3(thr[0], thr[1], thr[2]);
+  if (hr.inst >= 0) {
+    Hit h; h.t = hr.t; h.u = hr.u; h.v = hr.v; h.prim = hr.prim; h.inst = hr.inst;
+    const float ac = fadd(1.f, -occluder_opacity(sc, h));
+    lc.r = fmul(lc.r, ac); lc.g = fmul(lc.g, ac); lc.b = fmul(lc.b, ac);
   }
-  const DShader &sh = a.sc.shaders[head.filter_shader];
-  const float dmx = __uint_as_float((unsigned)(head.node >> 32)), dmy = __int_as_float(head.pad2), dmz = __int_as_float(head.pad3);
-  const long long fr_ = to_fix(fmul(head.thr[0], fmul(fmul(diff.r, sh.diffuse[0]), dmx)));
-  const long long fg_ = to_fix(fmul(head.thr[1], fmul(fmul(diff.g, sh.diffuse[1]), dmy)));
-  const long long fb_ = to_fix(fmul(head.thr[2], fmul(fmul(diff.b, sh.diffuse[2]), dmz)));
-  Accum *acc = a.accum + head.slot;
-  if (fr_) atomicAdd((unsigned long long *)&acc->r, (unsigned long long)fr_);
-  if (fg_) atomicAdd((unsigned long long *)&acc->g, (unsigned long long)fg_);
-  if (fb_) atomicAdd((unsigned long long *)&acc->b, (unsigned long long)fb_);
+  const float Kd = __int_as_float(kdbits);
+  return c3(fmul(Kd, lc.r), fmul(Kd, lc.g), fmul(Kd, lc.b));
 }
 
+// One thread per traced ray of queue[cur]: shader evaluation, radiance into the sample accumulators, secondary rays
+// compacted into queue[cur ^ 1] by warp ballot (Shader::Evaluate + the Sl*Context/SlTrace calls the plugins make).
+// PLASTIC = false drops the light loop and the shadow-ray blocks from the kernel (scenes without a plastic shader).
+// PLASTIC = true: a warp walks 32 consecutive records; the lanes that hold traced shadow rays compute their terms, the
+// lane that holds the block's header gathers them IN SAMPLE ORDER with shuffles (and reads the few that lie beyond the
+// warp's 32 records from memory), so the float sum equals the inline loop's bit for bit.
 template <typename T, bool PLASTIC, int MINB = (PLASTIC ? 3 : 5)>
 __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   const int lane = threadIdx.x & 31;
@@ -822,16 +811,58 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->head = 0;                  // the next k_extend starts at the queue head
   const RayRec *rays = a.queue[a.cur];
   ShadeCounters cnt; memset(&cnt, 0, sizeof cnt);
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    RayRec cur; load_ray_cs(&cur, rays + i);
-    if (PLASTIC && cur.type == RAY_SHADOW_HEAD) { finish_shadow_block(a, rays, i, cur, cnt); continue; }
-    HitRec hr; load_hit_cs(&hr, a.hits + i);
-    cnt.rays[cur.type]++;
-    if (hr.inst < 0) continue;
-    if (PLASTIC && cur.type == RAY_SHADOW) {        // traced for its block's header; counted like the inline shadow rays
-      cnt.hits++; cnt.levels += a.sc.meshes[a.sc.inst[hr.inst].mesh].log2_tris;
-      continue;
+  // PLASTIC: whole 32-record groups per warp (the gather below is warp-synchronous); otherwise one record per thread
+  const unsigned start = PLASTIC ? ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u) : (blockIdx.x * blockDim.x + threadIdx.x);
+  for (unsigned i0 = start; i0 < count; i0 += gridDim.x * blockDim.x) {
+    const unsigned i = PLASTIC ? i0 + lane : i0;
+    const bool valid = i < count;
+    RayRec cur; HitRec hr; hr.inst = -1;
+    if constexpr (PLASTIC) { cur.type = 255; cur.node = 0; cur.pad2 = 0; cur.thr[0] = cur.thr[1] = cur.thr[2] = 0.f; }
+    if (valid) {
+      load_ray_cs(&cur, rays + i);
+      if (!PLASTIC || cur.type != RAY_SHADOW_HEAD) { load_hit_cs(&hr, a.hits + i); cnt.rays[cur.type]++; }
     }
+    if constexpr (PLASTIC) {
+      const bool is_head = cur.type == RAY_SHADOW_HEAD, is_shadow = cur.type == RAY_SHADOW;
+      C3 term = c3(0, 0, 0);
+      if (is_shadow) {
+        if (hr.inst >= 0) { cnt.hits++; cnt.levels += a.sc.meshes[a.sc.inst[hr.inst].mesh].log2_tris; }       // counted like the inline shadow rays
+        term = shadow_term(a.sc, cur.thr, cur.pad2, hr);
+      }
+      const int n = is_head ? (int)(unsigned)(cur.node & 0xffffffffull) : 0;
+      const int n_in = min(n, 31 - lane);                     // records of the block inside this warp's 32
+      int maxn = n_in;
+      for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
+      C3 diff = c3(0, 0, 0);
+      for (int k = 1; k <= maxn; k++) {
+        const float tr = __shfl_sync(0xffffffffu, term.r, (lane + k) & 31), tg = __shfl_sync(0xffffffffu, term.g, (lane + k) & 31),
+                    tb = __shfl_sync(0xffffffffu, term.b, (lane + k) & 31);
+        if (k <= n_in) { diff.r = fadd(diff.r, tr); diff.g = fadd(diff.g, tg); diff.b = fadd(diff.b, tb); }
+      }
+      if (is_head) {
+        for (int k = n_in + 1; k <= n; k++) {                 // the rest of the block belongs to the next warp's records
+          const RayRec *rr = rays + i + k;
+          const float4 w = __ldcs(reinterpret_cast<const float4 *>(rr) + 4);          // thr[3], slot
+          const int kdbits = __ldcs(reinterpret_cast<const int *>(rr) + 26);           // pad2
+          HitRec h2; load_hit_cs(&h2, a.hits + i + k);
+          const float th[3] = {w.x, w.y, w.z};
+          const C3 t2 = shadow_term(a.sc, th, kdbits, h2);
+          diff.r = fadd(diff.r, t2.r); diff.g = fadd(diff.g, t2.g); diff.b = fadd(diff.b, t2.b);
+        }
+        // Cs = diff * diffuse * diff_map, times the parent's throughput (plastic_shader.cc:148-156)
+        const DShader &sh = a.sc.shaders[cur.filter_shader];
+        const float dmx = __uint_as_float((unsigned)(cur.node >> 32)), dmy = __int_as_float(cur.pad2), dmz = __int_as_float(cur.pad3);
+        const long long fr_ = to_fix(fmul(cur.thr[0], fmul(fmul(diff.r, sh.diffuse[0]), dmx)));
+        const long long fg_ = to_fix(fmul(cur.thr[1], fmul(fmul(diff.g, sh.diffuse[1]), dmy)));
+        const long long fb_ = to_fix(fmul(cur.thr[2], fmul(fmul(diff.b, sh.diffuse[2]), dmz)));
+        Accum *acc = a.accum + cur.slot;
+        if (fr_) atomicAdd((unsigned long long *)&acc->r, (unsigned long long)fr_);
+        if (fg_) atomicAdd((unsigned long long *)&acc->g, (unsigned long long)fg_);
+        if (fb_) atomicAdd((unsigned long long *)&acc->b, (unsigned long long)fb_);
+      }
+      if (is_head || is_shadow) continue;
+    }
+    if (!valid || hr.inst < 0) continue;
     int ti, x, y; TileGrid g;
     slot_decode(a.fr, a.tiles, a.wstride, cur.slot, &ti, &g, &x, &y);
     PathKey key; key.seed = a.fr.seed; key.tile = (uint32_t)a.tiles[ti].id; key.sample = (uint32_t)(y * g.nsx + x);
