@@ -632,7 +632,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
           launch_extend(ctx, a, grid);
           CK(cudaGetLastError());
           CK(cudaEventRecord(e1, ctx->stream));
-          if (has_plastic) fj::k_shade<float, true><<<ctx->sm_count * 6, 128, 0, ctx->stream>>>(a);
+          if (has_plastic) fj::k_shade<float, true><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a);
           else {
             const int smb = env_int("FJGPU_SHADE_MINBLOCKS", 5), per = env_int("FJGPU_SHADE_CTAS", 2);
             if (smb >= 8) fj::k_shade<float, false, 8><<<ctx->sm_count * 8 * per, 128, 0, ctx->stream>>>(a);

@@ -179,12 +179,13 @@ struct Shading {
 
   // diff = sum over all light samples of max(0, Nf.Ln) * Cl — the loop of PlasticShader::evaluate (plastic_shader.cc:117-137),
   // shadow rays traced inline (SlShadowContext :266-279).
+  template <bool TRACE>
   __device__ C3 gather_lights(const D3 &P, const D3 &Nf, int shaded_object, unsigned long long node) {
     C3 diff = c3(0, 0, 0);
     for_each_light_sample(node, [&](const DLight &lt, const LightSample &ls) {
       C3 lc; D3 Ln; double distance;
       if (!light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) return;
-      if (fr.cast_shadow) {
+      if (TRACE && fr.cast_shadow) {
         RayD sr; sr.o = P; sr.d = Ln; sr.tmin = .0001; sr.tmax = distance;
         Hit h;
         cnt.rays[RAY_SHADOW]++;
@@ -293,7 +294,7 @@ struct Shading {
       if (sh.texture) { float tu, tv; hit_uv(sc, h, &tu, &tv); dm = tex_lookup(sc.textures[sh.texture - 1], tu, tv); }
       if (DEFER && fr.cast_shadow) defer_lights(cur, thr, P, Nf, h.inst, slot, dm, sink);
       else {
-        const C3 diff = gather_lights(P, Nf, h.inst, cur.node);
+        const C3 diff = gather_lights<!DEFER>(P, Nf, h.inst, cur.node);      // (DEFER: only reached without shadow casting)
         sink.add(fmul(thr.r, fmul(fmul(diff.r, sh.diffuse[0]), dm.x)), fmul(thr.g, fmul(fmul(diff.g, sh.diffuse[1]), dm.y)), fmul(thr.b, fmul(fmul(diff.b, sh.diffuse[2]), dm.z)));
       }
       if (sh.do_reflect && (int)cur.rd + 1 <= fr.max_reflect) {    // SlReflectContext :242-252, gate :467-499
@@ -804,7 +805,7 @@ __device__ __forceinline__ C3 shadow_term(const DScene &sc, const float thr[3], 
 // PLASTIC = true: a warp walks 32 consecutive records; the lanes that hold traced shadow rays compute their terms, the
 // lane that holds the block's header gathers them IN SAMPLE ORDER with shuffles (and reads the few that lie beyond the
 // warp's 32 records from memory), so the float sum equals the inline loop's bit for bit.
-template <typename T, bool PLASTIC, int MINB = (PLASTIC ? 3 : 5)>
+template <typename T, bool PLASTIC, int MINB = (PLASTIC ? 4 : 5)>
 __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
