@@ -99,6 +99,7 @@ FJGPU_SYMBOLS = [
     "fjgpu_lights_set", "fjgpu_camera_set", "fjgpu_render_tiles", "fjgpu_render_tiles_device",
     "fjgpu_render_tiles_resident", "fjgpu_trace_closest", "fjgpu_render_tile_samples",
     "fjgpu_scene_info_get", "fjgpu_scene_resend", "fjgpu_textures_set", "fjgpu_mesh_set_uv",
+    "fjgpu_time_table", "fjgpu_instance_motion_set", "fjgpu_camera_motion_set",
 ]
 
 _P = C.POINTER
@@ -124,6 +125,9 @@ def _proto(lib):
     lib.fjgpu_render_tile_samples.argtypes = [vp, _P(RenderParams), _P(Tile), i32, f64p, _P(C.c_float), i32p]
     lib.fjgpu_scene_info_get.argtypes = [vp, _P(SceneInfo)]
     lib.fjgpu_scene_resend.argtypes = [vp, _P(C.c_uint64)]
+    lib.fjgpu_time_table.argtypes = [_P(RenderParams), _P(Tile), i32, C.c_double, C.c_double, f64p, i32]
+    lib.fjgpu_instance_motion_set.argtypes = [vp, i32, i32, f64p, f64p]
+    lib.fjgpu_camera_motion_set.argtypes = [vp, i32, f64p]
     return lib
 
 

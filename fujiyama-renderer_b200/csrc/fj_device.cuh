@@ -81,7 +81,13 @@ struct DInstance {
   int32_t mesh;
   int32_t shader_of_group[FJ_MAX_SHADING_GROUPS];
   int32_t reflect_target, refract_target, shadow_target;
+  const double *motion;     // time-sampled transform (motion blur): 24 doubles per entry of the frame's time table, inv[12] then
+                            // fwd[12], evaluated by the caller with the reference's own transform code (fjgpu.h); null = static
 };
+// The matrices of an instance for a ray whose sample drew entry `tidx` of the time table
+// (XfmLerpTransformSample per ray, src/fj_object_instance.cc:219-220).
+__device__ __forceinline__ const double *inst_inv(const DInstance &in, uint32_t tidx) { return in.motion ? in.motion + 24 * (size_t)tidx : in.inv; }
+__device__ __forceinline__ const double *inst_fwd(const DInstance &in, uint32_t tidx) { return in.motion ? in.motion + 24 * (size_t)tidx + 12 : in.fwd; }
 // Everything k_extend2 needs to enter an instance, in TLAS-leaf order (leaf `first` indexes this array directly): one
 // 144-B record instead of the chain order[] -> DInstance -> DMesh (the kernel is bound by dependent-load latency).
 struct DInstRec {
@@ -90,7 +96,7 @@ struct DInstRec {
   const void *tri;          // tri32 or tri64 packets
   float bmag, bmagq;
   int32_t tri64, inst;      // packet format, instance index (DScene::inst)
-  int32_t pad[2];
+  const double *motion;     // DInstance::motion
 };
 static_assert(sizeof(DInstRec) == 144, "instance record must be 144 bytes");
 struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; const float4 *nodes4q; const float4 *nodesq; float bmagq, pad2; const DInstRec *irec; };   // TLAS leaf (first,count) -> order[first..] = instance indices
@@ -114,7 +120,7 @@ struct DScene {
   const DMesh *meshes; const DInstance *inst; const DGroup *groups; const DShader *shaders; const DLight *lights;
   int32_t nmeshes, ninst, ngroups, nshaders, nlights, pad;
 };
-struct DCamera { double fwd[12]; double uvx, uvy, znear, zfar; };   // uv_size_ computed on the host (fj_camera.cc:97-101)
+struct DCamera { double fwd[12]; double uvx, uvy, znear, zfar; const double *motion; };   // motion: fwd[12] per time-table entry, null = static   // uv_size_ computed on the host (fj_camera.cc:97-101)
 struct DFrame {
   int32_t xres, yres, xrate, yrate;
   int32_t mx, my;                 // margin samples, count_samples_in_margin (fj_fixed_grid_sampler.cc:131-136)
@@ -147,7 +153,7 @@ __device__ __forceinline__ double ctr_rand(uint32_t seed, uint32_t tile, uint32_
 }
 
 // ------------------------------------------------------------------------------------------ traversal
-struct RayD { D3 o, d; double tmin, tmax; };
+struct RayD { D3 o, d; double tmin, tmax; uint32_t tidx = 0; };   // tidx: entry of the frame's time table (TraceContext::time)
 
 // TriRayIntersect, non-culling branch — src/fj_triangle.cc:81-153 (:127-151), EPSILON :12
 __device__ __forceinline__ bool tri_intersect(const D3 &v0, const D3 &v1, const D3 &v2, const D3 &orig, const D3 &dir,
@@ -279,8 +285,8 @@ __device__ __noinline__ bool trace_closest(const DScene &sc, int g, const RayD &
         for (int k = count - 1; k >= 1; k--) stack[sp++] = ~(((first + k) << 3) | 0);
         cur_inst = grp.order[first];
         const DInstance &in = sc.inst[cur_inst];
-        o = mat_point(in.inv, ray.o);
-        d = mat_vector(in.inv, ray.d);
+        o = mat_point(inst_inv(in, ray.tidx), ray.o);
+        d = mat_vector(inst_inv(in, ray.tidx), ray.d);
         make_box_ray<T>(o, d, br);
         mesh = &sc.meshes[in.mesh];
         nodes = mesh->nodes;
@@ -360,7 +366,8 @@ struct RayRec {
   int32_t target;                 // object group traced
   uint8_t type, dd, rd, fd;       // ray context and the three depth counters of TraceContext (fj_shading.h:26-47)
   int32_t filter_shader;          // >= 0: refracted child whose radiance is scaled by pow(transmit, t_hit) of that shader
-  uint32_t key;                   // sort key of the ray (direction octant | Morton code of the origin cell), see k_shade
+  uint32_t key;                   // sort key of the ray (direction octant | Morton code of the origin cell), see k_shade; in
+                                  // frames with time-sampled transforms (sorting off): the ray's entry of the time table
   int32_t pad2, pad3;
 };
 static_assert(sizeof(RayRec) == 112, "ray record must be 112 bytes");
@@ -384,7 +391,8 @@ __device__ __forceinline__ float from_fix(long long v) { return (float)dmul((dou
 __device__ __forceinline__ void hit_surface(const DScene &sc, const RayD &ray, const Hit &h, D3 *P, D3 *N, int *shader_slot) {
   const DInstance &in = sc.inst[h.inst];
   const DMesh &m = sc.meshes[in.mesh];
-  const D3 o = mat_point(in.inv, ray.o), d = mat_vector(in.inv, ray.d);
+  const double *inv = inst_inv(in, ray.tidx), *fwd = inst_fwd(in, ray.tidx);
+  const D3 o = mat_point(inv, ray.o), d = mat_vector(inv, ray.d);
   const D3 Pobj = o + h.t * d;                                   // RayPointAt, fj_ray.h:24-27
   D3 Nobj = mk(0, 0, 0);
   const int i0 = m.idx[3 * (size_t)h.prim], i1 = m.idx[3 * (size_t)h.prim + 1], i2 = m.idx[3 * (size_t)h.prim + 2];
@@ -394,8 +402,8 @@ __device__ __forceinline__ void hit_surface(const DScene &sc, const RayD &ray, c
     const D3 N2 = mk(m.N[3 * (size_t)i2], m.N[3 * (size_t)i2 + 1], m.N[3 * (size_t)i2 + 2]);
     Nobj = (dsub(dsub(1., h.u), h.v) * N0 + h.u * N1) + h.v * N2;   // TriComputeNormal, fj_triangle.cc:44-49
   }
-  *P = mat_point(in.fwd, Pobj);
-  *N = normalize(mat_vector(in.fwd, Nobj));
+  *P = mat_point(fwd, Pobj);
+  *N = normalize(mat_vector(fwd, Nobj));
   int gid = m.group ? m.group[h.prim] : 0;                         // ObjectInstance::GetShader, fj_object_instance.cc:177-191
   int slot = (gid < 0 || gid >= FJ_MAX_SHADING_GROUPS) ? in.shader_of_group[0] : in.shader_of_group[gid];
   if (slot < 0) slot = in.shader_of_group[0];
@@ -418,7 +426,7 @@ __device__ __forceinline__ void hit_uv(const DScene &sc, const Hit &h, float *tu
 // dPdu, dPdv of a hit in world space: TriComputeDerivatives (src/fj_triangle.cc:51-74: float uv differences and determinant,
 // `const float invdet = 1. / determinant`, FP64 edges) inside Mesh::ray_intersect (fj_mesh.cc:287-290), then the instance's
 // forward matrix (XfmTransformVector, fj_object_instance.cc:237-238).  Zero without uv or with a degenerate uv triangle.
-__device__ __forceinline__ void hit_derivatives(const DScene &sc, const Hit &h, D3 *dPdu, D3 *dPdv) {
+__device__ __forceinline__ void hit_derivatives(const DScene &sc, const Hit &h, uint32_t tidx, D3 *dPdu, D3 *dPdv) {
   const DInstance &in = sc.inst[h.inst];
   const DMesh &m = sc.meshes[in.mesh];
   *dPdu = mk(0, 0, 0); *dPdv = mk(0, 0, 0);
@@ -435,7 +443,7 @@ __device__ __forceinline__ void hit_derivatives(const DScene &sc, const Hit &h, 
   const float invdet = (float)ddiv(1., (double)det);
   const D3 a = ((double)dv2 * dP1 - (double)dv1 * dP2) * (double)invdet;
   const D3 b = ((double)(-du2) * dP1 + (double)du1 * dP2) * (double)invdet;
-  *dPdu = mat_vector(in.fwd, a); *dPdv = mat_vector(in.fwd, b);
+  *dPdu = mat_vector(inst_fwd(in, tidx), a); *dPdv = mat_vector(inst_fwd(in, tidx), b);
 }
 
 // TextureCache::LookupTexture, src/fj_texture.cc:51-78: wrap to [0,1), flip v, tile = floor(coordinate * tile count) clamped

@@ -294,8 +294,9 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           const RayRec &r = rays[S.ridx[tid]];
           const DInstRec &in = sc.groups[r.target].irec[first];          // one record: matrix, tree, packets (no order[] -> instance -> mesh chain)
           S.cur_inst[tid] = in.inst;
-          const D3 o = mat_point(in.inv, mk(r.o[0], r.o[1], r.o[2]));
-          const D3 d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
+          const double *inv = in.motion ? in.motion + 24 * (size_t)r.key : in.inv;     // time-sampled transform: the ray's entry of the time table
+          const D3 o = mat_point(inv, mk(r.o[0], r.o[1], r.o[2]));
+          const D3 d = mat_vector(inv, mk(r.d[0], r.d[1], r.d[2]));
           S.ox[tid] = o.x; S.oy[tid] = o.y; S.oz[tid] = o.z; S.dx[tid] = d.x; S.dy[tid] = d.y; S.dz[tid] = d.z;
           make_box_ray_mm(o, d, QUANT ? in.bmagq : in.bmag, br);
           nodes = QUANT ? in.nodesq : in.nodes4;

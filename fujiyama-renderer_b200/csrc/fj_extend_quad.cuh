@@ -236,8 +236,9 @@ __global__ void __launch_bounds__(FJ_QT, MINB) k_extend3(const RenderArgs a, con
           const RayRec &r = rays[S.ridx[rs]];
           const int ci = sc.groups[r.target].order[first];
           const DInstance &in = sc.inst[ci];
-          const D3 o = mat_point(in.inv, mk(r.o[0], r.o[1], r.o[2]));
-          const D3 d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
+          const double *inv = inst_inv(in, r.key);
+          const D3 o = mat_point(inv, mk(r.o[0], r.o[1], r.o[2]));
+          const D3 d = mat_vector(inv, mk(r.d[0], r.d[1], r.d[2]));
           const DMesh &m = sc.meshes[in.mesh];
           make_box_ray_mm(o, d, m.bmag, br);
           nodes = (const char *)m.nodes4q;

@@ -61,6 +61,10 @@ struct fjgpu_context {
   std::vector<std::vector<float>> dome_cols;
   fjgpu_camera cam;
   bool have_cam = false, dirty = true;
+  // motion blur: per-instance / camera matrices at every entry of the frame's time table (fjgpu.h)
+  std::map<int, std::vector<double>> inst_motion;     // instance -> ntimes x (inv[12], fwd[12])
+  std::vector<double> cam_motion;                     // ntimes x fwd[12]
+  std::map<int, DevBuf> d_inst_motion; DevBuf d_cam_motion; bool cam_motion_dirty = false;
 
   // device scene
   DevBuf d_meshes, d_inst, d_groups, d_shaders, d_lights;
@@ -144,6 +148,10 @@ int commit_scene(fjgpu_context *ctx) {
   if (int rc = dev_upload(ctx, ctx->d_meshes, dm.data(), dm.size() * sizeof(fj::DMesh), true)) return rc;
 
   const int ninst = (int)ctx->inst.size();
+  for (auto it = ctx->d_inst_motion.begin(); it != ctx->d_inst_motion.end();) {
+    auto mit = ctx->inst_motion.find(it->first);
+    if (it->first >= ninst || mit == ctx->inst_motion.end() || mit->second.empty()) { it->second.release(); it = ctx->d_inst_motion.erase(it); } else ++it;
+  }
   std::vector<fj::DInstance> di(ninst);
   std::vector<fjb::Aabb> ibox(ninst);
   for (int i = 0; i < ninst; i++) {
@@ -154,6 +162,13 @@ int commit_scene(fjgpu_context *ctx) {
     memset(&d, 0, sizeof d);
     rows12(s.inv, d.inv); rows12(s.fwd, d.fwd);
     d.mesh = slot[s.mesh_id];
+    const std::vector<double> *motion = nullptr;
+    { auto mit = ctx->inst_motion.find(i); if (mit != ctx->inst_motion.end() && !mit->second.empty()) motion = &mit->second; }
+    if (motion) {
+      DevBuf &mb = ctx->d_inst_motion[i];
+      if (int rc = dev_upload(ctx, mb, motion->data(), motion->size() * sizeof(double), true)) return rc;
+      d.motion = (const double *)mb.p;
+    }
     for (int g = 0; g < FJGPU_MAX_SHADING_GROUPS; g++) {
       d.shader_of_group[g] = s.shader_of_group[g];
       if (d.shader_of_group[g] >= (int)ctx->shaders.size()) return fail(ctx, FJGPU_ERR_INVALID, "instance refers to an unknown shader slot");
@@ -168,11 +183,19 @@ int commit_scene(fjgpu_context *ctx) {
     const MeshRec &m = it->second;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     if (m.nfaces > 0) {
-      for (int c = 0; c < 8; c++) {
-        double p[3], q[3];
-        for (int a = 0; a < 3; a++) p[a] = ((c >> a) & 1) ? m.bmax[a] + 1e-4 : m.bmin[a] - 1e-4;
-        xpoint(s.fwd, p, q);
-        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[a]); }
+      // a moving instance is bounded over every entry of its table: rays only ever carry those times, so the union is
+      // conservative without the reference's bounding-sphere estimate (merge_sampled_bounds, fj_object_instance.cc:313-360)
+      const size_t nt = motion ? motion->size() / 24 : 1;
+      for (size_t t = 0; t < nt; t++) {
+        double f16[16] = {0};
+        if (motion) memcpy(f16, motion->data() + 24 * t + 12, 12 * sizeof(double));
+        const double *fwd = motion ? f16 : s.fwd;
+        for (int c = 0; c < 8; c++) {
+          double p[3], q[3];
+          for (int a = 0; a < 3; a++) p[a] = ((c >> a) & 1) ? m.bmax[a] + 1e-4 : m.bmin[a] - 1e-4;
+          xpoint(fwd, p, q);
+          for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[a]); }
+        }
       }
       pad_box(lo, hi, &ibox[i]);
     } else {
@@ -246,7 +269,7 @@ int commit_scene(fjgpu_context *ctx) {
         memcpy(r.inv, in.inv, sizeof r.inv);
         r.nodes4 = (const char *)me.nodes4; r.nodesq = (const char *)me.nodesq;
         r.tri64 = me.tri32 == nullptr; r.tri = r.tri64 ? (const void *)me.tri64 : (const void *)me.tri32;
-        r.bmag = me.bmag; r.bmagq = me.bmagq; r.inst = order[k];
+        r.bmag = me.bmag; r.bmagq = me.bmagq; r.inst = order[k]; r.motion = in.motion;
       }
       if (int rc = dev_upload(ctx, ctx->d_group_irec[g], rec.data(), rec.size() * sizeof(fj::DInstRec), true)) return rc;
       dg[g].irec = (const fj::DInstRec *)ctx->d_group_irec[g].p;
@@ -421,6 +444,20 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
   pl->cam.uvy = 2 * std::tan((ctx->cam.fov / 2.) * PI / 180.);
   pl->cam.uvx = pl->cam.uvy * aspect;
   rows12(ctx->cam.fwd, pl->cam.fwd); pl->cam.znear = ctx->cam.znear; pl->cam.zfar = ctx->cam.zfar;
+  // time-sampled transforms: every table must cover the frame's time table (one entry per sample of the largest tile)
+  pl->cam.motion = nullptr;
+  for (auto &kv : ctx->inst_motion)
+    if (!kv.second.empty() && kv.second.size() / 24 < (size_t)fr.max_ns)
+      return fail(ctx, FJGPU_ERR_INVALID, "instance motion table is shorter than the frame's time table (fjgpu_time_table)");
+  if (!ctx->cam_motion.empty()) {
+    if (ctx->cam_motion.size() / 12 < (size_t)fr.max_ns) return fail(ctx, FJGPU_ERR_INVALID, "camera motion table is shorter than the frame's time table (fjgpu_time_table)");
+    if (ctx->cam_motion_dirty) {
+      if (int rc = dev_upload(ctx, ctx->d_cam_motion, ctx->cam_motion.data(), ctx->cam_motion.size() * sizeof(double))) return rc;
+      CK(cudaStreamSynchronize(ctx->stream));
+      ctx->cam_motion_dirty = false;
+    }
+    pl->cam.motion = (const double *)ctx->d_cam_motion.p;
+  }
   // batch so the per-batch buffers (accumulators + two ray queues + hit records) stay bounded
   double block = 0;
   frontier(ctx, p, &pl->waves, &pl->peak, &block);
@@ -600,7 +637,9 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         a.queue[0] = (fj::RayRec *)ctx->d_queue[0].p; a.queue[1] = (fj::RayRec *)((char *)ctx->d_queue[0].p + qbytes + pad);
         a.hits = (fj::HitRec *)((char *)ctx->d_queue[0].p + 2 * (qbytes + pad));
         a.ctl = (fj::QueueCtl *)ctl_p; a.capacity = (uint32_t)capacity; a.cur = 0;
-        const int sort_bits = pl.waves > 1 ? std::min(7, std::max(0, env_int("FJGPU_SORT_BITS", 0))) : 0;
+        bool moving = !ctx->cam_motion.empty();            // RayRec::key carries the time-table entry then: no sorting
+        for (auto &kv : ctx->inst_motion) moving = moving || !kv.second.empty();
+        const int sort_bits = pl.waves > 1 && !moving ? std::min(7, std::max(0, env_int("FJGPU_SORT_BITS", 0))) : 0;
         a.hist = nullptr; a.perm = nullptr; a.sort_bits = sort_bits; a.sort_bins = 8u << (3 * sort_bits);
         if (sort_bits > 0) {
           if (int rc = dev_alloc(ctx, ctx->d_hist, ((size_t)a.sort_bins + 1) * 4)) return rc;
@@ -754,6 +793,8 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &b : ctx->d_dome) b.release();
   for (auto &b : ctx->d_tex_tiles) b.release();
   ctx->d_textures.release();
+  for (auto &kv : ctx->d_inst_motion) kv.second.release();
+  ctx->d_cam_motion.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
                    &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl, &ctx->d_hist, &ctx->d_perm};
   for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -893,6 +934,52 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
 int fjgpu_instances_set(fjgpu_context *ctx, int32_t n, const fjgpu_instance *inst) {
   if (!ctx || n < 0 || (n > 0 && !inst)) return fail(ctx, FJGPU_ERR_INVALID, "bad instance array");
   ctx->inst.assign(inst, inst + n); ctx->dirty = true;
+  ctx->inst_motion.clear();
+  return FJGPU_OK;
+}
+
+namespace {
+// count_samples_in_region of the largest tile, src/fj_fixed_grid_sampler.cc:119-136
+long max_tile_samples(const fjgpu_render_params *p, const fjgpu_tile *tiles, int ntiles) {
+  int mx = (int)std::ceil(((p->xfwidth - 1) * p->xrate) * .5), my = (int)std::ceil(((p->yfwidth - 1) * p->yrate) * .5);
+  if (mx < 0) mx = 0; if (my < 0) my = 0;
+  int tw = 1, th = 1;
+  for (int i = 0; i < ntiles; i++) { tw = std::max(tw, tiles[i].xmax - tiles[i].xmin); th = std::max(th, tiles[i].ymax - tiles[i].ymin); }
+  return ((long)p->xrate * tw + 2 * mx) * ((long)p->yrate * th + 2 * my);
+}
+}  // namespace
+
+int fjgpu_time_table(const fjgpu_render_params *p, const fjgpu_tile *tiles, int32_t ntiles, double t0, double t1, double *times, int32_t cap) {
+  if (!p || (!tiles && ntiles > 0) || ntiles < 0 || p->xrate <= 0 || p->yrate <= 0 || !(p->xfwidth > 0) || !(p->yfwidth > 0) || (cap > 0 && !times)) return -1;
+  const long n = max_tile_samples(p, tiles, ntiles);
+  if (n > (1l << 30)) return -1;
+  uint32_t s[4] = {123456789u, 362436069u, 521288629u, 88675123u};       // XorShift, src/fj_random.cc:10-43
+  for (long i = 0; i < n && i < cap; i++) {
+    const uint32_t t = s[0] ^ (s[0] << 11);
+    s[0] = s[1]; s[1] = s[2]; s[2] = s[3];
+    s[3] = (s[3] ^ (s[3] >> 19)) ^ (t ^ (t >> 8));
+    const double rnd = (double)s[3] / 4294967295.0;                      // NextFloat01
+    // Fit(rnd, 0, 1, t0, t1), src/fj_numeric.h:84-93
+    times[i] = rnd <= 0 ? t0 : (rnd >= 1 ? t1 : t0 + (t1 - t0) * ((rnd - 0) / (1. - 0)));
+  }
+  return (int32_t)n;
+}
+
+int fjgpu_instance_motion_set(fjgpu_context *ctx, int32_t instance, int32_t ntimes, const double *fwd16, const double *inv16) {
+  if (!ctx || instance < 0 || instance >= (int32_t)ctx->inst.size() || ntimes < 0 || (ntimes > 0 && (!fwd16 || !inv16)))
+    return fail(ctx, FJGPU_ERR_INVALID, "bad instance motion table (call fjgpu_instances_set first)");
+  std::vector<double> &tab = ctx->inst_motion[instance];
+  tab.resize((size_t)ntimes * 24);
+  for (int32_t t = 0; t < ntimes; t++) { rows12(inv16 + 16 * (size_t)t, &tab[24 * (size_t)t]); rows12(fwd16 + 16 * (size_t)t, &tab[24 * (size_t)t + 12]); }
+  ctx->dirty = true;
+  return FJGPU_OK;
+}
+
+int fjgpu_camera_motion_set(fjgpu_context *ctx, int32_t ntimes, const double *fwd16) {
+  if (!ctx || ntimes < 0 || (ntimes > 0 && !fwd16)) return fail(ctx, FJGPU_ERR_INVALID, "bad camera motion table");
+  ctx->cam_motion.resize((size_t)ntimes * 12);
+  for (int32_t t = 0; t < ntimes; t++) rows12(fwd16 + 16 * (size_t)t, &ctx->cam_motion[12 * (size_t)t]);
+  ctx->cam_motion_dirty = true;
   return FJGPU_OK;
 }
 
@@ -1107,6 +1194,7 @@ int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent) {
   for (auto &b : ctx->d_group_nodesq) all.push_back(&b);
   for (auto &b : ctx->d_group_order) all.push_back(&b);
   for (auto &b : ctx->d_group_irec) all.push_back(&b);
+  for (auto &kv : ctx->d_inst_motion) all.push_back(&kv.second);
   uint64_t total = 0;
   for (DevBuf *b : all) {
     if (!b->h || !b->used) continue;

@@ -68,11 +68,12 @@ __device__ __forceinline__ void sample_uv(const DFrame &fr, const TileGrid &g, i
   }
   *u = su; *v = sv;
 }
-// Camera::GetRay, src/fj_camera.cc:79-110 (static camera: one matrix)
-__device__ __forceinline__ void camera_ray(const DCamera &c, double u, double v, RayD *ray) {
-  const D3 target = mat_point(c.fwd, mk(dmul(dsub(u, .5), c.uvx), dmul(dsub(v, .5), c.uvy), -1.));
-  const D3 eye = mat_point(c.fwd, mk(0., 0., 0.));
-  ray->d = normalize(target - eye); ray->o = eye; ray->tmin = c.znear; ray->tmax = c.zfar;
+// Camera::GetRay, src/fj_camera.cc:79-110; `tidx` = the sample's entry of the time table (its matrix when the camera moves)
+__device__ __forceinline__ void camera_ray(const DCamera &c, double u, double v, uint32_t tidx, RayD *ray) {
+  const double *fwd = c.motion ? c.motion + 12 * (size_t)tidx : c.fwd;
+  const D3 target = mat_point(fwd, mk(dmul(dsub(u, .5), c.uvx), dmul(dsub(v, .5), c.uvy), -1.));
+  const D3 eye = mat_point(fwd, mk(0., 0., 0.));
+  ray->d = normalize(target - eye); ray->o = eye; ray->tmin = c.znear; ray->tmax = c.zfar; ray->tidx = tidx;
 }
 
 // ------------------------------------------------------------------------------------------ lights
@@ -186,7 +187,7 @@ struct Shading {
       C3 lc; D3 Ln; double distance;
       if (!light_sample_reaches(lt, ls, P, Nf, &lc, &Ln, &distance)) return;
       if (TRACE && fr.cast_shadow) {
-        RayD sr; sr.o = P; sr.d = Ln; sr.tmin = .0001; sr.tmax = distance;
+        RayD sr; sr.o = P; sr.d = Ln; sr.tmin = .0001; sr.tmax = distance; sr.tidx = key.sample;
         Hit h;
         cnt.rays[RAY_SHADOW]++;
         if (trace_closest<T>(sc, sc.inst[shaded_object].shadow_target, sr, &h)) {
@@ -230,6 +231,7 @@ struct Shading {
     c.target = sc.inst[shaded_object].shadow_target; c.type = RAY_SHADOW_HEAD; c.filter_shader = slot;
     sink.put(at++, c);
     RayRec r; memset(&r, 0, sizeof r);
+    r.key = key.sample;                                            // shadow rays see the scene at the sample's time (SlShadowContext copies cxt)
     r.o[0] = P.x; r.o[1] = P.y; r.o[2] = P.z; r.tmin = .0001; r.slot = cur.slot;
     r.target = sc.inst[shaded_object].shadow_target; r.type = RAY_SHADOW; r.filter_shader = -1;
     const int nc = min(n, FJ_LIGHT_CACHE);
@@ -256,6 +258,7 @@ struct Shading {
   template <typename Sink>
   __device__ void shade(const RayRec &cur, const Hit &h, Sink &sink) {
     RayD ray; ray.o = mk(cur.o[0], cur.o[1], cur.o[2]); ray.d = mk(cur.d[0], cur.d[1], cur.d[2]); ray.tmin = cur.tmin; ray.tmax = cur.tmax;
+    ray.tidx = key.sample;                                         // key.sample = y * nsx + x = the sample's entry of the time table
     cnt.hits++; cnt.levels += sc.meshes[sc.inst[h.inst].mesh].log2_tris;
     C3 thr = c3(cur.thr[0], cur.thr[1], cur.thr[2]);
     if (cur.filter_shader >= 0) {    // pathtracing_shader.cc:247-251: C *= pow(transmit, t_hit) of the refracted child
@@ -270,7 +273,7 @@ struct Shading {
     float Os = 1.f;
     const int kind = slot < 0 ? 0 : sc.shaders[slot].kind;
     RayRec c;
-    c.o[0] = P.x; c.o[1] = P.y; c.o[2] = P.z; c.tmax = 1000.; c.slot = cur.slot; c.key = 0; c.pad2 = c.pad3 = 0; c.filter_shader = -1;
+    c.o[0] = P.x; c.o[1] = P.y; c.o[2] = P.z; c.tmax = 1000.; c.slot = cur.slot; c.key = key.sample; c.pad2 = c.pad3 = 0; c.filter_shader = -1;
     c.dd = cur.dd; c.rd = cur.rd; c.fd = cur.fd;
     if (kind == 0) {                                               // NO_SHADER_COLOR, fj_shading.cc:26,555-560
       sink.add(fmul(thr.r, .5f), thr.g, 0.f);
@@ -287,7 +290,7 @@ struct Shading {
       D3 Nf = sl_faceforward(ray.d, N);
       if (sh.bump_texture) {                                       // plastic_shader.cc:115-123
         float tu, tv; hit_uv(sc, h, &tu, &tv);
-        D3 dPdu, dPdv; hit_derivatives(sc, h, &dPdu, &dPdv);
+        D3 dPdu, dPdv; hit_derivatives(sc, h, key.sample, &dPdu, &dPdv);
         Nf = sl_bump_mapping(sc.textures[sh.bump_texture - 1], dPdu, dPdv, tu, tv, (double)sh.bump_amplitude, Nf);
       }
       float4 dm = make_float4(1.f, 1.f, 1.f, 1.f);                 // diffuse_map, plastic_shader.cc:148-156: Cs = diff * diffuse * diff_map
@@ -445,18 +448,18 @@ __global__ void __launch_bounds__(128) k_render_samples(const RenderArgs a) {
     Accum out; out.r = out.g = out.b = 0; out.a = 0.f; out.pad = 0;
     if (x < g.nsx && y < g.nsy) {
       double u, v; sample_uv(a.fr, g, x, y, &u, &v);
-      RayD ray; camera_ray(a.cam, u, v, &ray);
+      RayD ray; camera_ray(a.cam, u, v, (uint32_t)(y * g.nsx + x), &ray);
       PathKey key; key.seed = a.fr.seed; key.tile = (uint32_t)tile.id; key.sample = (uint32_t)(y * g.nsx + x);
       Shading<T> sh(a.sc, a.fr, key, cnt);
       StackSink sink; sink.stack = stack; sink.sp = 0; sink.acc = c3(0, 0, 0); sink.a = 0.f;
       RayRec cur;
       cur.o[0] = ray.o.x; cur.o[1] = ray.o.y; cur.o[2] = ray.o.z; cur.d[0] = ray.d.x; cur.d[1] = ray.d.y; cur.d[2] = ray.d.z;
       cur.tmin = ray.tmin; cur.tmax = ray.tmax; cur.thr[0] = cur.thr[1] = cur.thr[2] = 1.f; cur.slot = 0; cur.node = 1;
-      cur.target = a.fr.target_group; cur.type = RAY_CAMERA; cur.dd = cur.rd = cur.fd = 0; cur.filter_shader = -1; cur.key = 0; cur.pad2 = cur.pad3 = 0;
+      cur.target = a.fr.target_group; cur.type = RAY_CAMERA; cur.dd = cur.rd = cur.fd = 0; cur.filter_shader = -1; cur.key = key.sample; cur.pad2 = cur.pad3 = 0;
       sink.spawn(cur);
       while (sink.sp > 0) {
         cur = stack[--sink.sp];
-        RayD r; r.o = mk(cur.o[0], cur.o[1], cur.o[2]); r.d = mk(cur.d[0], cur.d[1], cur.d[2]); r.tmin = cur.tmin; r.tmax = cur.tmax;
+        RayD r; r.o = mk(cur.o[0], cur.o[1], cur.o[2]); r.d = mk(cur.d[0], cur.d[1], cur.d[2]); r.tmin = cur.tmin; r.tmax = cur.tmax; r.tidx = key.sample;
         cnt.rays[cur.type]++;
         Hit h;
         if (!trace_closest<T>(a.sc, cur.target, r, &h)) continue;
@@ -487,10 +490,10 @@ __global__ void __launch_bounds__(256) k_generate(const RenderArgs a) {
       a.accum[w] = z;
       if (x < g.nsx && y < g.nsy) {
         double u, v; sample_uv(a.fr, g, x, y, &u, &v);
-        RayD ray; camera_ray(a.cam, u, v, &ray);
+        RayD ray; camera_ray(a.cam, u, v, (uint32_t)(y * g.nsx + x), &ray);
         r.o[0] = ray.o.x; r.o[1] = ray.o.y; r.o[2] = ray.o.z; r.d[0] = ray.d.x; r.d[1] = ray.d.y; r.d[2] = ray.d.z;
         r.tmin = ray.tmin; r.tmax = ray.tmax; r.thr[0] = r.thr[1] = r.thr[2] = 1.f; r.slot = (uint32_t)w; r.node = 1;
-        r.target = a.fr.target_group; r.type = RAY_CAMERA; r.dd = r.rd = r.fd = 0; r.filter_shader = -1; r.key = 0; r.pad2 = r.pad3 = 0;
+        r.target = a.fr.target_group; r.type = RAY_CAMERA; r.dd = r.rd = r.fd = 0; r.filter_shader = -1; r.key = ray.tidx; r.pad2 = r.pad3 = 0;
         valid = true; nsamp++;
       }
     }
@@ -688,8 +691,9 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
           cur_inst = order[first];
           const DInstance &in = sc.inst[cur_inst];
           const RayRec &r = rays[ridx];
-          o = mat_point(in.inv, mk(r.o[0], r.o[1], r.o[2]));
-          d = mat_vector(in.inv, mk(r.d[0], r.d[1], r.d[2]));
+          const double *inv = inst_inv(in, r.key);
+          o = mat_point(inv, mk(r.o[0], r.o[1], r.o[2]));
+          d = mat_vector(inv, mk(r.d[0], r.d[1], r.d[2]));
           const DMesh &m = sc.meshes[in.mesh];
           make_box_ray32(o, d, m.bmag, br); oct = box_octant(br);
           br_world = false;

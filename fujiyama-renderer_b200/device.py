@@ -89,6 +89,17 @@ class Device:
         self._ck(self.lib.fjgpu_instances_set(self.ctx, st["ninstances"], st["instances"]))
         self._ck(self.lib.fjgpu_lights_set(self.ctx, st["nlights"], st["lights"]))
         self._ck(self.lib.fjgpu_camera_set(self.ctx, C.byref(st["camera"])))
+        # motion blur: matrices at every entry of the frame's time table (st["motion"]: index -> (fwd [n,16], inv [n,16]),
+        # index -1 = the camera); a scene without them resets what an earlier scene left in the context
+        motion = st.get("motion", {})
+        for i, (fwd, inv) in motion.items():
+            fwd, inv = np.ascontiguousarray(fwd, np.float64), np.ascontiguousarray(inv, np.float64)
+            if i < 0:
+                self._ck(self.lib.fjgpu_camera_motion_set(self.ctx, len(fwd), _dp(fwd)))
+            else:
+                self._ck(self.lib.fjgpu_instance_motion_set(self.ctx, i, len(fwd), _dp(fwd), _dp(inv)))
+        if -1 not in motion:
+            self._ck(self.lib.fjgpu_camera_motion_set(self.ctx, 0, None))
 
     def info(self):
         i = abi.SceneInfo()

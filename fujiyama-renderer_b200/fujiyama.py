@@ -63,6 +63,7 @@ def load_fjscene():
     lib.fjscene_instance_matrices.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.fjscene_mesh_normals.argtypes = [C.c_long, C.POINTER(C.c_double), C.c_int32]
     lib.fjscene_last_message.restype = C.c_char_p
+    lib.fjscene_lerp_transform.argtypes = [C.c_long, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.fjscene_make_transform.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 5
     _lib = lib
     return lib

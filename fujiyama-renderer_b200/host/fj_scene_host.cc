@@ -116,19 +116,36 @@ struct TimeSamples {                           // PropertySampleList, src/fj_pro
   std::vector<std::pair<double, std::array<double, 3>>> s;
   explicit TimeSamples(double v) { s.push_back({0., {v, v, v}}); }
   bool push(double x, double y, double z, double time) {          // PropPushSample, src/fj_property.cc:294-312
+    if (s.size() >= 8) return false;                               // checked before the equal-time replacement, as the reference does
     for (auto &e : s) if (e.first == time) { e.second = {x, y, z}; return true; }
-    if (s.size() >= 8) return false;
     s.push_back({time, {x, y, z}});
     std::stable_sort(s.begin(), s.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
     return true;
   }
   bool is_static() const { return s.size() == 1; }
+  // PropLerpSamples, src/fj_property.cc:317-345 (Fit src/fj_numeric.h:84-93, VEC4_LERP :18-23)
+  std::array<double, 3> at(double time) const {
+    if (s.front().first >= time || s.size() == 1) return s.front().second;
+    if (s.back().first <= time) return s.back().second;
+    for (size_t i = 0; i < s.size(); i++) {
+      if (s[i].first == time) return s[i].second;
+      if (s[i].first > time) {
+        const double t0 = s[i - 1].first, t1 = s[i].first;
+        const double t = time <= t0 ? 0. : (time >= t1 ? 1. : 0. + (1. - 0.) * ((time - t0) / (t1 - t0)));
+        const std::array<double, 3> &a = s[i - 1].second, &b = s[i].second;
+        return {(1 - t) * a[0] + t * b[0], (1 - t) * a[1] + t * b[1], (1 - t) * a[2] + t * b[2]};
+      }
+    }
+    return s.back().second;
+  }
 };
 struct Xform {
   int torder = SI_ORDER_SRT, rorder = SI_ORDER_ZXY;               // XfmInitTransformSampleList, fj_transform.cc:240-254
   TimeSamples T{0.}, R{0.}, S{1.};
   bool is_static() const { return T.is_static() && R.is_static() && S.is_static(); }
   M4 matrix() const { return compose(torder, rorder, T.s[0].second.data(), R.s[0].second.data(), S.s[0].second.data()); }
+  // XfmLerpTransformSample, src/fj_transform.cc:306-322: the transform the reference rebuilds for a ray of time `time`
+  M4 matrix_at(double time) const { const auto t = T.at(time), r = R.at(time), sc = S.at(time); return compose(torder, rorder, t.data(), r.data(), sc.data()); }
 };
 
 struct Plugin { std::string name; int kind; };   // kind: FJGPU_SHADER_* for shaders, 100 = StanfordPlyProcedure
@@ -454,9 +471,8 @@ Status flatten(Scene &sc, const Renderer &r, Flat *f) {
   if (r.sampler_type != SI_FIXED_GRID_SAMPLER) return failmsg("sampler_type 1 (adaptive grid sampler) has no device implementation");
   const Camera *cam = get(sc.cameras, r.camera, Type_Camera);
   if (!cam) return failmsg("renderer has no camera");
-  if (!cam->x.is_static()) return failmsg("time-sampled camera transforms (motion blur) are outside the device path");
   memset(&f->cam, 0, sizeof f->cam);
-  const M4 cm = cam->x.matrix();
+  const M4 cm = cam->x.matrix_at(0.);
   memcpy(f->cam.fwd, cm.e, sizeof cm.e); f->cam.fov = cam->fov; f->cam.znear = cam->znear; f->cam.zfar = cam->zfar;
 
   // create_implicit_groups, src/fj_scene_interface.cc:1077-1135: device group 0 = all objects, user groups follow
@@ -472,7 +488,6 @@ Status flatten(Scene &sc, const Renderer &r, Flat *f) {
   for (int i = 0; i < ni; i++) {
     const Instance &o = sc.instances[i]; fjgpu_instance &d = f->inst[i];
     memset(&d, 0, sizeof d);
-    if (!o.x.is_static()) return failmsg("time-sampled instance transforms (motion blur) are outside the device path");
     int t, mi; decode_id(o.mesh, &t, &mi); d.mesh_id = mi;
     for (int g = 0; g < FJGPU_MAX_SHADING_GROUPS; g++) d.shader_of_group[g] = -1;
     // ObjectInstance::AddShader / GetShader, src/fj_object_instance.cc:160-191: the mesh of this path has one
@@ -481,7 +496,7 @@ Status flatten(Scene &sc, const Renderer &r, Flat *f) {
     if (d.shader_of_group[0] < 0 && !o.shaders.empty()) { int st, si; decode_id(o.shaders.begin()->second, &st, &si); d.shader_of_group[0] = si; }
     const int gr = group_index_of(o.reflect), gf = group_index_of(o.refract), gs = group_index_of(o.shadow);
     d.reflect_target = gr < 0 ? 0 : gr + 1; d.refract_target = gf < 0 ? 0 : gf + 1; d.shadow_target = gs < 0 ? 0 : gs + 1;
-    const M4 m = o.x.matrix(), inv = inverse(m);
+    const M4 m = o.x.matrix_at(0.), inv = inverse(m);      // moving instances: replaced per ray by the motion table (render)
     memcpy(d.fwd, m.e, sizeof m.e); memcpy(d.inv, inv.e, sizeof inv.e);
   }
   const int nl = (int)sc.lights.size();
@@ -489,11 +504,10 @@ Status flatten(Scene &sc, const Renderer &r, Flat *f) {
   for (int i = 0; i < nl; i++) {
     const Light &l = sc.lights[i]; fjgpu_light &d = f->lights[i];
     memset(&d, 0, sizeof d);
-    if (!l.x.is_static()) return failmsg("time-sampled light transforms are outside the device path");
-    d.kind = l.type; d.sample_count = l.sample_count; d.double_sided = l.double_sided;
-    for (int k = 0; k < 3; k++) { d.color[k] = (float)l.color[k]; d.translate[k] = l.x.T.s[0].second[k]; }
+    d.kind = l.type;                                        // lights are sampled at time 0 (`const float time = 0`, fj_point_light.cc:27-29 and the other three) d.sample_count = l.sample_count; d.double_sided = l.double_sided;
+    for (int k = 0; k < 3; k++) { d.color[k] = (float)l.color[k]; d.translate[k] = l.x.T.at(0.)[k]; }
     d.intensity = (float)l.intensity;
-    const M4 m = l.x.matrix(); memcpy(d.fwd, m.e, sizeof m.e);
+    const M4 m = l.x.matrix_at(0.); memcpy(d.fwd, m.e, sizeof m.e);
     int et, ei;
     if (l.type == SI_DOME_LIGHT && l.envmap != SI_BADID && decode_id(l.envmap, &et, &ei) && et == Type_Texture && ei < (int)sc.textures.size()) {
       if (!dome_samples_from_envmap(sc.textures[ei], l.sample_count, &f->dome_dirs[i], &f->dome_cols[i])) return failmsg("environment map too small to sample");
@@ -562,10 +576,36 @@ Status render(Scene &sc, Renderer &r) {
   if (!rc) rc = fjgpu_camera_set(sc.gpu, &f.cam);
   if (rc) return failmsg(std::string("scene upload: ") + fjgpu_last_error(sc.gpu));
   sc.flat_inst = f.inst;
-  g_upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
   std::vector<fjgpu_tile> mine;
   for (size_t i = 0; i < f.tiles.size(); i++) if ((int)(i % (size_t)g_world) == g_rank) mine.push_back(f.tiles[i]);
+  {
+    // Motion blur: the frame's time table (one entry per sample of a tile: src/fj_fixed_grid_sampler.cc:42,72-77) and the
+    // transform XfmLerpTransformSample would rebuild for a ray of each entry's time, for every time-sampled instance / camera
+    const Camera *cam = get(sc.cameras, r.camera, Type_Camera);
+    bool moving = !cam->x.is_static();
+    for (const Instance &o : sc.instances) moving = moving || !o.x.is_static();
+    std::vector<double> times, fwd, inv;
+    if (moving && !mine.empty()) {
+      const int n = fjgpu_time_table(&f.params, mine.data(), (int32_t)mine.size(), r.time_range[0], r.time_range[1], nullptr, 0);
+      if (n <= 0) return failmsg("fjgpu_time_table failed");
+      times.resize(n); fwd.resize((size_t)n * 16); inv.resize((size_t)n * 16);
+      fjgpu_time_table(&f.params, mine.data(), (int32_t)mine.size(), r.time_range[0], r.time_range[1], times.data(), n);
+      for (size_t i = 0; i < sc.instances.size() && !rc; i++) {
+        const Xform &x = sc.instances[i].x;
+        if (x.is_static()) continue;
+        for (int k = 0; k < n; k++) { const M4 m = x.matrix_at(times[k]), mi = inverse(m); memcpy(&fwd[16 * (size_t)k], m.e, 128); memcpy(&inv[16 * (size_t)k], mi.e, 128); }
+        rc = fjgpu_instance_motion_set(sc.gpu, (int32_t)i, n, fwd.data(), inv.data());
+      }
+    }
+    if (!rc && moving && !mine.empty() && !cam->x.is_static()) {
+      for (size_t k = 0; k < times.size(); k++) { const M4 m = cam->x.matrix_at(times[k]); memcpy(&fwd[16 * k], m.e, 128); }
+      rc = fjgpu_camera_motion_set(sc.gpu, (int32_t)times.size(), fwd.data());
+    } else if (!rc) rc = fjgpu_camera_motion_set(sc.gpu, 0, nullptr);
+    if (rc) return failmsg(std::string("motion tables: ") + fjgpu_last_error(sc.gpu));
+  }
+  g_upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
   FrameInfo info; memset(&info, 0, sizeof info);
   info.frame_id = ++g_frame_id; info.worker_count = 1; info.tile_count = (int)mine.size(); info.xres = r.res[0]; info.yres = r.res[1];
   info.frame_region.min[0] = r.region[0]; info.frame_region.min[1] = r.region[1]; info.frame_region.max[0] = r.region[2]; info.frame_region.max[1] = r.region[3];
@@ -998,6 +1038,18 @@ int fjscene_mesh_normals(long mesh_id, double *N_out, int32_t nverts) {
   return 0;
 }
 const char *fjscene_last_message(void) { return last_message.c_str(); }
+int fjscene_lerp_transform(long id, double time, double *fwd16, double *inv16) {
+  const Xform *x = nullptr;
+  if (the_scene) {
+    if (const Instance *o = get(the_scene->instances, id, Type_ObjectInstance)) x = &o->x;
+    else if (const Camera *c = get(the_scene->cameras, id, Type_Camera)) x = &c->x;
+    else if (const Light *l = get(the_scene->lights, id, Type_Light)) x = &l->x;
+  }
+  if (!x) return -1;
+  const M4 m = x->matrix_at(time), mi = inverse(m);
+  memcpy(fwd16, m.e, 128); memcpy(inv16, mi.e, 128);
+  return 0;
+}
 void fjscene_make_transform(int transform_order, int rotate_order, const double *T, const double *R, const double *S, double *fwd16, double *inv16) {
   const M4 m = compose(transform_order, rotate_order, T, R, S), inv = inverse(m);
   memcpy(fwd16, m.e, 128); memcpy(inv16, inv.e, 128);

@@ -143,6 +143,7 @@ typedef struct fjgpu_camera {
 
 int fjgpu_camera_set(fjgpu_context *ctx, const fjgpu_camera *cam);
 
+
 /* ---- frame: Renderer properties (src/internal/fj_property_list_include.cc:451-474) ----- */
 enum { FJGPU_RNG_COUNTER = 0 };   /* Philox-4x32-10 keyed (seed, tile id, sample, path node): rank/thread independent */
 typedef struct fjgpu_render_params {
@@ -170,6 +171,25 @@ typedef struct fjgpu_tile {         /* Tile of src/fj_tiler.h; [xmin,xmax) x [ym
   int32_t id;                       /* global tile id in the frame's tile list (keys the RNG) */
   int32_t xmin, ymin, xmax, ymax;
 } fjgpu_tile;
+
+/* ---- motion blur: time-sampled transforms ---------------------------
+ * The reference draws ONE time per camera sample and every ray of that sample's tree inherits it (TraceContext::time,
+ * src/fj_renderer.cc:1073-1074, src/fj_shading.cc:226-264).  The k-th sample of EVERY tile (k = y * nsamples_x + x) takes
+ * the k-th draw of a freshly seeded XorShift mapped into sample_time_range (src/fj_fixed_grid_sampler.cc:42,72-77), so a
+ * frame only ever sees a finite table of times.  fjgpu_time_table returns that table; the caller evaluates its own
+ * XfmLerpTransformSample (src/fj_transform.cc:306-322 -- glibc sin/cos, which a device cannot return bit for bit) once per
+ * table entry and hands the matrices over; rays carry the table index.  An instance / camera without a table is static
+ * (fjgpu_instances_set / fjgpu_camera_set matrices).  Lights sample time 0 in the reference (fj_point_light.cc:27-29).
+ *
+ * fjgpu_time_table: writes min(cap, count) times and returns count = the largest per-tile sample count of `tiles`
+ * (< 0 on invalid arguments); call with cap = 0 to size the buffer.
+ * fjgpu_instance_motion_set: fwd16 / inv16 = ntimes x 16 doubles (Transform::matrix / inverse at each table time);
+ * ntimes = 0 makes the instance static again.  Call after fjgpu_instances_set (which clears every table).
+ * Rendering fails with FJGPU_ERR_INVALID if a table is shorter than the frame's time table. */
+int fjgpu_time_table(const fjgpu_render_params *params, const fjgpu_tile *tiles, int32_t ntiles,
+                     double time_start, double time_end, double *times, int32_t cap);
+int fjgpu_instance_motion_set(fjgpu_context *ctx, int32_t instance, int32_t ntimes, const double *fwd16, const double *inv16);
+int fjgpu_camera_motion_set(fjgpu_context *ctx, int32_t ntimes, const double *fwd16);
 
 typedef struct fjgpu_stats {
   uint64_t rays_camera, rays_shadow, rays_diffuse, rays_reflect, rays_refract;

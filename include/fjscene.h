@@ -144,6 +144,10 @@ void fjscene_set_device_blocks(void *d_tile_blocks, int tile_w_max, int tile_h_m
 int fjscene_instance_matrices(int32_t index, double *fwd16, double *inv16);
 int fjscene_mesh_normals(long mesh_id, double *N_out, int32_t nverts);
 const char *fjscene_last_message(void);
+/* XfmLerpTransformSample (src/fj_transform.cc:306-322) of an ObjectInstance / Camera / Light entry at `time`: the
+ * matrices SiRenderScene tabulates per entry of the frame's time table for fjgpu_instance_motion_set /
+ * fjgpu_camera_motion_set (motion blur); returns 0 or -1. */
+int fjscene_lerp_transform(long id, double time, double *fwd16, double *inv16);
 /* make_transform_matrix + MatInverse with the reference's arithmetic (src/fj_transform.cc:335-391,
  * src/fj_matrix.cc:119-207): the matrices SiRenderScene hands to fjgpu_instances_set. */
 void fjscene_make_transform(int transform_order, int rotate_order, const double *T, const double *R, const double *S,

@@ -26,6 +26,7 @@
 #include <cfloat>
 #include <limits>
 #include <vector>
+#include <array>
 #include <algorithm>
 #include <thread>
 #include <atomic>
@@ -431,8 +432,39 @@ bool grid_intersect(const Mesh &m, const Ray &ray, Isect *isect) {
   return hit;
 }
 
+// PropertySampleList / TransformSampleList (src/fj_property.h:117-137, src/fj_transform.h): up to 8 (x, y, z, time) samples
+// per channel, kept sorted by time.
+struct TimeSamples { std::vector<std::array<Real, 4>> v; };
+struct XfSamples { int torder, rorder; TimeSamples T, R, S; bool moving; XfSamples() : torder(0), rorder(0), moving(false) {} };
+inline Real Fit(Real x, Real src0, Real src1, Real dst0, Real dst1) {    // src/fj_numeric.h:84-93
+  if (x <= src0) return dst0;
+  if (x >= src1) return dst1;
+  return dst0 + (dst1 - dst0) * ((x - src0) / (src1 - src0));
+}
+// PropLerpSamples, src/fj_property.cc:317-345 (VEC4_LERP :18-23)
+void lerp_samples(const TimeSamples &l, Real time, Real out[3]) {
+  const size_t n = l.v.size();
+  if (l.v[0][3] >= time || n == 1) { for (int k = 0; k < 3; k++) out[k] = l.v[0][k]; return; }
+  if (l.v[n - 1][3] <= time) { for (int k = 0; k < 3; k++) out[k] = l.v[n - 1][k]; return; }
+  for (size_t i = 0; i < n; i++) {
+    if (l.v[i][3] == time) { for (int k = 0; k < 3; k++) out[k] = l.v[i][k]; return; }
+    if (l.v[i][3] > time) {
+      const Real t = Fit(time, l.v[i - 1][3], l.v[i][3], 0, 1);
+      for (int k = 0; k < 3; k++) out[k] = (1 - t) * l.v[i - 1][k] + t * l.v[i][k];
+      return;
+    }
+  }
+}
+// XfmLerpTransformSample, src/fj_transform.cc:306-322: lerp T, R, S at `time`, rebuild the matrix and its inverse
+void lerp_transform(const XfSamples &x, Real time, Mat *fwd, Mat *inv) {
+  Real T[3], R[3], S[3];
+  lerp_samples(x.T, time, T); lerp_samples(x.R, time, R); lerp_samples(x.S, time, S);
+  make_transform_matrix(x.torder, x.rorder, T[0], T[1], T[2], R[0], R[1], R[2], S[0], S[1], S[2], fwd);
+  MatInverse(inv, *fwd);
+}
+
 struct Instance { int mesh; Mat fwd, inv; Box bounds; int shader_of_group[FJGPU_MAX_SHADING_GROUPS];
-                  int reflect_target, refract_target, shadow_target; };
+                  int reflect_target, refract_target, shadow_target; XfSamples xs; };
 
 // BVHAccelerator over an ObjectSet, src/fj_bvh_accelerator.cc:39-56,79-107,253-334
 struct BvhNode { int left, right; Box bounds; int prim_id; BvhNode() : left(-1), right(-1), prim_id(-1) {} };
@@ -472,27 +504,31 @@ struct Scene {
   std::vector<Tex> textures;
   std::map<int, Mesh> meshes; std::vector<Instance> inst; std::vector<Group> groups;
   std::vector<Shader> shaders; std::vector<Light> lights; fjgpu_camera cam; bool built;
-  Scene() : built(false) { memset(&cam, 0, sizeof cam); }
+  XfSamples cam_xs; Real time_range[2];                 // Renderer::SetSampleTimeRange(0, 1), src/fj_renderer.cc:381
+  Scene() : built(false) { memset(&cam, 0, sizeof cam); time_range[0] = 0; time_range[1] = 1; }
 };
 
-// ObjectInstance::RayIntersect, src/fj_object_instance.cc:213-243 (static transform:
-// XfmLerpTransformSample rebuilds the same matrix for every ray)
-bool instance_ray_intersect(const Scene &s, int iid, const Ray &ray, Isect *isect) {
+// ObjectInstance::RayIntersect, src/fj_object_instance.cc:213-243 (with a single sample per channel
+// XfmLerpTransformSample rebuilds the same matrix for every ray; with several it is rebuilt at the ray's time)
+bool instance_ray_intersect(const Scene &s, int iid, const Ray &ray, Real time, Isect *isect) {
   const Instance &in = s.inst[iid];
+  Mat fwd_t, inv_t;
+  if (in.xs.moving) lerp_transform(in.xs, time, &fwd_t, &inv_t);
+  const Mat &fwd = in.xs.moving ? fwd_t : in.fwd, &inv = in.xs.moving ? inv_t : in.inv;
   Ray ro = ray;
-  ro.orig = MatPoint(in.inv, ray.orig);
-  ro.dir = MatVector(in.inv, ray.dir);
+  ro.orig = MatPoint(inv, ray.orig);
+  ro.dir = MatVector(inv, ray.dir);
   const Mesh &m = s.meshes.find(in.mesh)->second;
   if (!grid_intersect(m, ro, isect)) return false;
-  isect->P = MatPoint(in.fwd, isect->P);
-  isect->N = Normalize(MatVector(in.fwd, isect->N));
-  isect->dPdu = MatVector(in.fwd, isect->dPdu); isect->dPdv = MatVector(in.fwd, isect->dPdv);     // fj_object_instance.cc:237-238
+  isect->P = MatPoint(fwd, isect->P);
+  isect->N = Normalize(MatVector(fwd, isect->N));
+  isect->dPdu = MatVector(fwd, isect->dPdu); isect->dPdv = MatVector(fwd, isect->dPdv);     // fj_object_instance.cc:237-238
   isect->object = iid;
   return true;
 }
 
 // Accelerator::Intersect + intersect_bvh_loop, src/fj_accelerator.cc:94-113, src/fj_bvh_accelerator.cc:164-241
-bool group_intersect(const Scene &s, const Group &g, const Ray &ray, Isect *isect) {
+bool group_intersect(const Scene &s, const Group &g, const Ray &ray, Real time, Isect *isect) {
   Real t0, t1;
   if (!BoxRayIntersect(g.acc_bounds, ray.orig, ray.dir, ray.tmin, ray.tmax, &t0, &t1)) return false;
   if (g.root < 0) return false;
@@ -502,7 +538,7 @@ bool group_intersect(const Scene &s, const Group &g, const Ray &ray, Isect *isec
   for (;;) {
     const BvhNode &n = g.nodes[node];
     if (n.left == -1 && n.right == -1 && n.prim_id != -1) {
-      bool hittmp = instance_ray_intersect(s, g.inst[n.prim_id], ray, itmp);
+      bool hittmp = instance_ray_intersect(s, g.inst[n.prim_id], ray, time, itmp);
       if (!hittmp) itmp->t_hit = REAL_MAX;                      // PrimitiveSet::RayIntersect
       else if (!RayInRange(ray, itmp->t_hit)) { itmp->t_hit = REAL_MAX; hittmp = false; }
       if (hittmp && itmp->t_hit < imin->t_hit) { std::swap(imin, itmp); hit = hittmp; }
@@ -525,7 +561,8 @@ bool group_intersect(const Scene &s, const Group &g, const Ray &ray, Isect *isec
 enum { CXT_CAMERA_RAY = 0, CXT_SHADOW_RAY, CXT_DIFFUSE_RAY, CXT_REFLECT_RAY, CXT_REFRACT_RAY };
 struct Cxt { int ray_context, diffuse_depth, reflect_depth, refract_depth, max_diffuse_depth, max_reflect_depth,
              max_refract_depth, cast_shadow; float opacity_threshold; int trace_target;
-             uint64_t node; };   // node = path-tree code for the counter RNG (not in the reference)
+             uint64_t node;      // node = path-tree code for the counter RNG (not in the reference)
+             Real time; };       // TraceContext::time: every context is a copy of its parent's (src/fj_shading.cc:226-289)
 
 struct RenderState {
   const Scene *s; int rng_mode;      // 0 = counter (Philox), 1 = reference sequential XorShift (single thread)
@@ -821,7 +858,7 @@ int SlTrace(RenderState &rs, const Cxt &cxt, const V3 &o, const V3 &d, double tm
   rs.rays[cxt.ray_context]++;
   Ray ray; ray.orig = o; ray.dir = d; ray.tmin = tmin; ray.tmax = tmax;
   Isect isect;
-  const bool hit = group_intersect(*rs.s, rs.s->groups[cxt.trace_target], ray, &isect);
+  const bool hit = group_intersect(*rs.s, rs.s->groups[cxt.trace_target], ray, cxt.time, &isect);
   Col4 surf;
   if (hit) {
     SurfIn in; in.shaded_object = isect.object; in.P = isect.P; in.N = isect.N; in.Cd = Col(1, 1, 1); in.I = ray.dir;
@@ -849,19 +886,20 @@ int SlTrace(RenderState &rs, const Cxt &cxt, const V3 &o, const V3 &d, double tm
 }
 
 // ---------------------------------------------------------------- sampler / camera / filter
-struct Sample { Real u, v; Real data[4]; };
+struct Sample { Real u, v; Real data[4]; Real time; };
 
 inline void sampler_counts(const fjgpu_render_params &p, int m[2]) {   // count_samples_in_margin, fj_fixed_grid_sampler.cc:131-136
   m[0] = static_cast<int>(std::ceil(((p.xfwidth - 1) * p.xrate) * .5));
   m[1] = static_cast<int>(std::ceil(((p.yfwidth - 1) * p.yrate) * .5));
 }
 // FixedGridSampler::generate_samples, src/fj_fixed_grid_sampler.cc:33-84
-void generate_samples(const fjgpu_render_params &p, const fjgpu_tile &t, std::vector<Sample> &out, int ns[2]) {
+void generate_samples(const fjgpu_render_params &p, const fjgpu_tile &t, std::vector<Sample> &out, int ns[2], const Real *time_range = nullptr) {
   int m[2]; sampler_counts(p, m);
   ns[0] = p.xrate * (t.xmax - t.xmin) + 2 * m[0];
   ns[1] = p.yrate * (t.ymax - t.ymin) + 2 * m[1];
   out.resize((size_t)ns[0] * ns[1]);
   XorShift rng;
+  XorShift rng_time;                                                   // :42: a second, identically seeded stream
   const Real udelta = 1. / (p.xrate * p.xres), vdelta = 1. / (p.yrate * p.yres);
   const int xoffset = t.xmin * p.xrate - m[0], yoffset = t.ymin * p.yrate - m[1];
   Sample *s = out.data();
@@ -872,13 +910,17 @@ void generate_samples(const fjgpu_render_params &p, const fjgpu_tile &t, std::ve
       const Real uj = rng.NextFloat01() * p.jitter, vj = rng.NextFloat01() * p.jitter;
       s->u += udelta * (uj - .5); s->v += vdelta * (vj - .5);
     }
+    // :72-77 (IsSamplingTime() is always true: Renderer's constructor calls SetSampleTimeRange(0, 1))
+    if (time_range) { const Real rnd = rng_time.NextFloat01(); s->time = Fit(rnd, 0, 1, time_range[0], time_range[1]); }
+    else s->time = 0;
     s->data[0] = s->data[1] = s->data[2] = s->data[3] = 0;
     s++;
   }
 }
 // Camera::GetRay, src/fj_camera.cc:79-110
-void camera_ray(const fjgpu_camera &c, int xres, int yres, Real u, Real v, Ray *ray) {
+void camera_ray(const fjgpu_camera &c, int xres, int yres, Real u, Real v, Ray *ray, const XfSamples *xs = nullptr, Real time = 0) {
   Mat m; memcpy(m.e, c.fwd, sizeof m.e);
+  if (xs && xs->moving) { Mat inv; lerp_transform(*xs, time, &m, &inv); }      // :81-82
   const Real aspect = xres / (double)yres;
   const Real uvy = 2 * std::tan(Radian(c.fov / 2.)), uvx = uvy * aspect;
   const V3 target = MatPoint(m, V3((u - .5) * uvx, (v - .5) * uvy, -1));
@@ -891,14 +933,15 @@ inline Real eval_gaussian(Real xw, Real yw, Real x, Real y) {          // src/fj
 // render_tile: integrate_samples + reconstruct_image, src/fj_renderer.cc:1061-1121, :939-995
 void render_tile(RenderState &rs, const fjgpu_render_params &p, const fjgpu_tile &t, float *rgba,
                  double *dump_uv, float *dump_rgba) {
-  std::vector<Sample> smp; int ns[2]; generate_samples(p, t, smp, ns);
+  std::vector<Sample> smp; int ns[2]; generate_samples(p, t, smp, ns, rs.s->time_range);
   Cxt cxt; memset(&cxt, 0, sizeof cxt);                                // SlCameraContext + init_worker :896-905
   cxt.ray_context = CXT_CAMERA_RAY; cxt.max_diffuse_depth = p.max_diffuse_depth; cxt.max_reflect_depth = p.max_reflect_depth;
   cxt.max_refract_depth = p.max_refract_depth; cxt.cast_shadow = p.cast_shadow; cxt.opacity_threshold = .995f;
   cxt.trace_target = p.target_group; cxt.node = 1;
   rs.tile_id = (uint32_t)t.id;
   for (size_t i = 0; i < smp.size(); i++) {
-    Ray ray; camera_ray(rs.s->cam, p.xres, p.yres, smp[i].u, smp[i].v, &ray);
+    Ray ray; camera_ray(rs.s->cam, p.xres, p.yres, smp[i].u, smp[i].v, &ray, &rs.s->cam_xs, smp[i].time);
+    cxt.time = smp[i].time;                                            // src/fj_renderer.cc:1073-1074
     Col4 C; double t_hit = FLT_MAX;
     rs.sample_id = (uint32_t)i;
     const int hit = SlTrace(rs, cxt, ray.orig, ray.dir, ray.tmin, ray.tmax, &C, &t_hit);
@@ -1031,7 +1074,38 @@ int fjo_lights(fjo_scene *sc, int n, const fjgpu_light *l) {
   }
   return 0;
 }
-int fjo_camera(fjo_scene *sc, const fjgpu_camera *c) { sc->s.cam = *c; return 0; }
+int fjo_camera(fjo_scene *sc, const fjgpu_camera *c) { sc->s.cam = *c; sc->s.cam_xs = XfSamples(); return 0; }
+
+// Time-sampled transforms (SiSetSampleProperty3 on translate / rotate / scale): samples as (x, y, z, time) rows sorted by
+// time; target < 0 = the camera, else the instance index.  More than one sample in any channel makes the transform
+// time dependent.  fjo_time_range = Renderer sample_time_range.
+static void load_samples(TimeSamples *l, int n, const double *v4) { l->v.resize(n); for (int i = 0; i < n; i++) for (int k = 0; k < 4; k++) l->v[i][k] = v4[4 * i + k]; }
+int fjo_transform_samples(fjo_scene *sc, int target, int torder, int rorder, int nT, const double *T4, int nR, const double *R4, int nS, const double *S4) {
+  if (nT < 1 || nR < 1 || nS < 1 || nT > 8 || nR > 8 || nS > 8) return -1;
+  XfSamples xs; xs.torder = torder; xs.rorder = rorder;
+  load_samples(&xs.T, nT, T4); load_samples(&xs.R, nR, R4); load_samples(&xs.S, nS, S4);
+  xs.moving = nT > 1 || nR > 1 || nS > 1;
+  if (target < 0) sc->s.cam_xs = xs;
+  else { if (target >= (int)sc->s.inst.size()) return -1; sc->s.inst[target].xs = xs; }
+  sc->s.built = false; return 0;
+}
+// probe: XfmLerpTransformSample of a sample list at one time
+int fjo_lerp_transform(int torder, int rorder, int nT, const double *T4, int nR, const double *R4, int nS, const double *S4, double time, double *fwd16, double *inv16) {
+  if (nT < 1 || nR < 1 || nS < 1) return -1;
+  XfSamples xs; xs.torder = torder; xs.rorder = rorder;
+  load_samples(&xs.T, nT, T4); load_samples(&xs.R, nR, R4); load_samples(&xs.S, nS, S4);
+  Mat f, i; lerp_transform(xs, time, &f, &i);
+  memcpy(fwd16, f.e, sizeof f.e); memcpy(inv16, i.e, sizeof i.e);
+  return 0;
+}
+void fjo_time_range(fjo_scene *sc, double t0, double t1) { sc->s.time_range[0] = t0; sc->s.time_range[1] = t1; }
+// the frame's time table as fjgpu_time_table defines it: time of the k-th sample of a tile
+int fjo_sample_times(const fjgpu_render_params *p, const fjgpu_tile *t, double t0, double t1, double *times, int cap) {
+  const Real tr[2] = {t0, t1};
+  std::vector<Sample> s; int ns[2]; generate_samples(*p, *t, s, ns, tr);
+  for (size_t i = 0; i < s.size() && (int)i < cap; i++) times[i] = s[i].time;
+  return (int)s.size();
+}
 
 // compute_objects_bounds + build_accelerators, src/fj_scene_interface.cc:1137-1202
 int fjo_build(fjo_scene *sc) {
@@ -1040,6 +1114,24 @@ int fjo_build(fjo_scene *sc) {
   for (auto &in : s.inst) {                               // ObjectInstance::update_bounds :299-360 (single sample)
     auto it = s.meshes.find(in.mesh); if (it == s.meshes.end()) return -1;
     in.bounds = it->second.acc_bounds; MatTransformBounds(in.fwd, &in.bounds);
+    if (in.xs.moving) {                                   // merge_sampled_bounds :313-360, index quirk (rotate sample i of translate sample i) kept
+      Box ob = it->second.acc_bounds;
+      if (in.xs.R.v.size() > 1) {
+        const V3 dg = ob.max - ob.min; const Real half = .5 * Length(dg);
+        const V3 c = ob.Centroid(); ob.min = c; ob.max = c; ob.Expand(half);
+      }
+      Real S[3] = {0, 0, 0};
+      for (auto &e : in.xs.S.v) for (int k = 0; k < 3; k++) S[k] = std::max(S[k], std::fabs(e[k]));
+      Box merged; merged.ReverseInfinite();
+      for (size_t i = 0; i < in.xs.T.v.size(); i++) {
+        const Real *T = in.xs.T.v[i].data();
+        const Real zero[4] = {0, 0, 0, 0};
+        const Real *R = i < in.xs.R.v.size() ? in.xs.R.v[i].data() : zero;     // unused slots of the 8-entry array are zero
+        Mat m; make_transform_matrix(in.xs.torder, in.xs.rorder, T[0], T[1], T[2], R[0], R[1], R[2], S[0], S[1], S[2], &m);
+        Box sb = ob; MatTransformBounds(m, &sb); merged.AddBox(sb);
+      }
+      in.bounds = merged;
+    }
   }
   for (auto &g : s.groups) {
     Box b; b.ReverseInfinite();
@@ -1100,7 +1192,7 @@ int fjo_trace_closest(fjo_scene *sc, int group, int n, const double *o, const do
   if (!sc->s.built && fjo_build(sc)) return -1;
   for (int i = 0; i < n; i++) {
     Ray r; r.orig = V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.dir = V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]); r.tmin = tmin[i]; r.tmax = tmax[i];
-    Isect is; const bool hit = group_intersect(sc->s, sc->s.groups[group], r, &is);
+    Isect is; const bool hit = group_intersect(sc->s, sc->s.groups[group], r, 0, &is);
     out_t[i] = hit ? is.t_hit : REAL_MAX; out_u[i] = hit ? is.u : 0; out_v[i] = hit ? is.v : 0;
     out_prim[i] = hit ? is.prim_id : -1; out_inst[i] = hit ? is.object : -1;
   }

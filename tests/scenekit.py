@@ -76,6 +76,11 @@ def oracle():
     lib.fjo_dome_samples.argtypes = [P(a.Texture), i32, f64p, P(C.c_float)]
     lib.fjo_lights.argtypes = [vp, i32, P(a.Light)]
     lib.fjo_camera.argtypes = [vp, P(a.Camera)]
+    lib.fjo_transform_samples.argtypes = [vp, i32, i32, i32, i32, f64p, i32, f64p, i32, f64p]
+    lib.fjo_time_range.argtypes = [vp, C.c_double, C.c_double]
+    lib.fjo_time_range.restype = None
+    lib.fjo_sample_times.argtypes = [P(a.RenderParams), P(a.Tile), C.c_double, C.c_double, f64p, i32]
+    lib.fjo_lerp_transform.argtypes = [i32, i32, i32, f64p, i32, f64p, i32, f64p, C.c_double, f64p, f64p]
     lib.fjo_build.argtypes = [vp]
     lib.fjo_render.argtypes = [vp, P(a.RenderParams), P(a.Tile), i32, P(C.c_float), i32, i32, P(a.Stats)]
     lib.fjo_render_tile_samples.argtypes = [vp, P(a.RenderParams), P(a.Tile), i32, f64p, P(C.c_float)]
@@ -123,6 +128,41 @@ def make_transform(T=(0, 0, 0), R=(0, 0, 0), S=(1, 1, 1), torder=0, rorder=10):
     return fwd, inv
 
 
+def sample_rows(samples, default, initial=(0.0, 0.0, 0.0)):
+    """Time samples of one transform channel as sorted (x, y, z, time) rows.  A PropertySampleList starts with one sample
+    at time 0 (`initial`: zeros, ones for scale; PropInitSampleList / XfmInitTransformSampleList), PropPushSample keeps
+    the list sorted by time and a sample at an existing time replaces it (src/fj_property.cc:284-312): SetProperty3
+    (`default`, time 0) or the SetSampleProperty3 keys (`samples`) are applied on top of that."""
+    rows = {0.0: [float(initial[0]), float(initial[1]), float(initial[2]), 0.0]}
+    for r in (samples if samples else [tuple(default) + (0.0,)]):
+        rows[float(r[3])] = [float(r[0]), float(r[1]), float(r[2]), float(r[3])]
+    return np.ascontiguousarray([rows[t] for t in sorted(rows)], np.float64)
+
+
+def lerp_rows(rows, time):
+    """PropLerpSamples (src/fj_property.cc:317-345) on sample_rows output, in the reference's operation order."""
+    if rows[0][3] >= time or len(rows) == 1:
+        return rows[0][:3]
+    if rows[-1][3] <= time:
+        return rows[-1][:3]
+    for i in range(len(rows)):
+        if rows[i][3] == time:
+            return rows[i][:3]
+        if rows[i][3] > time:
+            a, b = rows[i - 1], rows[i]
+            t = (time - a[3]) / (b[3] - a[3])          # Fit(time, t0, t1, 0, 1) strictly inside the interval
+            return np.array([(1 - t) * a[k] + t * b[k] for k in range(3)])
+
+
+def motion_table(T4, R4, S4, times, torder=0, rorder=10):
+    """Transform::matrix / inverse at every time of the frame's time table (XfmLerpTransformSample per entry)."""
+    fwd = np.zeros((len(times), 16))
+    inv = np.zeros((len(times), 16))
+    for k, t in enumerate(times):
+        fwd[k], inv[k] = make_transform(lerp_rows(T4, t), lerp_rows(R4, t), lerp_rows(S4, t), torder, rorder)
+    return fwd, inv
+
+
 def make_tiles(xres, yres, tile=32, region=None):
     """Tiler::GenerateTiles (src/fj_tiler.cc:56-113): row-major tiles clipped to the region."""
     x0, y0, x1, y1 = region if region else (0, 0, xres, yres)
@@ -154,7 +194,9 @@ class SceneDesc:
         self.cam = dict(T=(0, 0, 4.5), R=(0, 0, 0), fov=30.0, znear=.01, zfar=1000.0)
         self.ren = dict(resolution=(320, 240), pixelsamples=(3, 3), filterwidth=(2, 2), sample_jitter=1.0,
                         max_diffuse_depth=3, max_reflect_depth=3, max_refract_depth=3, cast_shadow=1, tilesize=32,
-                        seed=1)
+                        seed=1, sample_time_range=(0.0, 1.0))
+        # motion blur: an instance dict / self.cam may hold "samples" = dict(T=[(x, y, z, time), ...], R=[...], S=[...]);
+        # channels listed there are set with SetSampleProperty3 instead of SetProperty3
 
     # ---- construction
     def mesh(self, name, P, idx, ply_path=None, uv=None):
@@ -168,8 +210,27 @@ class SceneDesc:
     def shader(self, name, kind, **props):
         self.shaders.append((name, kind, props))
 
-    def instance(self, name, mesh, shader, T=(0, 0, 0), R=(0, 0, 0), S=(1, 1, 1)):
-        self.instances.append(dict(name=name, mesh=mesh, shader=shader, T=T, R=R, S=S))
+    def instance(self, name, mesh, shader, T=(0, 0, 0), R=(0, 0, 0), S=(1, 1, 1), samples=None):
+        self.instances.append(dict(name=name, mesh=mesh, shader=shader, T=T, R=R, S=S, samples=samples))
+
+    @staticmethod
+    def channel_rows(d):
+        """(T4, R4, S4, moving) of an instance / camera dict."""
+        smp = d.get("samples") or {}
+        T4 = sample_rows(smp.get("T"), d["T"])
+        R4 = sample_rows(smp.get("R"), d["R"])
+        S4 = sample_rows(smp.get("S"), d.get("S", (1, 1, 1)), (1.0, 1.0, 1.0))
+        return T4, R4, S4, max(len(T4), len(R4), len(S4)) > 1
+
+    @staticmethod
+    def scn_transform(L, name, d, channels):
+        smp = d.get("samples") or {}
+        for key, prop in channels:
+            if smp.get(key):
+                for r in smp[key]:
+                    L.append("SetSampleProperty3 %s %s %r %r %r %r" % ((name, prop) + tuple(float(x) for x in r)))
+            else:
+                L.append("SetProperty3 %s %s %r %r %r" % ((name, prop) + tuple(float(x) for x in d[key])))
 
     def light(self, kind=0, T=(0, 0, 0), R=(0, 0, 0), S=(1, 1, 1), intensity=1.0, color=(1, 1, 1), sample_count=16,
               double_sided=0, environment_map=None):
@@ -189,8 +250,7 @@ class SceneDesc:
             L.append("OpenPlugin %s %s" % (SHADER_PLUGIN[k][0], os.path.join(plugin_dir, SHADER_PLUGIN[k][1])))
         L.append("OpenPlugin stanfordply_procedure %s" % os.path.join(plugin_dir, "StanfordPlyProcedure"))
         L.append("NewCamera cam1 PerspectiveCamera")
-        L.append("SetProperty3 cam1 translate %r %r %r" % tuple(float(x) for x in self.cam["T"]))
-        L.append("SetProperty3 cam1 rotate %r %r %r" % tuple(float(x) for x in self.cam["R"]))
+        self.scn_transform(L, "cam1", self.cam, (("T", "translate"), ("R", "rotate")))
         L.append("SetProperty1 cam1 fov %r" % float(self.cam["fov"]))
         env_assign = []
         for i, lt in enumerate(self.lights):
@@ -234,9 +294,7 @@ class SceneDesc:
         for ins in self.instances:
             n = ins["name"]
             L.append("NewObjectInstance %s %s" % (n, ins["mesh"]))
-            L.append("SetProperty3 %s translate %r %r %r" % ((n,) + tuple(float(x) for x in ins["T"])))
-            L.append("SetProperty3 %s rotate %r %r %r" % ((n,) + tuple(float(x) for x in ins["R"])))
-            L.append("SetProperty3 %s scale %r %r %r" % ((n,) + tuple(float(x) for x in ins["S"])))
+            self.scn_transform(L, n, ins, (("T", "translate"), ("R", "rotate"), ("S", "scale")))
             if ins["shader"] is not None:
                 L.append("AssignShader %s DEFAULT_SHADING_GROUP %s" % (n, ins["shader"]))
         r = self.ren
@@ -250,6 +308,7 @@ class SceneDesc:
               "SetProperty1 ren1 max_reflect_depth %d" % r["max_reflect_depth"],
               "SetProperty1 ren1 max_refract_depth %d" % r["max_refract_depth"],
               "SetProperty1 ren1 cast_shadow %d" % r["cast_shadow"],
+              "SetProperty2 ren1 sample_time_range %r %r" % tuple(float(x) for x in r["sample_time_range"]),
               "SetProperty1 ren1 use_max_thread 0", "SetProperty1 ren1 thread_count %d" % threads]
         if region:
             L.append("SetProperty4 ren1 render_region %d %d %d %d" % tuple(region))
@@ -340,8 +399,12 @@ class SceneDesc:
         out["shaders"] = shs
         out["nshaders"] = len(self.shaders)
         ins = (a.Instance * max(1, len(self.instances)))()
+        samples = {}          # instance index (-1 = camera) -> (T4, R4, S4) of the time-sampled transforms
         for i, d in enumerate(self.instances):
-            fwd, inv = make_transform(d["T"], d["R"], d["S"])
+            T4, R4, S4, moving = self.channel_rows(d)
+            if moving:
+                samples[i] = (T4, R4, S4)
+            fwd, inv = make_transform(lerp_rows(T4, 0.0), lerp_rows(R4, 0.0), lerp_rows(S4, 0.0))
             ins[i].mesh_id = mesh_ids[d["mesh"]]
             for g in range(a.FJGPU_MAX_SHADING_GROUPS):
                 ins[i].shader_of_group[g] = -1
@@ -385,7 +448,10 @@ class SceneDesc:
         out["lights"] = lts
         out["nlights"] = len(self.lights)
         cam = a.Camera()
-        fwd, _ = make_transform(self.cam["T"], self.cam["R"], (1, 1, 1))
+        T4, R4, S4, moving = self.channel_rows(self.cam)
+        if moving:
+            samples[-1] = (T4, R4, S4)
+        fwd, _ = make_transform(lerp_rows(T4, 0.0), lerp_rows(R4, 0.0), (1, 1, 1))
         cam.fwd[:] = list(fwd)
         cam.fov, cam.znear, cam.zfar = self.cam["fov"], self.cam["znear"], self.cam["zfar"]
         out["camera"] = cam
@@ -401,6 +467,20 @@ class SceneDesc:
         p.target_group = 0
         p.seed = r["seed"]
         out["params"] = p
+        out["samples"] = samples
+        out["time_range"] = tuple(float(x) for x in r["sample_time_range"])
+        if samples:
+            # the frame's time table (include/fjgpu.h, motion blur) and every moving transform evaluated at its entries
+            # with the reference's arithmetic: what a caller of the C-ABI hands to fjgpu_*_motion_set
+            from fujiyama_renderer_b200 import abi
+            lib = abi.load_fjgpu()
+            ta = self.tile_array(self.tiles())
+            n = lib.fjgpu_time_table(C.byref(p), ta, len(ta), out["time_range"][0], out["time_range"][1], None, 0)
+            assert n > 0
+            times = np.zeros(n)
+            assert lib.fjgpu_time_table(C.byref(p), ta, len(ta), out["time_range"][0], out["time_range"][1], dptr(times), n) == n
+            out["times"] = times
+            out["motion"] = {i: motion_table(T4, R4, S4, times) for i, (T4, R4, S4) in samples.items()}
         return out
 
     @staticmethod
@@ -426,6 +506,10 @@ def oracle_scene(st):
     o.fjo_shaders(sc, st["nshaders"], st["shaders"])
     o.fjo_lights(sc, st["nlights"], st["lights"])
     o.fjo_camera(sc, C.byref(st["camera"]))
+    for target, (T4, R4, S4) in st.get("samples", {}).items():
+        assert o.fjo_transform_samples(sc, target, 0, 10, len(T4), dptr(T4), len(R4), dptr(R4), len(S4), dptr(S4)) == 0
+    if "time_range" in st:
+        o.fjo_time_range(sc, st["time_range"][0], st["time_range"][1])
     o.fjo_build(sc)
     return sc
 

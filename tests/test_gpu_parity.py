@@ -140,7 +140,7 @@ def test_sample_positions_bit_exact(sk, device):
     dev.close()
 
 
-@pytest.mark.parametrize("name", ["plastic", "pt_branching", "grid_light", "sphere_light"])
+@pytest.mark.parametrize("name", ["plastic", "pt_branching", "grid_light", "sphere_light", "motion_blur"])
 def test_tile_samples_match_oracle(sk, device, name):
     """Per-sample radiance before the pixel filter (Sample::data), same counter RNG on both sides."""
     desc = golden_scenes.SCENES[name]()
@@ -178,7 +178,7 @@ def test_frame_matches_oracle(sk, device, name):
     assert stats.kernel_launches >= 2
 
 
-@pytest.mark.parametrize("name", ["plastic_4l", "multi", "pt_branching", "sphere_light"])
+@pytest.mark.parametrize("name", ["plastic_4l", "multi", "pt_branching", "sphere_light", "motion_blur"])
 @pytest.mark.parametrize("flags", [1, 2])
 def test_megakernel_cross_check(sk, device, name, flags):
     """The two independent device implementations (wavefront rounds over ray queues vs one sample per lane with a
@@ -397,7 +397,7 @@ def test_extend_variants_bit_exact(sk, device, scene, monkeypatch):
         dev.close()
 
 
-@pytest.mark.parametrize("name", ["multi", "pt_branching"])
+@pytest.mark.parametrize("name", ["multi", "pt_branching", "motion_blur"])
 def test_extend_variants_same_frame(sk, device, name, monkeypatch):
     """Whole frames (shadow rays, mirror bounces, branching path trees) are bit-identical whichever extend kernel traces
     them, and so are the ray counts."""

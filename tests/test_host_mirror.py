@@ -116,7 +116,7 @@ def test_python_shim_emits_reference_grammar(fuji):
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cube_c1", "plastic", "multi", "dome_light", "glass", "textured", "dome_envmap"])
+@pytest.mark.parametrize("name", ["cube_c1", "plastic", "multi", "dome_light", "glass", "textured", "dome_envmap", "motion_blur"])
 def test_scn_file_renders_like_the_reference(fuji, tmp_path, name):
     """The exact command text the reference's bin/scene was given for the golden .fb, fed to libfjscene."""
     from fujiyama_renderer_b200 import fbio
