@@ -3,7 +3,7 @@
 path-traced frame of a ~1M-triangle synthetic mesh, with the HBM roofline fraction of the dominant kernel
 and the reference's own CPU path timed on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload north_star|config2|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload north_star|north_star_motion|config2|small]
 
 A step = one frame.  Own arm: the scene is built through libfjscene (the host mirror of fj_scene_interface) from
 `.scn` text and rendered by libfjgpu (sm_100a).  `value` is timed with the scene resident in HBM and the frame left
@@ -32,6 +32,8 @@ WORKLOADS = {
     # name: (scene builder, kwargs, description)
     "north_star": ("pathtracing_blob", dict(n=707, res=(1920, 1080), rate=8, depth=3),
                    "S-blob(707)=999698 tris + emissive shell, pathtracing_shader depth 3, 1920x1080, 8x8=64spp, tile 32, filter 2"),
+    "north_star_motion": ("pathtracing_blob", dict(n=707, res=(1920, 1080), rate=8, depth=3, motion=True),
+                          "north-star scene with motion blur: the blob's rotate and the camera's translate carry two time samples (SURVEY.md 8f row 4)"),
     "config2": ("plastic_blob", dict(n=187, res=(1280, 720), rate=4),
                 "S-blob(187)=69938 tris, plastic_shader + 1 point light, 1280x720, 4x4=16spp"),
     "config3": ("pathtracing_blob", dict(n=1871, res=(1920, 1080), rate=8, depth=3),

@@ -65,6 +65,7 @@ struct fjgpu_context {
   std::map<int, std::vector<double>> inst_motion;     // instance -> ntimes x (inv[12], fwd[12])
   std::vector<double> cam_motion;                     // ntimes x fwd[12]
   std::map<int, DevBuf> d_inst_motion; DevBuf d_cam_motion; bool cam_motion_dirty = false;
+  std::map<int, bool> inst_motion_dirty;              // tables that changed since their last upload
 
   // device scene
   DevBuf d_meshes, d_inst, d_groups, d_shaders, d_lights;
@@ -166,7 +167,10 @@ int commit_scene(fjgpu_context *ctx) {
     { auto mit = ctx->inst_motion.find(i); if (mit != ctx->inst_motion.end() && !mit->second.empty()) motion = &mit->second; }
     if (motion) {
       DevBuf &mb = ctx->d_inst_motion[i];
-      if (int rc = dev_upload(ctx, mb, motion->data(), motion->size() * sizeof(double), true)) return rc;
+      if (!mb.p || ctx->inst_motion_dirty[i]) {
+        if (int rc = dev_upload(ctx, mb, motion->data(), motion->size() * sizeof(double), true)) return rc;
+        ctx->inst_motion_dirty[i] = false;
+      }
       d.motion = (const double *)mb.p;
     }
     for (int g = 0; g < FJGPU_MAX_SHADING_GROUPS; g++) {
@@ -933,8 +937,9 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
 
 int fjgpu_instances_set(fjgpu_context *ctx, int32_t n, const fjgpu_instance *inst) {
   if (!ctx || n < 0 || (n > 0 && !inst)) return fail(ctx, FJGPU_ERR_INVALID, "bad instance array");
+  if ((size_t)n == ctx->inst.size() && (n == 0 || memcmp(ctx->inst.data(), inst, (size_t)n * sizeof(fjgpu_instance)) == 0)) return FJGPU_OK;   // unchanged
   ctx->inst.assign(inst, inst + n); ctx->dirty = true;
-  ctx->inst_motion.clear();
+  for (auto it = ctx->inst_motion.begin(); it != ctx->inst_motion.end();) { if (it->first >= n) it = ctx->inst_motion.erase(it); else ++it; }
   return FJGPU_OK;
 }
 
@@ -968,17 +973,22 @@ int fjgpu_time_table(const fjgpu_render_params *p, const fjgpu_tile *tiles, int3
 int fjgpu_instance_motion_set(fjgpu_context *ctx, int32_t instance, int32_t ntimes, const double *fwd16, const double *inv16) {
   if (!ctx || instance < 0 || instance >= (int32_t)ctx->inst.size() || ntimes < 0 || (ntimes > 0 && (!fwd16 || !inv16)))
     return fail(ctx, FJGPU_ERR_INVALID, "bad instance motion table (call fjgpu_instances_set first)");
-  std::vector<double> &tab = ctx->inst_motion[instance];
-  tab.resize((size_t)ntimes * 24);
+  if (ntimes == 0 && ctx->inst_motion.find(instance) == ctx->inst_motion.end()) return FJGPU_OK;      // was static already
+  std::vector<double> tab((size_t)ntimes * 24);
   for (int32_t t = 0; t < ntimes; t++) { rows12(inv16 + 16 * (size_t)t, &tab[24 * (size_t)t]); rows12(fwd16 + 16 * (size_t)t, &tab[24 * (size_t)t + 12]); }
-  ctx->dirty = true;
+  std::vector<double> &cur = ctx->inst_motion[instance];
+  if (cur.size() == tab.size() && !tab.empty() && memcmp(cur.data(), tab.data(), tab.size() * sizeof(double)) == 0) return FJGPU_OK;   // unchanged
+  cur.swap(tab);
+  ctx->inst_motion_dirty[instance] = true; ctx->dirty = true;
   return FJGPU_OK;
 }
 
 int fjgpu_camera_motion_set(fjgpu_context *ctx, int32_t ntimes, const double *fwd16) {
   if (!ctx || ntimes < 0 || (ntimes > 0 && !fwd16)) return fail(ctx, FJGPU_ERR_INVALID, "bad camera motion table");
-  ctx->cam_motion.resize((size_t)ntimes * 12);
-  for (int32_t t = 0; t < ntimes; t++) rows12(fwd16 + 16 * (size_t)t, &ctx->cam_motion[12 * (size_t)t]);
+  std::vector<double> tab((size_t)ntimes * 12);
+  for (int32_t t = 0; t < ntimes; t++) rows12(fwd16 + 16 * (size_t)t, &tab[12 * (size_t)t]);
+  if (tab == ctx->cam_motion) return FJGPU_OK;
+  ctx->cam_motion.swap(tab);
   ctx->cam_motion_dirty = true;
   return FJGPU_OK;
 }

@@ -100,6 +100,9 @@ class Device:
                 self._ck(self.lib.fjgpu_instance_motion_set(self.ctx, i, len(fwd), _dp(fwd), _dp(inv)))
         if -1 not in motion:
             self._ck(self.lib.fjgpu_camera_motion_set(self.ctx, 0, None))
+        for i in range(st["ninstances"]):
+            if i not in motion:
+                self._ck(self.lib.fjgpu_instance_motion_set(self.ctx, i, 0, None, None))
 
     def info(self):
         i = abi.SceneInfo()

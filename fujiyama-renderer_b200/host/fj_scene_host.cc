@@ -174,6 +174,7 @@ struct Scene {
   std::vector<FrameBuf> framebuffers; std::vector<Renderer> renderers;
   fjgpu_context *gpu = nullptr; int gpu_device = -1;
   std::vector<fjgpu_instance> flat_inst;
+  std::map<int, std::vector<double>> motion_key;      // what the motion table held by libfjgpu for instance i (-1: camera) was built from
   ~Scene() { if (gpu) fjgpu_destroy(gpu); }
 };
 
@@ -504,7 +505,8 @@ Status flatten(Scene &sc, const Renderer &r, Flat *f) {
   for (int i = 0; i < nl; i++) {
     const Light &l = sc.lights[i]; fjgpu_light &d = f->lights[i];
     memset(&d, 0, sizeof d);
-    d.kind = l.type;                                        // lights are sampled at time 0 (`const float time = 0`, fj_point_light.cc:27-29 and the other three) d.sample_count = l.sample_count; d.double_sided = l.double_sided;
+    // lights are sampled at time 0 (`const float time = 0`, fj_point_light.cc:27-29 and the other three light types)
+    d.kind = l.type; d.sample_count = l.sample_count; d.double_sided = l.double_sided;
     for (int k = 0; k < 3; k++) { d.color[k] = (float)l.color[k]; d.translate[k] = l.x.T.at(0.)[k]; }
     d.intensity = (float)l.intensity;
     const M4 m = l.x.matrix_at(0.); memcpy(d.fwd, m.e, sizeof m.e);
@@ -547,10 +549,10 @@ Status render(Scene &sc, Renderer &r) {
   if (flatten(sc, r, &f) != SI_SUCCESS) return SI_FAIL;
   // preprocess_framebuffer, src/fj_renderer.cc:805-815: Resize clears the buffer
   fb->w = r.res[0]; fb->h = r.res[1]; fb->c = 4; fb->px.assign((size_t)fb->w * fb->h * 4, 0.f);
-  if (sc.gpu && sc.gpu_device != g_device) { fjgpu_destroy(sc.gpu); sc.gpu = nullptr; for (Mesh &m : sc.meshes) m.dirty = true; }
+  if (sc.gpu && sc.gpu_device != g_device) { fjgpu_destroy(sc.gpu); sc.gpu = nullptr; sc.motion_key.clear(); for (Mesh &m : sc.meshes) m.dirty = true; }
   if (!sc.gpu) {
     if (fjgpu_create(g_device, &sc.gpu) != FJGPU_OK) return failmsg(std::string("fjgpu_create: ") + fjgpu_last_error(nullptr));
-    sc.gpu_device = g_device;
+    sc.gpu_device = g_device; sc.motion_key.clear();
   }
   const auto t0 = std::chrono::steady_clock::now();
   printf("# Building Accelerators\n");                                  // src/fj_scene_interface.cc:1172-1201
@@ -586,22 +588,34 @@ Status render(Scene &sc, Renderer &r) {
     bool moving = !cam->x.is_static();
     for (const Instance &o : sc.instances) moving = moving || !o.x.is_static();
     std::vector<double> times, fwd, inv;
+    int n = 0;
     if (moving && !mine.empty()) {
-      const int n = fjgpu_time_table(&f.params, mine.data(), (int32_t)mine.size(), r.time_range[0], r.time_range[1], nullptr, 0);
+      n = fjgpu_time_table(&f.params, mine.data(), (int32_t)mine.size(), r.time_range[0], r.time_range[1], nullptr, 0);
       if (n <= 0) return failmsg("fjgpu_time_table failed");
-      times.resize(n); fwd.resize((size_t)n * 16); inv.resize((size_t)n * 16);
+      times.resize(n);
       fjgpu_time_table(&f.params, mine.data(), (int32_t)mine.size(), r.time_range[0], r.time_range[1], times.data(), n);
-      for (size_t i = 0; i < sc.instances.size() && !rc; i++) {
-        const Xform &x = sc.instances[i].x;
-        if (x.is_static()) continue;
-        for (int k = 0; k < n; k++) { const M4 m = x.matrix_at(times[k]), mi = inverse(m); memcpy(&fwd[16 * (size_t)k], m.e, 128); memcpy(&inv[16 * (size_t)k], mi.e, 128); }
-        rc = fjgpu_instance_motion_set(sc.gpu, (int32_t)i, n, fwd.data(), inv.data());
-      }
     }
-    if (!rc && moving && !mine.empty() && !cam->x.is_static()) {
-      for (size_t k = 0; k < times.size(); k++) { const M4 m = cam->x.matrix_at(times[k]); memcpy(&fwd[16 * k], m.e, 128); }
-      rc = fjgpu_camera_motion_set(sc.gpu, (int32_t)times.size(), fwd.data());
-    } else if (!rc) rc = fjgpu_camera_motion_set(sc.gpu, 0, nullptr);
+    // a table is rebuilt only when what it was built from changed: the time table (count, range) or the entry's samples
+    auto key_of = [&](const Xform &x) {
+      std::vector<double> k = {(double)n, r.time_range[0], r.time_range[1], (double)x.torder, (double)x.rorder};
+      for (const TimeSamples *ts : {&x.T, &x.R, &x.S}) { k.push_back((double)ts->s.size()); for (auto &e : ts->s) { k.push_back(e.first); k.insert(k.end(), e.second.begin(), e.second.end()); } }
+      return k;
+    };
+    for (int i = -1; i < (int)sc.instances.size() && !rc; i++) {                       // -1: the camera
+      const Xform &x = i < 0 ? cam->x : sc.instances[i].x;
+      if (x.is_static() || n == 0) {
+        rc = i < 0 ? fjgpu_camera_motion_set(sc.gpu, 0, nullptr) : fjgpu_instance_motion_set(sc.gpu, i, 0, nullptr, nullptr);
+        sc.motion_key.erase(i);
+        continue;
+      }
+      std::vector<double> key = key_of(x);
+      auto it = sc.motion_key.find(i);
+      if (it != sc.motion_key.end() && it->second == key) continue;
+      fwd.resize((size_t)n * 16); inv.resize((size_t)n * 16);
+      for (int k = 0; k < n; k++) { const M4 m = x.matrix_at(times[k]), mi = inverse(m); memcpy(&fwd[16 * (size_t)k], m.e, 128); memcpy(&inv[16 * (size_t)k], mi.e, 128); }
+      rc = i < 0 ? fjgpu_camera_motion_set(sc.gpu, n, fwd.data()) : fjgpu_instance_motion_set(sc.gpu, i, n, fwd.data(), inv.data());
+      if (!rc) sc.motion_key[i].swap(key);
+    }
     if (rc) return failmsg(std::string("motion tables: ") + fjgpu_last_error(sc.gpu));
   }
   g_upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

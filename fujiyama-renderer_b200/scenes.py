@@ -35,7 +35,7 @@ def ensure_ply(workdir, name, maker):
     return path
 
 
-def pathtracing_blob(workdir, plugin_dir, n=707, res=(1920, 1080), rate=8, depth=3, threads=1, shell_n=64):
+def pathtracing_blob(workdir, plugin_dir, n=707, res=(1920, 1080), rate=8, depth=3, threads=1, shell_n=64, motion=False):
     """North star: ~1M-triangle bumpy sphere (S-blob(707) = 999 698 triangles) with pathtracing_shader inside an
     emissive shell (the shader ignores lights; scenes/pathtracing.py:78-88 does the same),
     1920x1080, 8x8 = 64 spp, max_diffuse_depth 3.  Returns the set-up commands (no RenderScene)."""
@@ -49,6 +49,9 @@ def pathtracing_blob(workdir, plugin_dir, n=707, res=(1920, 1080), rate=8, depth
     L += _mesh_cmds("blob", blob) + _mesh_cmds("shell", shell)
     L += ["NewObjectInstance obj1 blob", "SetProperty3 obj1 rotate 20 30 0", "AssignShader obj1 DEFAULT_SHADING_GROUP sh1",
           "NewObjectInstance shell1 shell", "SetProperty3 shell1 scale 8 8 8", "AssignShader shell1 DEFAULT_SHADING_GROUP sh2"]
+    if motion:       # motion blur (scenes/transform_motion_blur.py): the blob spins 15 degrees and the camera dollies during the shutter
+        L += ["SetSampleProperty3 obj1 rotate 20 30 0 0", "SetSampleProperty3 obj1 rotate 20 45 0 1",
+              "SetSampleProperty3 cam1 translate 0 0 4.5 0", "SetSampleProperty3 cam1 translate 0.1 0 4.45 1"]
     L += _renderer_cmds(res, rate, depth, threads)
     return "\n".join(L) + "\n"
 

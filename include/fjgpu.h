@@ -184,7 +184,8 @@ typedef struct fjgpu_tile {         /* Tile of src/fj_tiler.h; [xmin,xmax) x [ym
  * fjgpu_time_table: writes min(cap, count) times and returns count = the largest per-tile sample count of `tiles`
  * (< 0 on invalid arguments); call with cap = 0 to size the buffer.
  * fjgpu_instance_motion_set: fwd16 / inv16 = ntimes x 16 doubles (Transform::matrix / inverse at each table time);
- * ntimes = 0 makes the instance static again.  Call after fjgpu_instances_set (which clears every table).
+ * ntimes = 0 makes the instance static again.  A table belongs to its instance index: it survives fjgpu_instances_set
+ * as long as the index exists, and handing over an unchanged table (or instance array) costs one comparison, no upload.
  * Rendering fails with FJGPU_ERR_INVALID if a table is shorter than the frame's time table. */
 int fjgpu_time_table(const fjgpu_render_params *params, const fjgpu_tile *tiles, int32_t ntiles,
                      double time_start, double time_end, double *times, int32_t cap);
