@@ -74,9 +74,11 @@ __device__ __forceinline__ bool tri_intersect_smem(const D3 &v0, const D3 &v1, c
 // Lane state word: what the node loop has to know about the exact half of the state.
 enum { XS_BLAS = 1, XS_WORLD = 2, XS_TRI64 = 4, XS_LEAF = 8, XS_FOUND = 16 };
 
-template <int MINB, bool STATS, bool QUANT>
+template <int MINB, bool STATS, bool QUANT, bool COOP = false>
 __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   __shared__ ExtShared S;
+  // COOP: (owner lane | triangle k << 5) of every (ray, triangle) pair of the warp's parked leaves, in owner order
+  __shared__ unsigned char pairmap[COOP ? FJ_XT / 32 : 1][COOP ? 256 : 1];
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x;
   const RayRec *rays = a.queue[a.cur];
@@ -218,8 +220,90 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
       }
     }
 
+    // ---- phase B1 (COOP): the warp's parked leaves hold W (ray, triangle) pairs on typically 10-12 lanes; instead of every
+    // owner looping over its own <= 8 triangles, the pairs are dealt out 32 at a time to ALL lanes (the FP64 ray of any lane
+    // is in shared memory), and each owner then folds the hits among its pairs into its best hit in triangle order — the
+    // same comparisons in the same order as the loop below, so the result is bit-identical.
+    if (COOP && __any_sync(FULL, st & XS_LEAF)) {
+      const int lane = tid & 31, wbase = tid & ~31;
+      int cnt = 0;
+      if (st & XS_LEAF) { cnt = ((~S.leaf[tid]) & 7) + 1; st &= ~XS_LEAF; }
+      int off = cnt;                                           // inclusive, then exclusive prefix sum of the pair counts
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) { const int up = __shfl_up_sync(FULL, off, dlt); if (lane >= dlt) off += up; }
+      const int total = __shfl_sync(FULL, off, 31);
+      off -= cnt;
+      unsigned char *pm = pairmap[tid >> 5];
+      for (int k = 0; k < cnt; k++) pm[off + k] = (unsigned char)(lane | (k << 5));
+      __syncwarp();
+      if (STATS) n_tris += (unsigned)total;
+      const double tmin = S.tmin[tid];
+      double best_t = S.best_t[tid]; bool found = (st & XS_FOUND) != 0;       // owner state (unused on lanes without a leaf)
+      for (int R = 0; R < total; R += 32) {
+        const int p = R + lane;
+        const bool want = p < total;
+        const unsigned e = want ? pm[p] : (unsigned)lane;
+        const int otid = wbase + (int)(e & 31u), k = (int)(e >> 5);
+        const unsigned ost = __shfl_sync(FULL, st, (int)(e & 31u));
+        bool hit = false; double t = 0, u = 0, v = 0; int prim = 0;
+        if (want) {
+          const int first = (~S.leaf[otid]) >> 3;
+          const void *tp_ = S.tri[otid];
+          D3 v0, v1, v2;
+          if (!(ost & XS_TRI64)) {
+            const unsigned ti = (unsigned)(first + k);
+            const char *tb = (const char *)tp_ + 48 * (size_t)ti;
+            const bool odd = ti & 1u;
+            const float4 s4 = __ldg((const float4 *)(tb + (odd ? 0 : 32)));
+            const F8 w8 = ldg256(tb + (odd ? 16 : 0));
+            const float4 p0 = odd ? s4 : w8.a, p1 = odd ? w8.a : w8.b, p2 = odd ? w8.b : s4;
+            v0 = mk(p0.x, p0.y, p0.z); v1 = mk(p1.x, p1.y, p1.z); v2 = mk(p2.x, p2.y, p2.z); prim = __float_as_int(p0.w);
+          } else {
+            const double *q = (const double *)tp_ + 10 * (size_t)(first + k);
+            v0 = mk(__ldg(q), __ldg(q + 1), __ldg(q + 2)); v1 = mk(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)); v2 = mk(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
+            prim = (int)__double_as_longlong(__ldg(q + 9));
+          }
+          hit = tri_intersect_smem(v0, v1, v2, S, otid, &t, &u, &v);
+        }
+        // owners fold the hits among their pairs of this round, lowest triangle first
+        const unsigned hm = __ballot_sync(FULL, hit);
+        const int lo = off - R, hi = off + cnt - R;             // this owner's pairs sit on lanes [lo, hi) of this round
+        unsigned mine = 0;
+        if (cnt > 0 && hi > 0 && lo < 32) {
+          const unsigned upto = hi >= 32 ? FULL : ((1u << hi) - 1u);
+          const unsigned from = lo <= 0 ? 0u : ((1u << lo) - 1u);
+          mine = hm & upto & ~from;
+        }
+        while (__any_sync(FULL, mine != 0u)) {
+          const int src = mine ? __ffs(mine) - 1 : lane;
+          const double ht = __shfl_sync(FULL, t, src), hu = __shfl_sync(FULL, u, src), hv = __shfl_sync(FULL, v, src);
+          const int hp = __shfl_sync(FULL, prim, src);
+          if (mine) {
+            mine &= mine - 1u;
+            if (tmin <= ht && ht <= best_t) {
+              bool better = !found || ht < best_t;
+              if (!better) {                       // exact tie in t: lower instance, then higher face id (read back from the record)
+                const HitRec *cur = a.hits + S.ridx[tid];
+                const int ci = S.cur_inst[tid], bi = cur->inst;
+                better = ci < bi || (ci == bi && hp > cur->prim);
+              }
+              if (better) {
+                found = true; best_t = ht; st |= XS_FOUND;
+                S.best_t[tid] = ht;
+                HitRec hr; hr.t = ht; hr.u = hu; hr.v = hv; hr.prim = hp; hr.inst = S.cur_inst[tid];
+                uint4 *dst = reinterpret_cast<uint4 *>(a.hits + S.ridx[tid]); const uint4 *srcp = reinterpret_cast<const uint4 *>(&hr);
+                dst[0] = srcp[0]; dst[1] = srcp[1];
+                tf = __double2float_ru(ht);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();                                            // pairmap is rewritten by the next leaf phase
+    }
+
     // ---- phase B1: parked triangle leaves, exact FP64 tests, one triangle per lane per iteration
-    if (__any_sync(FULL, st & XS_LEAF)) {
+    if (!COOP && __any_sync(FULL, st & XS_LEAF)) {
       int first = 0, cnt = 0;
       double tmin = 0, best_t = 0; bool found = false;
       const void *tp_ = nullptr;

@@ -479,17 +479,17 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
 
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
-template <int MINB, bool QUANT>
+template <int MINB, bool QUANT, bool COOP = false>
 void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   // shared-memory carveout: MINB CTAs x (static shared memory + 1 KB the driver reserves per CTA), the rest stays L1
   static bool configured = false;
   if (!configured) {
-    int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * (sizeof(fj::ExtShared) + 1024) / (228.0 * 1024)));
+    int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * (sizeof(fj::ExtShared) + (COOP ? 1024 : 0) + 1024) / (228.0 * 1024)));
     pct = env_int("FJGPU_CARVEOUT_PCT", pct);
-    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     configured = true;
   }
-  fj::k_extend2<MINB, true, QUANT><<<blocks, FJ_XT, 0, ctx->stream>>>(a);
+  fj::k_extend2<MINB, true, QUANT, COOP><<<blocks, FJ_XT, 0, ctx->stream>>>(a);
 }
 
 template <int MINB>
@@ -530,7 +530,11 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
     const int cap = std::max(1, grid / 4 * minb);      // `grid` is 4 CTAs per SM worth of work (or fewer for small probes)
     (void)sms;
     const bool quant = ctx->quant_ok && env_int("FJGPU_QUANT", 1) != 0;
-    if (quant) {
+    if (quant && env_int("FJGPU_COOP", 1) != 0) {       // warp-cooperative exact triangle tests (fj_extend.cuh, phase B1)
+      if (minb >= 8) launch_extend2<8, true, true>(ctx, a, cap);
+      else if (minb == 7) launch_extend2<7, true, true>(ctx, a, cap);
+      else launch_extend2<6, true, true>(ctx, a, cap);
+    } else if (quant) {
       if (minb >= 8) launch_extend2<8, true>(ctx, a, cap);
       else if (minb == 7) launch_extend2<7, true>(ctx, a, cap);
       else launch_extend2<6, true>(ctx, a, cap);

@@ -351,8 +351,10 @@ def soup(sk):
 EXTEND_VARIANTS = {
     "v1_registers": {"FJGPU_EXTEND": "1"},
     "v2_float_nodes": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "0"},
-    "v2_quantised_6": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_EXTEND_MINBLOCKS": "6"},
-    "v2_quantised_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
+    "v2_quantised_6": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "0", "FJGPU_EXTEND_MINBLOCKS": "6"},
+    "v2_quantised_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "0", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
+    "v2_cooperative_leaves": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "1"},
+    "v2_cooperative_leaves_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "1", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
     "v3_quad_per_ray": {"FJGPU_EXTEND": "3"},
     "v3_quad_per_ray_12": {"FJGPU_EXTEND": "3", "FJGPU_EXTEND_MINBLOCKS": "12", "FJGPU_REFILL": "32", "FJGPU_PHASE_A_MIN": "32"},
 }
@@ -383,7 +385,7 @@ def test_extend_variants_bit_exact(sk, device, scene, monkeypatch):
     dev.load_structs(st)
     try:
         for name, env in EXTEND_VARIANTS.items():
-            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN"):
+            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
@@ -404,7 +406,7 @@ def test_extend_variants_same_frame(sk, device, name, monkeypatch):
     desc = golden_scenes.SCENES[name]()
     frames = {}
     for vname, env in EXTEND_VARIANTS.items():
-        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN"):
+        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -448,13 +450,13 @@ def test_device_built_bvh_gives_the_same_hits_and_frames(sk, device, scene, monk
             assert same.mean() > 0.999
             assert np.array_equal(u[same], ru[same]) and np.array_equal(v[same], rv[same])
         for name, env in EXTEND_VARIANTS.items():
-            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN"):
+            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP"):
                 monkeypatch.delenv(k, raising=False)
             for k, v_ in env.items():
                 monkeypatch.setenv(k, v_)
             t, u, v, p, i = dev.trace_closest(0, o, d, tmin, tmax, 0)
             assert np.array_equal(i, ri) and np.array_equal(t, rt), name
-        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN"):
+        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP"):
             monkeypatch.delenv(k, raising=False)
         img_dev, stats_dev = dev.render(st["params"], desc.tiles())
     finally:
