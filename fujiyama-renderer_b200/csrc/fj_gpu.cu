@@ -506,7 +506,7 @@ void launch_extend3(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks, int
 }
 
 // The closest-hit kernel of one wavefront round.  FJGPU_EXTEND=1 selects the register-resident first version (kept as
-// a cross-check), 2 the shared-memory-state version, 3 (default) the quad-per-ray version; FJGPU_EXTEND_MINBLOCKS = resident CTAs per SM.
+// a cross-check), 2 (default) the shared-memory-state version, 3 the quad-per-ray experiment; FJGPU_EXTEND_MINBLOCKS = resident CTAs per SM.
 void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
   a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
   a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 16)));
