@@ -63,6 +63,13 @@ def load_fjscene():
     lib.fjscene_instance_matrices.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.fjscene_mesh_normals.argtypes = [C.c_long, C.POINTER(C.c_double), C.c_int32]
     lib.fjscene_last_message.restype = C.c_char_p
+    i32p_ = C.POINTER(C.c_int32)
+    lib.fjscene_flatten.argtypes = [C.c_long, i32p_, i32p_, i32p_, i32p_]
+    lib.fjscene_flat_instance.argtypes = [C.c_int32, C.POINTER(abi.Instance)]
+    lib.fjscene_flat_light.argtypes = [C.c_int32, C.POINTER(abi.Light)]
+    lib.fjscene_flat_shader.argtypes = [C.c_int32, C.POINTER(abi.Shader)]
+    lib.fjscene_flat_tile.argtypes = [C.c_int32, C.POINTER(abi.Tile)]
+    lib.fjscene_flat_frame.argtypes = [C.POINTER(abi.Camera), C.POINTER(abi.RenderParams)]
     lib.fjscene_lerp_transform.argtypes = [C.c_long, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.fjscene_make_transform.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 5
     _lib = lib

@@ -371,7 +371,8 @@ fjgpu_shader flatten_shader(const Scene &sc, const Shader &s) {
   o.kind = kind;
   auto P = [&](const char *n) { return s.props.find(n)->second; };
   { int tt, ti; if (s.texture != SI_BADID && decode_id(s.texture, &tt, &ti) && tt == Type_Texture && kind != FJGPU_SHADER_GLASS) o.texture = ti + 1; }
-  { int tt, ti; if (s.bump != SI_BADID && decode_id(s.bump, &tt, &ti) && tt == Type_Texture && kind == FJGPU_SHADER_PLASTIC) { o.bump_texture = ti + 1; o.bump_amplitude = (float)P("bump_amplitude")[0]; } }
+  { int tt, ti; if (s.bump != SI_BADID && decode_id(s.bump, &tt, &ti) && tt == Type_Texture && kind == FJGPU_SHADER_PLASTIC) o.bump_texture = ti + 1; }
+  if (kind == FJGPU_SHADER_PLASTIC) o.bump_amplitude = (float)P("bump_amplitude")[0];     // set_bump_amplitude, default 1 (used only with a bump_map)
   if (kind == FJGPU_SHADER_CONSTANT) {                                      // constant_shader.cc:96-107
     for (int k = 0; k < 3; k++) o.diffuse[k] = clamp0(P("diffuse")[k]);
   } else if (kind == FJGPU_SHADER_PLASTIC) {                                // plastic_shader.cc:183-273
@@ -1052,6 +1053,27 @@ int fjscene_mesh_normals(long mesh_id, double *N_out, int32_t nverts) {
   return 0;
 }
 const char *fjscene_last_message(void) { return last_message.c_str(); }
+// The flat scene description SiRenderScene would hand to libfjgpu for renderer `renderer_id`, without touching a device
+// (host-logic tests compare it with an independent flattening of the same scene).  Pointers inside the returned
+// structs (dome sample tables) stay valid until the next fjscene_flatten call.
+static Flat g_flat;
+int fjscene_flatten(long renderer_id, int32_t *ninst, int32_t *nlights, int32_t *nshaders, int32_t *ntiles) {
+  Renderer *r = the_scene ? get(the_scene->renderers, renderer_id, Type_Renderer) : nullptr;
+  if (!r) return -1;
+  g_flat = Flat();
+  if (flatten(*the_scene, *r, &g_flat) != SI_SUCCESS) return -1;
+  if (ninst) *ninst = (int32_t)g_flat.inst.size();
+  if (nlights) *nlights = (int32_t)g_flat.lights.size();
+  if (nshaders) *nshaders = (int32_t)g_flat.shaders.size();
+  if (ntiles) *ntiles = (int32_t)g_flat.tiles.size();
+  return 0;
+}
+int fjscene_flat_instance(int32_t i, fjgpu_instance *out) { if (i < 0 || i >= (int)g_flat.inst.size() || !out) return -1; *out = g_flat.inst[i]; return 0; }
+int fjscene_flat_light(int32_t i, fjgpu_light *out) { if (i < 0 || i >= (int)g_flat.lights.size() || !out) return -1; *out = g_flat.lights[i]; return 0; }
+int fjscene_flat_shader(int32_t i, fjgpu_shader *out) { if (i < 0 || i >= (int)g_flat.shaders.size() || !out) return -1; *out = g_flat.shaders[i]; return 0; }
+int fjscene_flat_tile(int32_t i, fjgpu_tile *out) { if (i < 0 || i >= (int)g_flat.tiles.size() || !out) return -1; *out = g_flat.tiles[i]; return 0; }
+int fjscene_flat_frame(fjgpu_camera *cam, fjgpu_render_params *params) { if (cam) *cam = g_flat.cam; if (params) *params = g_flat.params; return 0; }
+
 int fjscene_lerp_transform(long id, double time, double *fwd16, double *inv16) {
   const Xform *x = nullptr;
   if (the_scene) {

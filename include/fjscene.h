@@ -144,6 +144,15 @@ void fjscene_set_device_blocks(void *d_tile_blocks, int tile_w_max, int tile_h_m
 int fjscene_instance_matrices(int32_t index, double *fwd16, double *inv16);
 int fjscene_mesh_normals(long mesh_id, double *N_out, int32_t nverts);
 const char *fjscene_last_message(void);
+/* The flat scene description SiRenderScene would hand to libfjgpu for a renderer (instances, lights, shaders, camera,
+ * frame parameters, tiles), built without touching a device: host-logic tests compare it with an independent
+ * flattening.  Pointers inside the returned structs stay valid until the next fjscene_flatten.  0 or -1. */
+int fjscene_flatten(long renderer_id, int32_t *ninst, int32_t *nlights, int32_t *nshaders, int32_t *ntiles);
+int fjscene_flat_instance(int32_t i, fjgpu_instance *out);
+int fjscene_flat_light(int32_t i, fjgpu_light *out);
+int fjscene_flat_shader(int32_t i, fjgpu_shader *out);
+int fjscene_flat_tile(int32_t i, fjgpu_tile *out);
+int fjscene_flat_frame(fjgpu_camera *cam, fjgpu_render_params *params);
 /* XfmLerpTransformSample (src/fj_transform.cc:306-322) of an ObjectInstance / Camera / Light entry at `time`: the
  * matrices SiRenderScene tabulates per entry of the frame's time table for fjgpu_instance_motion_set /
  * fjgpu_camera_motion_set (motion blur); returns 0 or -1. */

@@ -114,6 +114,58 @@ def test_python_shim_emits_reference_grammar(fuji):
         si.NewMesh("a", "b")
 
 
+@pytest.mark.parametrize("name", list(golden_scenes.SCENES))
+def test_flattened_scene_matches_the_test_kits(fuji, tmp_path, name):
+    """What SiRenderScene would hand to libfjgpu (fjscene_flatten, no device involved) against the test kit's independent
+    flattening of the same scene description (SceneDesc.to_structs, which feeds the oracle): instances, shaders, lights
+    incl. the dome sample tables, camera, frame parameters and tiles, field by field."""
+    abi = sk.abi
+    desc = golden_scenes.SCENES[name]()
+    st = desc.to_structs()
+    scn = desc.to_scn(str(tmp_path), None, plugin_dir="/x")
+    scn = "\n".join(l for l in scn.split("\n") if not l.startswith(("RenderScene", "SaveFrameBuffer"))) + "\n"
+    with fuji.Session() as s:
+        s.run(scn)
+        lib = s.lib
+        n = [C.c_int32() for _ in range(4)]
+        assert lib.fjscene_flatten(C.c_long(s.id("ren1")), *[C.byref(x) for x in n]) == 0
+        ninst, nlights, nshaders, ntiles = (x.value for x in n)
+        assert (ninst, nlights, nshaders) == (st["ninstances"], st["nlights"], st["nshaders"])
+        for i in range(ninst):
+            o, r = abi.Instance(), st["instances"][i]
+            assert lib.fjscene_flat_instance(i, C.byref(o)) == 0
+            assert o.mesh_id == r.mesh_id and o.shader_of_group[0] == r.shader_of_group[0]
+            assert (o.reflect_target, o.refract_target, o.shadow_target) == (r.reflect_target, r.refract_target, r.shadow_target)
+            assert list(o.fwd) == list(r.fwd) and list(o.inv) == list(r.inv)
+        for i in range(nshaders):
+            o, r = abi.Shader(), st["shaders"][i]
+            assert lib.fjscene_flat_shader(i, C.byref(o)) == 0
+            assert bytes(o) == bytes(r), (name, i)
+        for i in range(nlights):
+            o, r = abi.Light(), st["lights"][i]
+            assert lib.fjscene_flat_light(i, C.byref(o)) == 0
+            assert (o.kind, o.sample_count, o.double_sided, o.dome_sample_count) == (r.kind, r.sample_count, r.double_sided, r.dome_sample_count)
+            assert list(o.color) == list(r.color) and o.intensity == r.intensity
+            assert list(o.translate) == list(r.translate) and list(o.fwd) == list(r.fwd)
+            k = o.dome_sample_count
+            if k:
+                assert [o.dome_dirs[j] for j in range(3 * k)] == [r.dome_dirs[j] for j in range(3 * k)]
+                assert [o.dome_colors[j] for j in range(3 * k)] == [r.dome_colors[j] for j in range(3 * k)]
+        cam, p = abi.Camera(), abi.RenderParams()
+        assert lib.fjscene_flat_frame(C.byref(cam), C.byref(p)) == 0
+        rc, rp = st["camera"], st["params"]
+        assert list(cam.fwd) == list(rc.fwd) and (cam.fov, cam.znear, cam.zfar) == (rc.fov, rc.znear, rc.zfar)
+        for f in ("xres", "yres", "xrate", "yrate", "xfwidth", "yfwidth", "jitter", "max_diffuse_depth", "max_reflect_depth",
+                  "max_refract_depth", "cast_shadow", "target_group"):
+            assert getattr(p, f) == getattr(rp, f), f
+        tiles = desc.tiles()
+        assert ntiles == len(tiles)
+        for i, t in enumerate(tiles):
+            o = abi.Tile()
+            assert lib.fjscene_flat_tile(i, C.byref(o)) == 0
+            assert (o.id, o.xmin, o.ymin, o.xmax, o.ymax) == tuple(t)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cube_c1", "plastic", "multi", "dome_light", "glass", "textured", "dome_envmap", "motion_blur"])
