@@ -67,7 +67,7 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id,
  * fwd/inv are the row-major 4x4 matrix and inverse the reference rebuilds per ray in
  * XfmLerpTransformSample (src/fj_transform.cc:306-322); the host computes them once with
  * the reference's own arithmetic (make_transform_matrix + MatInverse) for single-sample
- * (static) transforms.  Motion-blurred instances are FJGPU_ERR_UNSUPPORTED. */
+ * (static) transforms.  Time-sampled transforms (motion blur): fjgpu_instance_motion_set below. */
 #define FJGPU_MAX_SHADING_GROUPS 8
 typedef struct fjgpu_instance {
   int32_t mesh_id;
@@ -136,7 +136,7 @@ int fjgpu_lights_set(fjgpu_context *ctx, int32_t n, const fjgpu_light *lights);
 
 /* ---- camera: Camera::GetRay, src/fj_camera.cc:79-110 ----------------------------------- */
 typedef struct fjgpu_camera {
-  double fwd[16];           /* camera transform matrix (static camera) */
+  double fwd[16];           /* camera transform matrix (a moving camera adds fjgpu_camera_motion_set) */
   double fov;               /* degrees, default 30 */
   double znear, zfar;       /* ray [tmin,tmax], defaults .01 / 1000 */
 } fjgpu_camera;
