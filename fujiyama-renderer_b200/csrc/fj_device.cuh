@@ -352,7 +352,8 @@ __device__ __forceinline__ D3 sl_refract(const D3 &I, const D3 &N, double ior) {
 }
 
 enum { RAY_CAMERA = 0, RAY_SHADOW = 1, RAY_DIFFUSE = 2, RAY_REFLECT = 3, RAY_REFRACT = 4,      // enum RayContext, fj_shading.h:18-24
-       RAY_SHADOW_HEAD = 5 };   // not a ray: the header record of a block of shadow rays in the wavefront's queue (fj_kernels.cuh)
+       RAY_SHADOW_HEAD = 5,     // not a ray: the header record of a block of shadow rays in the wavefront's queue (fj_kernels.cuh)
+       RAY_DEAD = 6 };          // not a ray: filler of a queue chunk a warp reserved and did not use up (QueueSink, fj_kernels.cuh)
 
 // One ray of the wavefront: an entry of the ray queues in HBM (and of the megakernel's per-path DFS stack).
 // `thr` is the throughput that multiplies whatever the ray returns — the reference multiplies after the recursive

@@ -636,7 +636,14 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
       for (;;) {      // retried with a larger queue only if a branching ray tree overflowed the optimistic capacity
         const double want = (double)nb * pl.wstride * factor;
         if (want > 4.0e9) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray tree too wide for one tile's ray queue");
-        const size_t capacity = (size_t)want;
+        // chunked slot reservation (fj_kernels.cuh, QueueSink): every k_shade warp may leave up to FJ_QCHUNK + FJ_QRESERVE
+        // reserved slots as fillers, on top of the records the ray tree can produce
+        const bool chunked = !has_plastic && env_int("FJGPU_QUEUE_CHUNK", 1) != 0;
+        const int shade_smb = env_int("FJGPU_SHADE_MINBLOCKS", 5), shade_per = env_int("FJGPU_SHADE_CTAS", 2);
+        const size_t shade_warps = (size_t)ctx->sm_count * (shade_smb >= 8 ? 8 : (shade_smb >= 6 ? 6 : 5)) * shade_per * 4;
+        const size_t capacity = (size_t)want + (chunked ? shade_warps * (FJ_QCHUNK + FJ_QRESERVE) : 0);
+        if (capacity > 4000000000ull) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray tree too wide for one tile's ray queue");
+        a.chunked = chunked ? 1 : 0;
         // the two ray queues and the hit records live in ONE allocation at fixed relative offsets, so that the streams k_shade
         // reads and writes side by side keep the same relative placement whatever the scene allocated before them
         const size_t pad = (size_t)env_int("FJGPU_ARENA_PAD_KB", 0) << 10;

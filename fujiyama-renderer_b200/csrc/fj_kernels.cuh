@@ -399,6 +399,7 @@ struct RenderArgs {
   RayRec *queue[2]; HitRec *hits; QueueCtl *ctl; uint32_t capacity; int cur;     // wavefront
   int refill, phase_a_min, park;          // k_extend scheduling: refill / phase-A thresholds (lanes), speculative leaf parking
   int prefetch;                           // k_extend2: 1 = prefetch the new stack top into L1, 2 = into L2, 0 = off
+  int chunked;                            // k_shade without plastic shaders: warps reserve queue slots in chunks (QueueSink)
   // ray sorting between bounces: counting sort of the next queue by (direction octant | origin cell)
   unsigned int *hist;                     // sort_bins + 1 counters (null = no sorting)
   unsigned int *perm;                     // order in which k_extend walks queue[cur] (null = queue order)
@@ -712,9 +713,20 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ wavefront: shade
+// Chunked slot reservation (RenderArgs::chunked): instead of one atomic on the queue counter per spawn, a warp takes
+// FJ_QCHUNK slots at a time and hands them out through a counter in shared memory.  The warp's local positions [0, alloc)
+// map to base[(p / FJ_QCHUNK) & 1] + p % FJ_QCHUNK; k_shade tops the reservation up at the head of every iteration so that
+// FJ_QRESERVE slots (32 lanes x at most 4 children) are free, which keeps at most two chunks live.  What a warp has not
+// used when it leaves the kernel is filled with RAY_DEAD records (tmin > tmax: k_extend retires them at the root, k_shade
+// skips them) — the queue stays one dense range [0, count).
+#define FJ_QCHUNK 256u
+#define FJ_QRESERVE 128u
+struct WarpChunks { unsigned used, alloc, base[2]; };
+
 struct QueueSink {
   const RenderArgs &a; RayRec *next; int lane;
   long long r, g, b; bool has_alpha; float av;
+  WarpChunks *wc;                         // null: one atomic on the queue counter per spawn
   __device__ __forceinline__ void add(float x, float y, float z) { r += to_fix(x); g += to_fix(y); b += to_fix(z); }
   __device__ __forceinline__ void alpha(float v) { has_alpha = true; av = v; }
   // writes record `c` into slot i of the next queue (and files it under its sort key when rays are sorted between bounces)
@@ -740,6 +752,12 @@ struct QueueSink {
     const unsigned m = __activemask();
     const int leader = __ffs(m) - 1;
     unsigned base = 0;
+    if (wc) {
+      if (lane == leader) base = atomicAdd(&wc->used, (unsigned)__popc(m));
+      const unsigned p = __shfl_sync(m, base, leader) + __popc(m & ((1u << lane) - 1));
+      put(wc->base[(p / FJ_QCHUNK) & 1u] + (p % FJ_QCHUNK), c);
+      return;
+    }
     if (lane == leader) base = atomicAdd(&a.ctl->count[a.cur ^ 1], (unsigned)__popc(m));
     base = __shfl_sync(m, base, leader);
     put(base + __popc(m & ((1u << lane) - 1)), c);
@@ -816,16 +834,29 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->head = 0;                  // the next k_extend starts at the queue head
   const RayRec *rays = a.queue[a.cur];
   ShadeCounters cnt; memset(&cnt, 0, sizeof cnt);
-  // PLASTIC: whole 32-record groups per warp (the gather below is warp-synchronous); otherwise one record per thread
-  const unsigned start = PLASTIC ? ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u) : (blockIdx.x * blockDim.x + threadIdx.x);
+  __shared__ WarpChunks chunks[4];
+  WarpChunks *wc = (!PLASTIC && a.chunked) ? &chunks[threadIdx.x >> 5] : nullptr;
+  if (wc && lane == 0) { wc->used = wc->alloc = 0; wc->base[0] = wc->base[1] = 0; }
+  __syncwarp();
+  // every warp walks whole 32-record groups (the loop bound is the same for its 32 lanes: the PLASTIC gather and the chunk
+  // top-up below are warp-synchronous)
+  const unsigned start = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
   for (unsigned i0 = start; i0 < count; i0 += gridDim.x * blockDim.x) {
-    const unsigned i = PLASTIC ? i0 + lane : i0;
+    const unsigned i = i0 + lane;
     const bool valid = i < count;
+    if (wc) {                               // top the warp's slot reservation up to FJ_QRESERVE free slots
+      if (lane == 0 && wc->alloc - wc->used < FJ_QRESERVE) {
+        wc->base[(wc->alloc / FJ_QCHUNK) & 1u] = atomicAdd(&a.ctl->count[a.cur ^ 1], FJ_QCHUNK);
+        wc->alloc += FJ_QCHUNK;
+      }
+      __syncwarp();
+    }
     RayRec cur; HitRec hr; hr.inst = -1;
     if constexpr (PLASTIC) { cur.type = 255; cur.node = 0; cur.pad2 = 0; cur.thr[0] = cur.thr[1] = cur.thr[2] = 0.f; }
     if (valid) {
       load_ray_cs(&cur, rays + i);
-      if (!PLASTIC || cur.type != RAY_SHADOW_HEAD) { load_hit_cs(&hr, a.hits + i); cnt.rays[cur.type]++; }
+      if (!PLASTIC && cur.type == RAY_DEAD) { /* filler of a chunk: nothing was traced */ }
+      else if (!PLASTIC || cur.type != RAY_SHADOW_HEAD) { load_hit_cs(&hr, a.hits + i); cnt.rays[cur.type]++; }
     }
     if constexpr (PLASTIC) {
       const bool is_head = cur.type == RAY_SHADOW_HEAD, is_shadow = cur.type == RAY_SHADOW;
@@ -872,7 +903,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
     slot_decode(a.fr, a.tiles, a.wstride, cur.slot, &ti, &g, &x, &y);
     PathKey key; key.seed = a.fr.seed; key.tile = (uint32_t)a.tiles[ti].id; key.sample = (uint32_t)(y * g.nsx + x);
     Shading<T, PLASTIC, true> sh(a.sc, a.fr, key, cnt);
-    QueueSink sink{a, a.queue[a.cur ^ 1], lane, 0, 0, 0, false, 0.f};
+    QueueSink sink{a, a.queue[a.cur ^ 1], lane, 0, 0, 0, false, 0.f, wc};
     Hit h; h.t = hr.t; h.u = hr.u; h.v = hr.v; h.prim = hr.prim; h.inst = hr.inst;
     sh.shade(cur, h, sink);
     Accum *acc = a.accum + cur.slot;
@@ -880,6 +911,16 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
     if (sink.g) atomicAdd((unsigned long long *)&acc->g, (unsigned long long)sink.g);
     if (sink.b) atomicAdd((unsigned long long *)&acc->b, (unsigned long long)sink.b);
     if (sink.has_alpha) acc->a = sink.av;
+  }
+  if (wc) {                                 // fill what the warp reserved and did not use
+    __syncwarp();
+    RayRec dead; memset(&dead, 0, sizeof dead);
+    dead.d[2] = 1.; dead.tmin = 1.; dead.tmax = 0.; dead.type = RAY_DEAD; dead.target = a.fr.target_group; dead.filter_shader = -1;
+    RayRec *next = a.queue[a.cur ^ 1];
+    for (unsigned p = wc->used + (unsigned)lane; p < wc->alloc; p += 32u) {
+      const unsigned slot = wc->base[(p / FJ_QCHUNK) & 1u] + (p % FJ_QCHUNK);
+      if (slot < a.capacity) store_ray_cs(next + slot, dead);
+    }
   }
   flush_counters(cnt, 0, a.counters, lane);
 }

@@ -355,6 +355,7 @@ EXTEND_VARIANTS = {
     "v2_quantised_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "0", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
     "v2_cooperative_leaves": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "1"},
     "v2_cooperative_leaves_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "1", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
+    "v2_unchunked_queue": {"FJGPU_QUEUE_CHUNK": "0"},
     "v3_quad_per_ray": {"FJGPU_EXTEND": "3"},
     "v3_quad_per_ray_12": {"FJGPU_EXTEND": "3", "FJGPU_EXTEND_MINBLOCKS": "12", "FJGPU_REFILL": "32", "FJGPU_PHASE_A_MIN": "32"},
 }
@@ -385,7 +386,7 @@ def test_extend_variants_bit_exact(sk, device, scene, monkeypatch):
     dev.load_structs(st)
     try:
         for name, env in EXTEND_VARIANTS.items():
-            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP"):
+            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
@@ -406,7 +407,7 @@ def test_extend_variants_same_frame(sk, device, name, monkeypatch):
     desc = golden_scenes.SCENES[name]()
     frames = {}
     for vname, env in EXTEND_VARIANTS.items():
-        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP"):
+        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -416,6 +417,22 @@ def test_extend_variants_same_frame(sk, device, name, monkeypatch):
     for vname, (img, rays) in frames.items():
         assert rays == ref_rays, vname
         assert np.array_equal(img, ref_img), vname
+
+
+def test_chunked_queue_same_frame(sk, device, monkeypatch):
+    """k_shade reserving queue slots in per-warp chunks (FJGPU_QUEUE_CHUNK=1, the default: fillers in the queue, another ray
+    order) renders the same frame bit for bit as one atomic per spawn (FJGPU_QUEUE_CHUNK=0) and counts the same rays, on a branching path tree large enough that every warp
+    goes through many chunks."""
+    desc = sk.scene_blob_pathtracing(n=32, res=(320, 180), rate=4, reflect=(.3, .3, .3), refract=(.4, .4, .4))
+    st = desc.to_structs()
+    monkeypatch.setenv("FJGPU_QUEUE_CHUNK", "0")
+    a, sa = gpu_render(device, desc, st)
+    monkeypatch.setenv("FJGPU_QUEUE_CHUNK", "1")
+    b, sb = gpu_render(device, desc, st)
+    assert np.array_equal(a, b)
+    for k in ("rays_camera", "rays_shadow", "rays_diffuse", "rays_reflect", "rays_refract", "rays_hit", "hit_mesh_levels"):
+        assert getattr(sa, k) == getattr(sb, k), k
+    assert sa.rays_diffuse > 0 and sa.rays_reflect > 0 and sa.rays_refract > 0
 
 
 # ---------------------------------------------------------------------------------------------- device BVH build (§8f row 2)
@@ -450,13 +467,13 @@ def test_device_built_bvh_gives_the_same_hits_and_frames(sk, device, scene, monk
             assert same.mean() > 0.999
             assert np.array_equal(u[same], ru[same]) and np.array_equal(v[same], rv[same])
         for name, env in EXTEND_VARIANTS.items():
-            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP"):
+            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK"):
                 monkeypatch.delenv(k, raising=False)
             for k, v_ in env.items():
                 monkeypatch.setenv(k, v_)
             t, u, v, p, i = dev.trace_closest(0, o, d, tmin, tmax, 0)
             assert np.array_equal(i, ri) and np.array_equal(t, rt), name
-        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP"):
+        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK"):
             monkeypatch.delenv(k, raising=False)
         img_dev, stats_dev = dev.render(st["params"], desc.tiles())
     finally:
