@@ -639,8 +639,11 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         // chunked slot reservation (fj_kernels.cuh, QueueSink): every k_shade warp may leave up to FJ_QCHUNK + FJ_QRESERVE
         // reserved slots as fillers, on top of the records the ray tree can produce
         const bool chunked = !has_plastic && env_int("FJGPU_QUEUE_CHUNK", 1) != 0;
-        const int shade_smb = env_int("FJGPU_SHADE_MINBLOCKS", 5), shade_per = env_int("FJGPU_SHADE_CTAS", 2);
-        const size_t shade_warps = (size_t)ctx->sm_count * (shade_smb >= 8 ? 8 : (shade_smb >= 6 ? 6 : 5)) * shade_per * 4;
+        // grid of the k_shade variant without plastic shaders: resident CTAs per SM (template parameter) x CTAs per slot
+        const int shade_env = env_int("FJGPU_SHADE_MINBLOCKS", 5), shade_per = std::max(1, env_int("FJGPU_SHADE_CTAS", 2));
+        const int shade_smb = shade_env >= 8 ? 8 : (shade_env >= 6 ? 6 : 5);
+        const int shade_ctas = ctx->sm_count * shade_smb * shade_per;
+        const size_t shade_warps = (size_t)shade_ctas * 4;      // 128 threads per CTA
         const size_t capacity = (size_t)want + (chunked ? shade_warps * (FJ_QCHUNK + FJ_QRESERVE) : 0);
         if (capacity > 4000000000ull) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray tree too wide for one tile's ray queue");
         a.chunked = chunked ? 1 : 0;
@@ -688,10 +691,9 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
           CK(cudaEventRecord(e1, ctx->stream));
           if (has_plastic) fj::k_shade<float, true><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a);
           else {
-            const int smb = env_int("FJGPU_SHADE_MINBLOCKS", 5), per = env_int("FJGPU_SHADE_CTAS", 2);
-            if (smb >= 8) fj::k_shade<float, false, 8><<<ctx->sm_count * 8 * per, 128, 0, ctx->stream>>>(a);
-            else if (smb >= 6) fj::k_shade<float, false, 6><<<ctx->sm_count * 6 * per, 128, 0, ctx->stream>>>(a);
-            else fj::k_shade<float, false, 5><<<ctx->sm_count * 5 * per, 128, 0, ctx->stream>>>(a);
+            if (shade_smb == 8) fj::k_shade<float, false, 8><<<shade_ctas, 128, 0, ctx->stream>>>(a);
+            else if (shade_smb == 6) fj::k_shade<float, false, 6><<<shade_ctas, 128, 0, ctx->stream>>>(a);
+            else fj::k_shade<float, false, 5><<<shade_ctas, 128, 0, ctx->stream>>>(a);
           }
           CK(cudaGetLastError());
           launches += 2;
