@@ -75,6 +75,8 @@ class Device:
 
     def load_structs(self, st):
         """`st`: the flat struct dict (meshes, instances, group_offsets/ids, shaders, lights, camera)."""
+        if st.get("velocity_meshes"):
+            raise FjGpuError(-1, "per-vertex velocity (mesh motion blur) has no device implementation yet")
         for mid, P, N, idx in st["meshes"]:
             self.mesh(mid, P, N, idx)
         for mid, uv in st.get("mesh_uv", {}).items():

@@ -277,6 +277,7 @@ struct Isect {                       // src/fj_intersection.h:21-55
 struct Mesh {                        // src/fj_mesh.h:200-216 (subset on the path)
   std::vector<V3> P, N; std::vector<int32_t> idx; std::vector<int32_t> group; int nfaces;
   std::vector<float> uv;             // 2 floats per vertex (empty: no point texture)
+  std::vector<V3> vel;               // per-vertex velocity (empty: none), Mesh::velocity_, src/fj_mesh.h:210
   Box bounds;                        // Mesh::ComputeBounds, src/fj_mesh.cc:235-244
   // GridAccelerator state, src/fj_grid_accelerator.h
   Box acc_bounds;                    // Accelerator::bounds_ (padded), src/fj_accelerator.cc:60-64
@@ -284,10 +285,84 @@ struct Mesh {                        // src/fj_mesh.h:200-216 (subset on the pat
   std::vector<int32_t> cell_head;    // cells_[id] -> first list node (-1 = NULL)
   std::vector<int32_t> node_prim, node_next;  // the singly linked Cell lists
   void tri(int f, V3 &a, V3 &b, V3 &c) const { a = P[idx[3 * f]]; b = P[idx[3 * f + 1]]; c = P[idx[3 * f + 2]]; }
-  void prim_bounds(int f, Box *b) const { V3 a, bb, c; tri(f, a, bb, c); b->ReverseInfinite(); b->AddPoint(a); b->AddPoint(bb); b->AddPoint(c); }
+  // Mesh::get_primitive_bounds, src/fj_mesh.cc:420-439: with velocity the bounds also hold the vertices at time 1
+  void prim_bounds(int f, Box *b) const {
+    V3 a, bb, c; tri(f, a, bb, c); b->ReverseInfinite(); b->AddPoint(a); b->AddPoint(bb); b->AddPoint(c);
+    if (!vel.empty()) { b->AddPoint(a + vel[idx[3 * f]]); b->AddPoint(bb + vel[idx[3 * f + 1]]); b->AddPoint(c + vel[idx[3 * f + 2]]); }
+  }
 };
 
 const Real PADDING = .0001;          // src/fj_accelerator.cc:13
+
+// ---------------------------------------------------------------- vertex velocity generator
+// Ken Perlin's "improved noise" (SIGGRAPH 2002) as src/fj_noise.cc:33-128 evaluates it: the published 256-entry permutation
+// (repeated once), quintic fade, 12 gradient directions from the low 4 hash bits; PerlinNoise sums `octaves` of it with
+// amplitude *= persistence and position *= lacunarity; PerlinNoise3d offsets the position for the y and z components.
+const unsigned char PERLIN_P[256] = {
+  151,160,137,91,90,15,131,13,201,95,96,53,194,233,7,225,140,36,103,30,69,142,8,99,37,240,21,10,23,190,6,148,
+  247,120,234,75,0,26,197,62,94,252,219,203,117,35,11,32,57,177,33,88,237,149,56,87,174,20,125,136,171,168,
+  68,175,74,165,71,134,139,48,27,166,77,146,158,231,83,111,229,122,60,211,133,230,220,105,92,41,55,46,245,40,
+  244,102,143,54,65,25,63,161,1,216,80,73,209,76,132,187,208,89,18,169,200,196,135,130,116,188,159,86,164,100,
+  109,198,173,186,3,64,52,217,226,250,124,123,5,202,38,147,118,126,255,82,85,212,207,206,59,227,47,16,58,17,
+  182,189,28,42,223,183,170,213,119,248,152,2,44,154,163,70,221,153,101,155,167,43,172,9,129,22,39,253,19,98,
+  108,110,79,113,224,232,178,185,112,104,218,246,97,228,251,34,242,193,238,210,144,12,191,179,162,241,81,51,
+  145,235,249,14,239,107,49,192,214,31,181,199,106,157,184,84,204,176,115,121,50,45,127,4,150,254,138,236,
+  205,93,222,114,67,29,24,72,243,141,128,195,78,66,215,61,156,180};
+inline int perlin_perm(int i) { return PERLIN_P[i & 255]; }            // perm[] holds the table twice: indices reach 511
+inline Real perlin_fade(Real t) { return t * t * t * (t * (t * 6 - 15) + 10); }
+inline Real perlin_lerp(Real t, Real a, Real b) { return a + t * (b - a); }
+inline Real perlin_grad(int hash, Real x, Real y, Real z) {
+  const int h = hash & 15;
+  const Real u = h < 8 ? x : y;
+  const Real v = h < 4 ? y : (h == 12 || h == 14 ? x : z);
+  return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+}
+Real PeriodicNoise3d(Real x, Real y, Real z) {                          // src/fj_noise.cc:90-128
+  const int X = (int)std::floor(x) & 255, Y = (int)std::floor(y) & 255, Z = (int)std::floor(z) & 255;
+  const Real xx = x - std::floor(x), yy = y - std::floor(y), zz = z - std::floor(z);
+  const Real u = perlin_fade(xx), v = perlin_fade(yy), w = perlin_fade(zz);
+  const int A = perlin_perm(X) + Y, AA = perlin_perm(A) + Z, AB = perlin_perm(A + 1) + Z;
+  const int B = perlin_perm(X + 1) + Y, BA = perlin_perm(B) + Z, BB = perlin_perm(B + 1) + Z;
+  return perlin_lerp(w,
+      perlin_lerp(v, perlin_lerp(u, perlin_grad(perlin_perm(AA), xx, yy, zz), perlin_grad(perlin_perm(BA), xx - 1, yy, zz)),
+                     perlin_lerp(u, perlin_grad(perlin_perm(AB), xx, yy - 1, zz), perlin_grad(perlin_perm(BB), xx - 1, yy - 1, zz))),
+      perlin_lerp(v, perlin_lerp(u, perlin_grad(perlin_perm(AA + 1), xx, yy, zz - 1), perlin_grad(perlin_perm(BA + 1), xx - 1, yy, zz - 1)),
+                     perlin_lerp(u, perlin_grad(perlin_perm(AB + 1), xx, yy - 1, zz - 1), perlin_grad(perlin_perm(BB + 1), xx - 1, yy - 1, zz - 1))));
+}
+Real PerlinNoise(const V3 &position, Real lacunarity, Real persistence, int octaves) {     // :33-49
+  V3 P = position; Real value = 0, amp = 1;
+  for (int i = 0; i < octaves; i++) { value += amp * PeriodicNoise3d(P.x, P.y, P.z); amp *= persistence; P = P * lacunarity; }
+  return value;
+}
+V3 PerlinNoise3d(const V3 &position, Real lacunarity, Real persistence, int octaves) {     // :51-68
+  V3 out;
+  out.x = PerlinNoise(position, lacunarity, persistence, octaves);
+  out.y = PerlinNoise(position + V3(131.977, 21.1823, 71.0231), lacunarity, persistence, octaves);
+  out.z = PerlinNoise(position + V3(237.492, 11.1312, 133.129), lacunarity, persistence, octaves);
+  return out;
+}
+inline Real SmoothStep(Real a, Real b, Real x) {                        // src/fj_numeric.h:66-77
+  const Real t = (x - a) / (b - a);
+  if (t <= 0) return 0;
+  if (t >= 1) return 1;
+  return t * t * (3 - 2 * t);
+}
+// generate_velocity of VelocityGeneratorProcedure (procedures/velocity_generator_procedure/velocity_generator_procedure.cc:101-124):
+// velocity = .2 (1 - smoothstep(.2, .7, z normalised over the mesh bounds)) * PerlinNoise3d(.2 P, 2, .5, 1), then the
+// mesh bounds are recomputed with it (ComputeNormals leaves the normals as they are: positions do not change).
+void generate_velocity(Mesh &m) {
+  const Real zmin = m.bounds.min.z, zmax = m.bounds.max.z;
+  m.vel.assign(m.P.size(), V3(0, 0, 0));
+  for (size_t i = 0; i < m.P.size(); i++) {
+    const V3 pos = m.P[i];
+    const Real znml = (pos.z - zmin) / (zmax - zmin);
+    const Real vscale = .2 * (1 - SmoothStep(.2, .7, znml));
+    const V3 noise_vec = PerlinNoise3d(.2 * pos, 2, .5, 1);
+    m.vel[i] = vscale * noise_vec;
+  }
+  m.bounds.ReverseInfinite();
+  for (int i = 0; i < m.nfaces; i++) { Box b; m.prim_bounds(i, &b); m.bounds.AddBox(b); }
+}
 
 // Mesh::ComputeNormals, src/fj_mesh.cc:195-233
 void compute_normals(Mesh &m) {
@@ -303,10 +378,14 @@ void compute_normals(Mesh &m) {
   for (int i = 0; i < nv; i++) m.N[i] = Normalize(m.N[i]);
 }
 
-// Mesh::ray_intersect, src/fj_mesh.cc:246-308 (no velocity) wrapped by
-// PrimitiveSet::RayIntersect, src/fj_primitive_set.cc:10-26
-bool mesh_ray_intersect(const Mesh &m, int prim, const Ray &ray, Isect *is) {
+// Mesh::ray_intersect, src/fj_mesh.cc:246-308 wrapped by PrimitiveSet::RayIntersect, src/fj_primitive_set.cc:10-26.
+// With per-vertex velocity the triangle is tested where it is at the ray's time (:252-259); the shading normal stays the
+// mesh's (:273-276).
+bool mesh_ray_intersect(const Mesh &m, int prim, const Ray &ray, Real time, Isect *is) {
   V3 P0, P1, P2; m.tri(prim, P0, P1, P2);
+  if (!m.vel.empty()) {
+    P0 = P0 + time * m.vel[m.idx[3 * prim]]; P1 = P1 + time * m.vel[m.idx[3 * prim + 1]]; P2 = P2 + time * m.vel[m.idx[3 * prim + 2]];
+  }
   Real t, u, v;
   if (!TriRayIntersect(P0, P1, P2, ray.orig, ray.dir, &t, &u, &v)) { is->t_hit = REAL_MAX; return false; }
   if (!m.N.empty()) {
@@ -370,7 +449,20 @@ void grid_build(Mesh &m) {
     Z0 = (int)Clamp(Z0, 0, Z); Z1 = (int)Clamp(Z1, 0, Z);
     for (int z = Z0; z < Z1; z++) for (int y = Y0; y < Y1; y++) for (int x = X0; x < X1; x++) {
       Box cell; cell.min = b.min + V3(x, y, z) * cs; cell.max = cell.min + cs;   // get_grid_cell :334-343
-      if (!BoxBoxIntersect(tri_bounds, cell)) continue;
+      if (m.vel.empty()) { if (!BoxBoxIntersect(tri_bounds, cell)) continue; }
+      else {                                     // box_tri_intersect, fj_mesh.cc:316-340: the sweep in 8 steps, each bounded by its two ends
+        V3 A, B, C; m.tri(i, A, B, C);
+        const int N_STEPS = 8;
+        const V3 s0 = m.vel[m.idx[3 * i]] / N_STEPS, s1 = m.vel[m.idx[3 * i + 1]] / N_STEPS, s2 = m.vel[m.idx[3 * i + 2]] / N_STEPS;
+        bool any = false;
+        for (int k = 0; k < N_STEPS && !any; k++) {
+          const V3 Q0 = A + k * s0, Q1 = B + k * s1, Q2 = C + k * s2;
+          Box sb; sb.ReverseInfinite(); sb.AddPoint(Q0); sb.AddPoint(Q1); sb.AddPoint(Q2);
+          sb.AddPoint(Q0 + s0); sb.AddPoint(Q1 + s1); sb.AddPoint(Q2 + s2);
+          any = BoxBoxIntersect(sb, cell);
+        }
+        if (!any) continue;
+      }
       const size_t cid = (size_t)z * Y * X + (size_t)y * X + x;
       m.node_prim.push_back(i); m.node_next.push_back(m.cell_head[cid]);         // new cell becomes the list head
       m.cell_head[cid] = (int32_t)m.node_prim.size() - 1;
@@ -381,7 +473,7 @@ void grid_build(Mesh &m) {
 
 // Accelerator::Intersect + GridAccelerator::intersect, src/fj_accelerator.cc:94-113,
 // src/fj_grid_accelerator.cc:162-306 (3D-DDA)
-bool grid_intersect(const Mesh &m, const Ray &ray, Isect *isect) {
+bool grid_intersect(const Mesh &m, const Ray &ray, Real time, Isect *isect) {
   Real bt0 = 0, bt1 = 0;
   if (!BoxRayIntersect(m.acc_bounds, ray.orig, ray.dir, ray.tmin, ray.tmax, &bt0, &bt1)) return false;
   Real boxhit_tmin = REAL_MAX, boxhit_tmax = REAL_MAX;
@@ -410,7 +502,7 @@ bool grid_intersect(const Mesh &m, const Ray &ray, Isect *isect) {
     imin->t_hit = REAL_MAX;
     const size_t id = (size_t)m.nc[0] * m.nc[1] * cell_id[2] + (size_t)m.nc[0] * cell_id[1] + cell_id[0];
     for (int c = m.cell_head[id]; c != -1; c = m.node_next[c]) {
-      const bool hittmp = mesh_ray_intersect(m, m.node_prim[c], ray, itmp);
+      const bool hittmp = mesh_ray_intersect(m, m.node_prim[c], ray, time, itmp);
       if (!hittmp) continue;
       Box cell; cell.min = m.grid_bounds.min + V3(cell_id[0], cell_id[1], cell_id[2]) * m.cellsize; cell.max = cell.min + m.cellsize;
       const V3 P_hit = RayPointAt(ray, itmp->t_hit);
@@ -519,7 +611,7 @@ bool instance_ray_intersect(const Scene &s, int iid, const Ray &ray, Real time, 
   ro.orig = MatPoint(inv, ray.orig);
   ro.dir = MatVector(inv, ray.dir);
   const Mesh &m = s.meshes.find(in.mesh)->second;
-  if (!grid_intersect(m, ro, isect)) return false;
+  if (!grid_intersect(m, ro, time, isect)) return false;
   isect->P = MatPoint(fwd, isect->P);
   isect->N = Normalize(MatVector(fwd, isect->N));
   isect->dPdu = MatVector(fwd, isect->dPdu); isect->dPdv = MatVector(fwd, isect->dPdv);     // fj_object_instance.cc:237-238
@@ -989,6 +1081,14 @@ int fjo_mesh(fjo_scene *sc, int mesh_id, const double *P, const double *N, int n
   sc->s.built = false;
   return 0;
 }
+// Runs the velocity generator on a mesh (second half); vel3_out (may be null) receives the velocities.
+int fjo_mesh_generate_velocity(fjo_scene *sc, int mesh_id, double *vel3_out) {
+  auto it = sc->s.meshes.find(mesh_id); if (it == sc->s.meshes.end()) return -1;
+  generate_velocity(it->second);
+  if (vel3_out) for (size_t i = 0; i < it->second.vel.size(); i++) { vel3_out[3 * i] = it->second.vel[i].x; vel3_out[3 * i + 1] = it->second.vel[i].y; vel3_out[3 * i + 2] = it->second.vel[i].z; }
+  sc->s.built = false;
+  return 0;
+}
 int fjo_mesh_set_uv(fjo_scene *sc, int mesh_id, const float *uv2, int nverts) {
   auto it = sc->s.meshes.find(mesh_id);
   if (it == sc->s.meshes.end() || (uv2 && nverts != (int)it->second.P.size())) return -1;
@@ -1089,6 +1189,11 @@ int fjo_transform_samples(fjo_scene *sc, int target, int torder, int rorder, int
   else { if (target >= (int)sc->s.inst.size()) return -1; sc->s.inst[target].xs = xs; }
   sc->s.built = false; return 0;
 }
+// probes: PerlinNoise3d / SmoothStep
+void fjo_perlin3d(const double *p3, double lacunarity, double persistence, int octaves, double *out3) {
+  const V3 n = PerlinNoise3d(V3(p3[0], p3[1], p3[2]), lacunarity, persistence, octaves); out3[0] = n.x; out3[1] = n.y; out3[2] = n.z;
+}
+double fjo_smoothstep(double a, double b, double x) { return SmoothStep(a, b, x); }
 // probe: XfmLerpTransformSample of a sample list at one time
 int fjo_lerp_transform(int torder, int rorder, int nT, const double *T4, int nR, const double *R4, int nS, const double *S4, double time, double *fwd16, double *inv16) {
   if (nT < 1 || nR < 1 || nS < 1) return -1;

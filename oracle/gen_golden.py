@@ -34,7 +34,7 @@ def main():
         f.write(txt)
     imgs = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for name, make in golden_scenes.SCENES.items():
+        for name, make in list(golden_scenes.SCENES.items()) + list(golden_scenes.ORACLE_ONLY.items()):
             img, secs = sk.reference_render(make(), os.path.join(tmp, name), threads=1)
             imgs[name] = img
             print("%-16s %s  %.3fs  mean %.6f" % (name, img.shape, secs, img.mean()))

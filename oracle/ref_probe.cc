@@ -23,6 +23,9 @@
 #include "fj_mesh.h"
 #include "fj_box.h"
 #include "fj_ray.h"
+#include "fj_noise.h"
+#include "fj_numeric.h"
+#include "fj_transform.h"
 
 #include <chrono>
 #include <cstdio>
@@ -174,8 +177,43 @@ static void dump_vectors()
     for (size_t k = 0; k < idx.size(); k++) printf("%d%s", idx[k], k + 1 < idx.size() ? "," : "");
     printf("],\"N\":[");
     for (size_t k = 0; k < P.size(); k++) { const Vector N = m.GetPointNormal(k); printf("[%.17g,%.17g,%.17g]%s", N.x, N.y, N.z, k + 1 < P.size() ? "," : ""); }
-    printf("]}\n");
+    printf("]},\n");
   }
+  // PerlinNoise3d / SmoothStep (src/fj_noise.cc:33-128, src/fj_numeric.h:66-77): what VelocityGeneratorProcedure evaluates
+  printf("\"perlin\":[\n");
+  for (int i = 0; i < 48; i++) {
+    const double sc = i < 40 ? 3. : 300.;
+    const Vector p(sc * srand11(), sc * srand11(), sc * srand11());
+    const Vector n = PerlinNoise3d(p, 2, .5, 1 + i % 3);
+    printf("{"); pv("p", p); printf("\"octaves\":%d,", 1 + i % 3); pv("n", n);
+    const double x = 1.5 * urand() - .25; printf("\"x\":%.17g,\"smooth\":%.17g}%s\n", x, SmoothStep(.2, .7, x), i < 47 ? "," : "");
+  }
+  printf("],\n");
+  // XfmLerpTransformSample (src/fj_transform.cc:306-322) over pushed sample lists (PropPushSample keeps them sorted by time
+  // on top of the initial time-0 sample, src/fj_property.cc:284-312)
+  printf("\"lerp\":[\n");
+  for (int i = 0; i < 24; i++) {
+    TransformSampleList list; XfmInitTransformSampleList(&list);
+    const int nt = 1 + i % 3, nr = 1 + (i / 3) % 3, ns = 1 + (i / 9) % 2;
+    printf("{\"T\":[");
+    for (int k = 0; k < nt; k++) { const double v[4] = {3 * srand11(), 3 * srand11(), 3 * srand11(), k == 0 && i % 2 ? 0. : 2 * urand() - .5}; XfmPushTranslateSample(&list, v[0], v[1], v[2], v[3]); printf("[%.17g,%.17g,%.17g,%.17g]%s", v[0], v[1], v[2], v[3], k < nt - 1 ? "," : ""); }
+    printf("],\"R\":[");
+    for (int k = 0; k < nr; k++) { const double v[4] = {180 * srand11(), 180 * srand11(), 180 * srand11(), k == 0 ? 0. : 2 * urand() - .5}; XfmPushRotateSample(&list, v[0], v[1], v[2], v[3]); printf("[%.17g,%.17g,%.17g,%.17g]%s", v[0], v[1], v[2], v[3], k < nr - 1 ? "," : ""); }
+    printf("],\"S\":[");
+    for (int k = 0; k < ns; k++) { const double v[4] = {.2 + 2 * urand(), .2 + 2 * urand(), .2 + 2 * urand(), k == 0 ? 0. : 2 * urand() - .5}; XfmPushScaleSample(&list, v[0], v[1], v[2], v[3]); printf("[%.17g,%.17g,%.17g,%.17g]%s", v[0], v[1], v[2], v[3], k < ns - 1 ? "," : ""); }
+    printf("],\"at\":[");
+    for (int k = 0; k < 5; k++) {
+      const double time = k == 0 ? 0. : (k == 1 ? 1. : 2.4 * urand() - .7);
+      Transform x; XfmLerpTransformSample(&list, time, &x);
+      printf("{\"time\":%.17g,\"fwd\":[", time);
+      for (int e = 0; e < 16; e++) printf("%.17g%s", x.matrix.e[e], e < 15 ? "," : "");
+      printf("],\"inv\":[");
+      for (int e = 0; e < 16; e++) printf("%.17g%s", x.inverse.e[e], e < 15 ? "," : "");
+      printf("]}%s", k < 4 ? "," : "");
+    }
+    printf("]}%s\n", i < 23 ? "," : "");
+  }
+  printf("]\n");
   printf("}\n");
 }
 

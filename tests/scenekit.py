@@ -72,6 +72,11 @@ def oracle():
     lib.fjo_groups.argtypes = [vp, i32, i32p, i32p]
     lib.fjo_shaders.argtypes = [vp, i32, P(a.Shader)]
     lib.fjo_mesh_set_uv.argtypes = [vp, i32, P(C.c_float), i32]
+    lib.fjo_mesh_generate_velocity.argtypes = [vp, i32, f64p]
+    lib.fjo_perlin3d.argtypes = [f64p, C.c_double, C.c_double, i32, f64p]
+    lib.fjo_perlin3d.restype = None
+    lib.fjo_smoothstep.argtypes = [C.c_double] * 3
+    lib.fjo_smoothstep.restype = C.c_double
     lib.fjo_textures.argtypes = [vp, i32, P(a.Texture)]
     lib.fjo_dome_samples.argtypes = [P(a.Texture), i32, f64p, P(C.c_float)]
     lib.fjo_lights.argtypes = [vp, i32, P(a.Light)]
@@ -186,6 +191,7 @@ class SceneDesc:
     def __init__(self):
         self.meshes = []      # (name, P float32 [V,3], idx int32 [F,3], ply_path or None)
         self.mesh_uv = {}     # name -> uv float32 [V,2] (PLY properties uv1 / uv2)
+        self.mesh_velocity = set()   # names of meshes the reference's VelocityGeneratorProcedure runs on (oracle-only so far)
         self.textures = []    # (name, image float32 [H,W,C]) written as .mip; shaders refer to them by name in the
                               # `texture` (constant) / `diffuse_map` (plastic, pathtracing) property
         self.shaders = []     # (name, kind str, props dict)
@@ -199,8 +205,10 @@ class SceneDesc:
         # channels listed there are set with SetSampleProperty3 instead of SetProperty3
 
     # ---- construction
-    def mesh(self, name, P, idx, ply_path=None, uv=None):
+    def mesh(self, name, P, idx, ply_path=None, uv=None, velocity=False):
         self.meshes.append((name, np.ascontiguousarray(P, np.float32), np.ascontiguousarray(idx, np.int32), ply_path))
+        if velocity:
+            self.mesh_velocity.add(name)
         if uv is not None:
             self.mesh_uv[name] = np.ascontiguousarray(uv, np.float32)
 
@@ -249,6 +257,8 @@ class SceneDesc:
         for k in kinds:
             L.append("OpenPlugin %s %s" % (SHADER_PLUGIN[k][0], os.path.join(plugin_dir, SHADER_PLUGIN[k][1])))
         L.append("OpenPlugin stanfordply_procedure %s" % os.path.join(plugin_dir, "StanfordPlyProcedure"))
+        if self.mesh_velocity:
+            L.append("OpenPlugin velocity_generator_procedure %s" % os.path.join(plugin_dir, "VelocityGeneratorProcedure"))
         L.append("NewCamera cam1 PerspectiveCamera")
         self.scn_transform(L, "cam1", self.cam, (("T", "translate"), ("R", "rotate")))
         L.append("SetProperty1 cam1 fov %r" % float(self.cam["fov"]))
@@ -291,6 +301,9 @@ class SceneDesc:
             L.append("SetStringProperty %s_proc filepath %s" % (name, ply))
             L.append("SetStringProperty %s_proc io_mode r" % name)
             L.append("RunProcedure %s_proc" % name)
+            if name in self.mesh_velocity:       # scenes/mesh_velocity_blur.py:70-73
+                L += ["NewProcedure %s_velgen velocity_generator_procedure" % name, "AssignMesh %s_velgen mesh %s" % (name, name),
+                      "RunProcedure %s_velgen" % name]
         for ins in self.instances:
             n = ins["name"]
             L.append("NewObjectInstance %s %s" % (n, ins["mesh"]))
@@ -370,6 +383,7 @@ class SceneDesc:
             o.fjo_compute_normals(dptr(P64), len(P64), iptr(idx), len(idx) // 3, dptr(N64))
             meshes.append((mid, P64, N64, idx))
         out["meshes"] = meshes
+        out["velocity_meshes"] = sorted(mesh_ids[n] for n in self.mesh_velocity)
         out["mesh_uv"] = {mesh_ids[n]: uv for n, uv in self.mesh_uv.items()}
         # textures: the tile arrays a .mip file of the image holds (synth.write_mip), as fjgpu_texture structs
         tex_ids = {}
@@ -500,6 +514,8 @@ def oracle_scene(st):
         o.fjo_mesh(sc, mid, dptr(P), dptr(N), len(P), iptr(idx), None, len(idx) // 3)
     for mid, uv in st.get("mesh_uv", {}).items():
         assert o.fjo_mesh_set_uv(sc, mid, fptr(uv), len(uv)) == 0
+    for mid in st.get("velocity_meshes", []):
+        assert o.fjo_mesh_generate_velocity(sc, mid, None) == 0
     o.fjo_textures(sc, st.get("ntextures", 0), st.get("textures"))
     o.fjo_instances(sc, st["ninstances"], st["instances"])
     o.fjo_groups(sc, 1, iptr(st["group_offsets"]), iptr(st["group_ids"]))

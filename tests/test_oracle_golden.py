@@ -139,6 +139,30 @@ def test_compute_normals_bit_exact(sk, vec):
     assert N.tolist() == c["N"]
 
 
+def test_perlin_noise_and_smoothstep_bit_exact(sk, vec):
+    """What VelocityGeneratorProcedure evaluates per vertex (src/fj_noise.cc, SmoothStep)."""
+    o = sk.oracle()
+    for c in vec["perlin"]:
+        p, out = np.asarray(c["p"], np.float64), np.zeros(3)
+        o.fjo_perlin3d(sk.dptr(p), 2.0, 0.5, c["octaves"], sk.dptr(out))
+        assert out.tolist() == c["n"]
+        assert o.fjo_smoothstep(.2, .7, c["x"]) == c["smooth"]
+
+
+def test_transform_sample_interpolation_bit_exact(sk, vec):
+    """XfmLerpTransformSample over pushed sample lists (motion blur): the oracle and the test kit's table builder against
+    the reference's matrices, bit for bit (libfjscene is held to the oracle in tests/test_motion_cpu.py)."""
+    o = sk.oracle()
+    for c in vec["lerp"]:
+        T4, R4, S4 = sk.sample_rows(c["T"], None), sk.sample_rows(c["R"], None), sk.sample_rows(c["S"], None, (1.0, 1.0, 1.0))
+        for a in c["at"]:
+            f, i = np.zeros(16), np.zeros(16)
+            assert o.fjo_lerp_transform(0, 10, len(T4), sk.dptr(T4), len(R4), sk.dptr(R4), len(S4), sk.dptr(S4), a["time"], sk.dptr(f), sk.dptr(i)) == 0
+            assert f.tolist() == a["fwd"] and i.tolist() == a["inv"]
+            fk, ik = sk.motion_table(T4, R4, S4, [a["time"]])
+            assert fk[0].tolist() == a["fwd"] and ik[0].tolist() == a["inv"]
+
+
 def _fb_tol(ref):
     # the reference's .fb text keeps 6 significant digits (src/fj_framebuffer_io.cc:62)
     return 6e-6 * np.maximum(np.abs(ref), .1) + 1e-9
@@ -153,6 +177,19 @@ def test_frames_match_reference(sk, images, name):
     assert img.shape == ref.shape
     assert np.all(np.abs(img - ref) <= _fb_tol(ref)), float(np.abs(img - ref).max())
     assert stats.rays_camera == stats.camera_samples
+
+
+@pytest.mark.parametrize("name", list(golden_scenes.ORACLE_ONLY))
+def test_oracle_only_frames_match_reference(sk, images, name):
+    """Rows the device does not render yet (per-vertex velocity): the oracle's restatement is already pinned on the
+    reference's frame, in both RNG modes (the scenes are deterministic)."""
+    ref = images[name]
+    for mode, threads in ((1, 1), (0, 4)):
+        img, stats = sk.oracle_render(golden_scenes.ORACLE_ONLY[name](), rng_mode=mode, threads=threads)
+        assert img.shape == ref.shape
+        assert np.all(np.abs(img - ref) <= _fb_tol(ref)), float(np.abs(img - ref).max())
+    static, _ = sk.oracle_render(golden_scenes.SCENES["multi"](), rng_mode=0, threads=4)
+    assert np.abs(static - ref).max() > 0.05          # the velocities do move the picture
 
 
 @pytest.mark.parametrize("name", golden_scenes.DETERMINISTIC)
