@@ -62,6 +62,7 @@ def load_fjscene():
     lib.fjscene_last_resend_bytes.restype = C.c_uint64
     lib.fjscene_instance_matrices.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.fjscene_mesh_normals.argtypes = [C.c_long, C.POINTER(C.c_double), C.c_int32]
+    lib.fjscene_mesh_velocity.argtypes = [C.c_long, C.POINTER(C.c_double), C.c_int32]
     lib.fjscene_last_message.restype = C.c_char_p
     i32p_ = C.POINTER(C.c_int32)
     lib.fjscene_flatten.argtypes = [C.c_long, i32p_, i32p_, i32p_, i32p_]

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -149,7 +150,8 @@ struct Xform {
 };
 
 struct Plugin { std::string name; int kind; };   // kind: FJGPU_SHADER_* for shaders, 100 = StanfordPlyProcedure
-struct Mesh { std::vector<double> P, N; std::vector<int32_t> idx; std::vector<float> uv; bool dirty = true; };
+struct Mesh { std::vector<double> P, N; std::vector<int32_t> idx; std::vector<float> uv; bool dirty = true;
+              std::vector<double> vel; };     // per-vertex velocity (VelocityGeneratorProcedure); empty = none
 struct Texture { int width = 0, height = 0, nch = 0, tilesize = 0; std::vector<float> tiles; };   // a `.mip` file's header and tiles (src/fj_mipmap.cc:124-180)
 struct Shader { int plugin; std::map<std::string, std::array<double, 4>> props; ID texture = SI_BADID, bump = SI_BADID; };   // texture: the `texture` / `diffuse_map` property
 struct Procedure { int plugin; ID mesh = SI_BADID; std::string filepath, io_mode; };
@@ -237,6 +239,64 @@ double ply_scalar(const unsigned char *p, const std::string &t, bool swap) {
   if (t == "float" || t == "float32") { float v; memcpy(&v, b, 4); return v; }
   double v; memcpy(&v, b, 8); return v;
 }
+// ---------------------------------------------------------------- VelocityGeneratorProcedure
+// procedures/velocity_generator_procedure/velocity_generator_procedure.cc:101-124 over Ken Perlin's improved noise as
+// src/fj_noise.cc:33-128 evaluates it (published permutation, quintic fade, 12 gradients; octaves with amplitude *= persistence,
+// position *= lacunarity; fixed offsets for the y and z components) and SmoothStep (src/fj_numeric.h:66-77).
+const unsigned char kPerlin[256] = {
+  151,160,137,91,90,15,131,13,201,95,96,53,194,233,7,225,140,36,103,30,69,142,8,99,37,240,21,10,23,190,6,148,
+  247,120,234,75,0,26,197,62,94,252,219,203,117,35,11,32,57,177,33,88,237,149,56,87,174,20,125,136,171,168,
+  68,175,74,165,71,134,139,48,27,166,77,146,158,231,83,111,229,122,60,211,133,230,220,105,92,41,55,46,245,40,
+  244,102,143,54,65,25,63,161,1,216,80,73,209,76,132,187,208,89,18,169,200,196,135,130,116,188,159,86,164,100,
+  109,198,173,186,3,64,52,217,226,250,124,123,5,202,38,147,118,126,255,82,85,212,207,206,59,227,47,16,58,17,
+  182,189,28,42,223,183,170,213,119,248,152,2,44,154,163,70,221,153,101,155,167,43,172,9,129,22,39,253,19,98,
+  108,110,79,113,224,232,178,185,112,104,218,246,97,228,251,34,242,193,238,210,144,12,191,179,162,241,81,51,
+  145,235,249,14,239,107,49,192,214,31,181,199,106,157,184,84,204,176,115,121,50,45,127,4,150,254,138,236,
+  205,93,222,114,67,29,24,72,243,141,128,195,78,66,215,61,156,180};
+inline int pperm(int i) { return kPerlin[i & 255]; }
+inline double pfade(double t) { return t * t * t * (t * (t * 6 - 15) + 10); }
+inline double plerp(double t, double a, double b) { return a + t * (b - a); }
+inline double pgrad(int hash, double x, double y, double z) {
+  const int h = hash & 15;
+  const double u = h < 8 ? x : y, v = h < 4 ? y : (h == 12 || h == 14 ? x : z);
+  return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+}
+double periodic_noise(double x, double y, double z) {
+  const int X = (int)std::floor(x) & 255, Y = (int)std::floor(y) & 255, Z = (int)std::floor(z) & 255;
+  const double xx = x - std::floor(x), yy = y - std::floor(y), zz = z - std::floor(z);
+  const double u = pfade(xx), v = pfade(yy), w = pfade(zz);
+  const int A = pperm(X) + Y, AA = pperm(A) + Z, AB = pperm(A + 1) + Z, B = pperm(X + 1) + Y, BA = pperm(B) + Z, BB = pperm(B + 1) + Z;
+  return plerp(w, plerp(v, plerp(u, pgrad(pperm(AA), xx, yy, zz), pgrad(pperm(BA), xx - 1, yy, zz)),
+                           plerp(u, pgrad(pperm(AB), xx, yy - 1, zz), pgrad(pperm(BB), xx - 1, yy - 1, zz))),
+                  plerp(v, plerp(u, pgrad(pperm(AA + 1), xx, yy, zz - 1), pgrad(pperm(BA + 1), xx - 1, yy, zz - 1)),
+                           plerp(u, pgrad(pperm(AB + 1), xx, yy - 1, zz - 1), pgrad(pperm(BB + 1), xx - 1, yy - 1, zz - 1))));
+}
+double perlin_noise(double x, double y, double z, double lacunarity, double persistence, int octaves) {
+  double value = 0, amp = 1;
+  for (int i = 0; i < octaves; i++) { value += amp * periodic_noise(x, y, z); amp *= persistence; x *= lacunarity; y *= lacunarity; z *= lacunarity; }
+  return value;
+}
+inline double smooth_step(double a, double b, double x) { const double t = (x - a) / (b - a); return t <= 0 ? 0 : (t >= 1 ? 1 : t * t * (3 - 2 * t)); }
+int generate_velocity(Mesh *m) {
+  if (m->idx.empty()) return -1;
+  double zmin = DBL_MAX, zmax = -DBL_MAX;              // Mesh::GetBounds: over the vertices the faces refer to (fj_mesh.cc:235-244)
+  for (int32_t v : m->idx) { zmin = std::min(zmin, m->P[3 * (size_t)v + 2]); zmax = std::max(zmax, m->P[3 * (size_t)v + 2]); }
+  const size_t n = m->P.size() / 3;
+  m->vel.assign(3 * n, 0.);
+  for (size_t i = 0; i < n; i++) {
+    const double px = m->P[3 * i], py = m->P[3 * i + 1], pz = m->P[3 * i + 2];
+    const double znml = (pz - zmin) / (zmax - zmin);
+    const double vscale = .2 * (1 - smooth_step(.2, .7, znml));
+    const double qx = px * .2, qy = py * .2, qz = pz * .2;                       // `.2 * pos`
+    const double nx = perlin_noise(qx, qy, qz, 2, .5, 1);
+    const double ny = perlin_noise(qx + 131.977, qy + 21.1823, qz + 71.0231, 2, .5, 1);
+    const double nz = perlin_noise(qx + 237.492, qy + 11.1312, qz + 133.129, 2, .5, 1);
+    m->vel[3 * i] = nx * vscale; m->vel[3 * i + 1] = ny * vscale; m->vel[3 * i + 2] = nz * vscale;    // `vscale * noise_vec`
+  }
+  m->dirty = true;
+  return 0;
+}
+
 int read_ply(const std::string &path, Mesh *mesh) {
   std::ifstream f(path.c_str(), std::ios::binary);
   if (!f) { fprintf(stderr, "error: couldn't open input file: %s\n", path.c_str()); return -1; }
@@ -491,6 +551,7 @@ Status flatten(Scene &sc, const Renderer &r, Flat *f) {
     const Instance &o = sc.instances[i]; fjgpu_instance &d = f->inst[i];
     memset(&d, 0, sizeof d);
     int t, mi; decode_id(o.mesh, &t, &mi); d.mesh_id = mi;
+    if (!sc.meshes[mi].vel.empty()) return failmsg("per-vertex velocity (mesh motion blur) has no device implementation yet");
     for (int g = 0; g < FJGPU_MAX_SHADING_GROUPS; g++) d.shader_of_group[g] = -1;
     // ObjectInstance::AddShader / GetShader, src/fj_object_instance.cc:160-191: the mesh of this path has one
     // shading group ("" = DEFAULT_SHADING_GROUP -> slot 0)
@@ -670,6 +731,7 @@ ID SiOpenPlugin(const char *filename) {
   else if (base == "PathtracingShader") kind = FJGPU_SHADER_PATHTRACING;
   else if (base == "GlassShader") kind = FJGPU_SHADER_GLASS;
   else if (base == "StanfordPlyProcedure") kind = 100;
+  else if (base == "VelocityGeneratorProcedure") kind = 101;
   if (kind < 0) { last_message = "plugin '" + base + "' has no device implementation"; return bad(SI_ERR_PLUGIN_NOT_FOUND); }
   the_scene->plugins.push_back({base, kind});
   si_errno = SI_ERR_NONE;
@@ -705,6 +767,10 @@ Status SiRunProcedure(ID procedure) {
   if (!p) return SI_FAIL;
   Mesh *m = get(the_scene->meshes, p->mesh, Type_Mesh);
   if (!m) return SI_FAIL;                                        // StanfordPlyProcedure::run: no mesh assigned
+  if (the_scene->plugins[p->plugin].kind == 101) {               // VelocityGeneratorProcedure::run
+    printf("Point Count: %d\n", (int)(m->P.size() / 3));
+    return generate_velocity(m) ? SI_FAIL : ok();
+  }
   if (p->io_mode == "w") return failmsg("StanfordPlyProcedure io_mode w is outside the device path");
   if (read_ply(p->filepath, m)) return SI_FAIL;
   return ok();
@@ -758,7 +824,7 @@ ID SiNewCurve(void) { return bad(SI_ERR_FAILNEW); }
 ID SiNewProcedure(ID plugin) {
   int t, i;
   if (!the_scene || !decode_id(plugin, &t, &i) || t != Type_Plugin || i >= (int)the_scene->plugins.size()) return bad(SI_ERR_BADTYPE);
-  if (the_scene->plugins[i].kind != 100) return bad(SI_ERR_FAILNEW);
+  if (the_scene->plugins[i].kind != 100 && the_scene->plugins[i].kind != 101) return bad(SI_ERR_FAILNEW);
   Procedure p; p.plugin = i; p.io_mode = "r";
   the_scene->procedures.push_back(p);
   si_errno = SI_ERR_NONE;
@@ -1050,6 +1116,12 @@ int fjscene_mesh_normals(long mesh_id, double *N_out, int32_t nverts) {
   Mesh *m = the_scene ? get(the_scene->meshes, mesh_id, Type_Mesh) : nullptr;
   if (!m || (size_t)nverts * 3 != m->N.size()) return -1;
   memcpy(N_out, m->N.data(), m->N.size() * 8);
+  return 0;
+}
+int fjscene_mesh_velocity(long mesh_id, double *vel_out, int32_t nverts) {
+  Mesh *m = the_scene ? get(the_scene->meshes, mesh_id, Type_Mesh) : nullptr;
+  if (!m || m->vel.empty() || (size_t)nverts * 3 != m->vel.size()) return -1;
+  memcpy(vel_out, m->vel.data(), m->vel.size() * 8);
   return 0;
 }
 const char *fjscene_last_message(void) { return last_message.c_str(); }

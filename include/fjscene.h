@@ -143,6 +143,9 @@ void fjscene_set_device_blocks(void *d_tile_blocks, int tile_w_max, int tile_h_m
  * oracle's): row-major 4x4 forward/inverse matrices of instance `index`; returns 0 or -1. */
 int fjscene_instance_matrices(int32_t index, double *fwd16, double *inv16);
 int fjscene_mesh_normals(long mesh_id, double *N_out, int32_t nverts);
+/* Per-vertex velocities VelocityGeneratorProcedure wrote on a mesh (3 doubles per vertex); -1 if it has none.  The
+ * procedure is mirrored bit for bit; rendering such a mesh fails until the device path has moving triangles. */
+int fjscene_mesh_velocity(long mesh_id, double *vel_out, int32_t nverts);
 const char *fjscene_last_message(void);
 /* The flat scene description SiRenderScene would hand to libfjgpu for a renderer (instances, lights, shaders, camera,
  * frame parameters, tiles), built without touching a device: host-logic tests compare it with an independent

@@ -113,3 +113,31 @@ def test_motion_scene_description_is_consistent(tmp_path):
         prod = np.einsum("nij,njk->nik", fwd.reshape(n, 4, 4), inv.reshape(n, 4, 4))
         assert np.abs(prod - np.eye(4)).max() < 1e-12
     assert "motion" not in golden_scenes.SCENES["multi"]().to_structs()
+
+
+def test_velocity_generator_matches_oracle_and_is_refused_at_render(libs, tmp_path):
+    """VelocityGeneratorProcedure through libfjscene writes the oracle's velocities bit for bit (the oracle's are pinned
+    on the reference: tests/test_oracle_golden.py); rendering such a mesh fails loudly — no device path for it yet."""
+    _, _, fuji = libs
+    d = golden_scenes.ORACLE_ONLY["velocity_blur"]()
+    st = d.to_structs()
+    scn = d.to_scn(str(tmp_path), None, plugin_dir="/x")
+    head = "\n".join(l for l in scn.split("\n") if not l.startswith("RenderScene")) + "\n"
+    o = sk.oracle()
+    mid, P, N, idx = st["meshes"][st["velocity_meshes"][0]]
+    sc = o.fjo_scene_new()                       # the generator runs once, on the static mesh
+    o.fjo_mesh(sc, mid, sk.dptr(P), sk.dptr(N), len(P), sk.iptr(idx), None, len(idx) // 3)
+    ref = np.zeros_like(P)
+    assert o.fjo_mesh_generate_velocity(sc, mid, sk.dptr(ref)) == 0
+    o.fjo_scene_free(sc)
+    assert np.abs(ref).max() > 0.01
+    with fuji.Session() as s:
+        s.run(head)
+        vel = np.zeros_like(P)
+        assert s.lib.fjscene_mesh_velocity(s.id("blob"), sk.dptr(vel), len(P)) == 0
+        assert np.array_equal(vel, ref)
+        assert s.lib.fjscene_mesh_velocity(s.id("floor"), sk.dptr(vel), 4) == -1          # a mesh without velocities
+        with pytest.raises(fuji.SceneError, match="command failed"):
+            s.run("RenderScene ren1\n")
+        assert s.lib.fjscene_flatten(C.c_long(s.id("ren1")), None, None, None, None) == -1      # the same check, without the parser
+        assert b"velocity" in s.lib.fjscene_last_message()
