@@ -8,7 +8,8 @@
  * Renderer::execute_rendering (src/fj_renderer.cc:747-791) through the C-ABI of fjgpu.h instead of the
  * CPU worker threads.  What differs, by design:
  *   - SiOpenPlugin() does not dlopen: the device shaders are keyed on the plugin NAME
- *     (ConstantShader, PlasticShader, PathtracingShader, GlassShader; StanfordPlyProcedure as the mesh loader).
+ *     (ConstantShader, PlasticShader, PathtracingShader, GlassShader; StanfordPlyProcedure as the mesh loader,
+ *     VelocityGeneratorProcedure — whose meshes SiRenderScene refuses until the kernels have moving triangles).
  *     Any other plugin yields SI_BADID / SI_ERR_PLUGIN_NOT_FOUND — there is no CPU fallback here.
  *   - entity kinds outside the path (Volume, Curve, PointCloud, Turbulence) yield SI_BADID / SI_ERR_FAILNEW; the
  *     adaptive sampler makes SiRenderScene() return SI_FAIL.  Time-sampled transforms of instances and cameras
