@@ -100,6 +100,7 @@ FJGPU_SYMBOLS = [
     "fjgpu_render_tiles_resident", "fjgpu_trace_closest", "fjgpu_render_tile_samples",
     "fjgpu_scene_info_get", "fjgpu_scene_resend", "fjgpu_textures_set", "fjgpu_mesh_set_uv",
     "fjgpu_time_table", "fjgpu_instance_motion_set", "fjgpu_camera_motion_set",
+    "fjgpu_mesh_upload_velocity", "fjgpu_shutter_set",
 ]
 
 _P = C.POINTER
@@ -128,6 +129,8 @@ def _proto(lib):
     lib.fjgpu_time_table.argtypes = [_P(RenderParams), _P(Tile), i32, C.c_double, C.c_double, f64p, i32]
     lib.fjgpu_instance_motion_set.argtypes = [vp, i32, i32, f64p, f64p]
     lib.fjgpu_camera_motion_set.argtypes = [vp, i32, f64p]
+    lib.fjgpu_mesh_upload_velocity.argtypes = [vp, i32, f64p, f64p, i32, i32p, i32p, i32, f64p]
+    lib.fjgpu_shutter_set.argtypes = [vp, C.c_double, C.c_double]
     return lib
 
 

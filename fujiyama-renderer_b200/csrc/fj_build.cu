@@ -12,7 +12,7 @@
 //   k_emit_binary       Node64 array (index = radix-tree node, root 0)
 //   k_collapse_level    level-synchronous collapse to 4-wide Node128 nodes (largest-area child opened first), carrying the
 //                       worst-case stack depth of a nearest-first walk
-//   k_finish_wide       Node4Q (child-major) and NodeQ64 (8-bit quantised, fj_quant.h) copies of every wide node
+//   k_finish_wide       NodeQ64 (8-bit quantised, fj_quant.h) copy of every wide node
 //   k_tris              triangle packets in leaf (= sorted) order
 #include "fj_build.h"
 #include "fj_bvh.h"
@@ -24,7 +24,7 @@
 
 namespace {
 
-using fjb::Node64; using fjb::Node128; using fjb::Node4Q; using fjb::NodeQ64;
+using fjb::Node64; using fjb::Node128; using fjb::NodeQ64;
 
 struct PBox { float lo[3], hi[3]; };
 
@@ -254,17 +254,10 @@ __global__ void k_collapse_level(Tree t, const Front *cur, int ncur, Front *next
   atomicMax(&c->depth4, fr.depth);
 }
 
-__global__ void k_finish_wide(const Node128 *in, int n, Node4Q *q4, NodeQ64 *qq, Ctl *c) {
+__global__ void k_finish_wide(const Node128 *in, int n, NodeQ64 *qq, Ctl *c) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Node128 w = in[i];
-  Node4Q a;
-  for (int k = 0; k < 4; k++) {
-    a.c[k].lo[0] = w.lox[k]; a.c[k].lo[1] = w.loy[k]; a.c[k].lo[2] = w.loz[k];
-    a.c[k].hi[0] = w.hix[k]; a.c[k].hi[1] = w.hiy[k]; a.c[k].hi[2] = w.hiz[k];
-    a.c[k].ref = w.c[k]; a.c[k].pad = 0;
-  }
-  q4[i] = a;
   NodeQ64 q; double mag = 0;
   if (!fjb::quantize_one(w, q, &mag)) { atomicOr(&c->quant_fail, 1); memset(&q, 0, sizeof q); }
   qq[i] = q;
@@ -309,7 +302,7 @@ int fj_device_build(cudaStream_t st, const double *dP, int32_t nverts, const int
                     bool force_tri64, FjDeviceBuild *out, std::string *err) {
   auto fail = [&](const std::string &m) {
     if (err) *err = m;
-    for (void **q : {&out->nodes, &out->nodes4, &out->nodes4q, &out->nodesq, &out->tri}) { if (*q) cudaFree(*q); *q = nullptr; }
+    for (void **q : {&out->nodes, &out->nodes4, &out->nodesq, &out->tri}) { if (*q) cudaFree(*q); *q = nullptr; }
     return -1;
   };
   if (n < 2) return fail("device build needs at least two triangles");
@@ -390,11 +383,11 @@ int fj_device_build(cudaStream_t st, const double *dP, int32_t nverts, const int
   cudaStreamSynchronize(st);
   const int nw = h.nwide;
   out->nnodes4 = nw; out->max_depth4 = h.depth4; out->stack_need4 = h.stack_need;
-  out->nodes4_bytes = (size_t)nw * sizeof(Node128); out->nodes4q_bytes = (size_t)nw * sizeof(Node4Q); out->nodesq_bytes = (size_t)nw * sizeof(NodeQ64);
-  alloc(&out->nodes4, out->nodes4_bytes); alloc(&out->nodes4q, out->nodes4q_bytes); alloc(&out->nodesq, out->nodesq_bytes);
+  out->nodes4_bytes = (size_t)nw * sizeof(Node128); out->nodesq_bytes = (size_t)nw * sizeof(NodeQ64);
+  alloc(&out->nodes4, out->nodes4_bytes); alloc(&out->nodesq, out->nodesq_bytes);
   if (e != cudaSuccess) { cudaFree(wide); return fail(std::string("device build outputs: ") + cudaGetErrorString(e)); }
   cudaMemcpyAsync(out->nodes4, wide, out->nodes4_bytes, cudaMemcpyDeviceToDevice, st);
-  k_finish_wide<<<(nw + T - 1) / T, T, 0, st>>>((const Node128 *)out->nodes4, nw, (Node4Q *)out->nodes4q, (NodeQ64 *)out->nodesq, ctl);
+  k_finish_wide<<<(nw + T - 1) / T, T, 0, st>>>((const Node128 *)out->nodes4, nw, (NodeQ64 *)out->nodesq, ctl);
   PBox rootbox;
   cudaMemcpyAsync(&rootbox, nbox, sizeof rootbox, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st);

@@ -5,8 +5,8 @@
 // src/fj_grid_accelerator.cc:69-160: ≈ 1.3 s per million triangles on one core).  Any conservative BVH returns the
 // reference's closest hit (fj_bvh.h), so the tree may be built differently: here a linear BVH — 63-bit Morton codes of
 // the padded triangle boxes' centres, one radix sort, the binary radix tree of Karras (HPG 2012), bottom-up boxes, then
-// the same products as the host builder: binary Node64, 4-wide Node128 (largest-area child opened first), child-major
-// Node4Q and 8-bit quantised NodeQ64, triangle packets in leaf order, worst-case stack depths.  Everything stays in HBM.
+// the same products as the host builder: binary Node64, 4-wide Node128 (largest-area child opened first),
+// 8-bit quantised NodeQ64, triangle packets in leaf order, worst-case stack depths.  Everything stays in HBM.
 #ifndef FJ_BUILD_H
 #define FJ_BUILD_H
 
@@ -15,8 +15,8 @@
 #include <string>
 
 struct FjDeviceBuild {
-  void *nodes = nullptr, *nodes4 = nullptr, *nodes4q = nullptr, *nodesq = nullptr, *tri = nullptr;   // cudaMalloc'ed, owned by the caller
-  size_t nodes_bytes = 0, nodes4_bytes = 0, nodes4q_bytes = 0, nodesq_bytes = 0, tri_bytes = 0;
+  void *nodes = nullptr, *nodes4 = nullptr, *nodesq = nullptr, *tri = nullptr;   // cudaMalloc'ed, owned by the caller
+  size_t nodes_bytes = 0, nodes4_bytes = 0, nodesq_bytes = 0, tri_bytes = 0;
   int32_t nnodes = 0, nnodes4 = 0, max_depth = 0, max_depth4 = 0, stack_need4 = 0;
   float bmag = 0, bmagq = 0;
   int quant_ok = 0, tri64 = 0;

@@ -139,7 +139,7 @@ inline int32_t leaf_ref(int32_t first, int32_t count) { return ~((first << 3) | 
 
 void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int top_levels, BuildResult *out) {
   out->nodes.clear(); out->order.clear(); out->top_count = 0; out->max_depth = 0;
-  out->nodes4.clear(); out->max_depth4 = 0;
+  out->nodes4.clear(); out->max_depth4 = 0; out->top_count4 = 0; out->stack_need4 = 0;
   Node128 empty4; memset(&empty4, 0, sizeof empty4);
   // unused slots: a valid box (lo == hi) at +3e38 that no ray interval reaches — the min/max slab test of k_extend2 needs lo <= hi
   for (int k = 0; k < 4; k++) { empty4.lox[k] = empty4.loy[k] = empty4.loz[k] = 3e38f; empty4.hix[k] = empty4.hiy[k] = empty4.hiz[k] = 3e38f; empty4.c[k] = ~0; }
@@ -276,6 +276,27 @@ void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int 
     }
     out->stack_need4 = n4 ? need[0] : 0;
   }
+  // Breadth-first front: the first min(n4, FJB_TOP4_MAX) nodes in level order move to the front of the array (the others
+  // keep their relative order), so that a prefix of the array is the top of the tree.
+  {
+    const size_t n4 = out->nodes4.size();
+    std::vector<int32_t> bfs; bfs.reserve(FJB_TOP4_MAX);
+    if (n4) bfs.push_back(0);
+    for (size_t h = 0; h < bfs.size() && bfs.size() < (size_t)FJB_TOP4_MAX; h++)
+      for (int k = 0; k < 4 && bfs.size() < (size_t)FJB_TOP4_MAX; k++) { const int32_t c = out->nodes4[bfs[h]].c[k]; if (c >= 0) bfs.push_back(c); }
+    std::vector<int32_t> newid(n4, -1);
+    for (size_t k = 0; k < bfs.size(); k++) newid[bfs[k]] = (int32_t)k;
+    int32_t next = (int32_t)bfs.size();
+    for (size_t i = 0; i < n4; i++) if (newid[i] < 0) newid[i] = next++;
+    std::vector<Node128> moved(n4);
+    for (size_t i = 0; i < n4; i++) {
+      Node128 w = out->nodes4[i];
+      for (int k = 0; k < 4; k++) if (w.c[k] >= 0) w.c[k] = newid[w.c[k]];
+      moved[newid[i]] = w;
+    }
+    out->nodes4.swap(moved);
+    out->top_count4 = (int32_t)bfs.size();
+  }
 }
 
 bool quantize_nodes(const Node128 *in, size_t n, NodeQ64 *out, float *bmag) {
@@ -284,16 +305,6 @@ bool quantize_nodes(const Node128 *in, size_t n, NodeQ64 *out, float *bmag) {
     if (!quantize_one(in[i], out[i], &mag)) return false;
   *bmag = round_up(mag * (1.0 + 1e-6));
   return true;
-}
-
-void to_quad_layout(const Node128 *in, size_t n, Node4Q *out) {
-  for (size_t i = 0; i < n; i++)
-    for (int k = 0; k < 4; k++) {
-      Child32 &c = out[i].c[k];
-      c.lo[0] = in[i].lox[k]; c.lo[1] = in[i].loy[k]; c.lo[2] = in[i].loz[k];
-      c.hi[0] = in[i].hix[k]; c.hi[1] = in[i].hiy[k]; c.hi[2] = in[i].hiz[k];
-      c.ref = in[i].c[k]; c.pad = 0;
-    }
 }
 
 }  // namespace fjb

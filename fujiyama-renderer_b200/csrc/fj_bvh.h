@@ -52,15 +52,10 @@ struct BuildResult {
   std::vector<Node128> nodes4;   // the same tree collapsed to 4-wide nodes, DFS preorder, nodes4[0] is the root
   int32_t max_depth4 = 0;
   int32_t stack_need4 = 0;       // worst-case traversal-stack entries of a nearest-first walk of nodes4 (see stack_need())
+  int32_t top_count4 = 0;        // nodes4[0 .. top_count4) are the top of the tree in breadth-first order (any prefix of them is
+                                 // a breadth-first prefix too): what k_extend2 stages in shared memory with one bulk copy
 };
-
-// The 4-wide tree in the child-major layout of the quad-per-ray kernel (k_extend3): child k of a node occupies bytes
-// 32k..32k+31 = lo.x lo.y lo.z hi.x | hi.y hi.z ref pad, so the four lanes of a quad fetch one child each with a single
-// 32-B load and the quad reads the node's 128-B line exactly once.
-struct Child32 { float lo[3]; float hi[3]; int32_t ref; int32_t pad; };
-struct Node4Q { Child32 c[4]; };
-static_assert(sizeof(Node4Q) == 128, "quad node must be 128 bytes");
-void to_quad_layout(const Node128 *in, size_t n, Node4Q *out);
+#define FJB_TOP4_MAX 341         // levels 0..4 of a full 4-wide tree
 
 // The 4-wide tree with child boxes quantised to 8 bits per plane inside the node's own box (64 B per node, two 32-B
 // loads): the closest-hit kernel is bound by the L1 data pipe, which moves 16 B per lane per pass when every lane reads

@@ -69,11 +69,13 @@ struct DMesh {
   float bmag;               // max |coordinate| of the mesh bounds: scales the FP32 slab-test error bound (extend kernel)
   float pad1;
   const float4 *nodes4;     // the same tree as 4-wide 128-B nodes (fj_bvh.h Node128) for the wavefront's k_extend
-  const float4 *nodes4q;    // the 4-wide tree in child-major layout (fj_bvh.h Node4Q) for the quad-per-ray k_extend3
   const float4 *nodesq;     // the 4-wide tree with 8-bit quantised child boxes (fj_bvh.h NodeQ64), null if not representable
   float bmagq, pad2;        // bound magnitude of the decoded planes
   const float *uv;          // per-vertex texture coordinates, 2 floats per vertex (null: uv = 0, fj_mesh.cc:292-297)
   const double *P;          // vertex positions by vertex index (FP64 as given), kept only for meshes with uv: dPdu / dPdv of bump maps
+  const double *tri64v;     // meshes with per-vertex velocity (Mesh::velocity_, src/fj_mesh.h:210): 20 doubles per triangle in leaf
+                            // order — v0 v1 v2, prim_id as bits, velocity0 velocity1 velocity2, pad; tri32 and tri64 are null then
+  const double *vel;        // the velocities by vertex index (only kept next to P, for dPdu / dPdv)
 };
 struct DInstance {
   double inv[12];           // rows 0..2 of MatInverse(matrix): world -> object (fj_object_instance.cc:222-225)
@@ -95,11 +97,11 @@ struct DInstRec {
   const char *nodes4, *nodesq;
   const void *tri;          // tri32 or tri64 packets
   float bmag, bmagq;
-  int32_t tri64, inst;      // packet format, instance index (DScene::inst)
+  int32_t tri64, inst;      // packet format (0 = tri32, 1 = tri64, 2 = tri64v: moving triangles), instance index (DScene::inst)
   const double *motion;     // DInstance::motion
 };
 static_assert(sizeof(DInstRec) == 144, "instance record must be 144 bytes");
-struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; const float4 *nodes4q; const float4 *nodesq; float bmagq, pad2; const DInstRec *irec; };   // TLAS leaf (first,count) -> order[first..] = instance indices
+struct DGroup { const float4 *nodes; const int32_t *order; int32_t ninst; float bmag; const float4 *nodes4; const float4 *nodesq; float bmagq, pad2; const DInstRec *irec; };   // TLAS leaf (first,count) -> order[first..] = instance indices
 struct DShader {
   int32_t kind, do_reflect, do_color_filter, texture;     // texture: 1 + index into DScene::textures, 0 = none
   float diffuse[3], reflect[3], refract[3], emission[3], transmit[3];
@@ -119,6 +121,8 @@ struct DScene {
   const DTexture *textures;
   const DMesh *meshes; const DInstance *inst; const DGroup *groups; const DShader *shaders; const DLight *lights;
   int32_t nmeshes, ninst, ngroups, nshaders, nlights, pad;
+  const double *time_tab;   // the frame's time table (fjgpu_time_table over the shutter): time VALUE of entry k, read only for
+                            // meshes with vertex velocity (rays carry the entry's index)
 };
 struct DCamera { double fwd[12]; double uvx, uvy, znear, zfar; const double *motion; };   // motion: fwd[12] per time-table entry, null = static   // uv_size_ computed on the host (fj_camera.cc:97-101)
 struct DFrame {
@@ -302,6 +306,11 @@ __device__ __noinline__ bool trace_closest(const DScene &sc, int g, const RayD &
           const float4 *tp = mesh->tri32 + 3 * (size_t)(first + k);
           const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
           v0 = mk(a.x, a.y, a.z); v1 = mk(b.x, b.y, b.z); v2 = mk(c.x, c.y, c.z); prim = __float_as_int(a.w);
+        } else if (mesh->tri64v) {                                       // `P0 += time * velocity0`, src/fj_mesh.cc:252-259
+          const double *p = mesh->tri64v + 20 * (size_t)(first + k);
+          const double tm = sc.time_tab[ray.tidx];
+          v0 = mk(p[0], p[1], p[2]) + tm * mk(p[10], p[11], p[12]); v1 = mk(p[3], p[4], p[5]) + tm * mk(p[13], p[14], p[15]);
+          v2 = mk(p[6], p[7], p[8]) + tm * mk(p[16], p[17], p[18]); prim = (int)__double_as_longlong(p[9]);
         } else {
           const double *p = mesh->tri64 + 10 * (size_t)(first + k);
           v0 = mk(p[0], p[1], p[2]); v1 = mk(p[3], p[4], p[5]); v2 = mk(p[6], p[7], p[8]); prim = (int)__double_as_longlong(p[9]);
@@ -433,9 +442,15 @@ __device__ __forceinline__ void hit_derivatives(const DScene &sc, const Hit &h, 
   *dPdu = mk(0, 0, 0); *dPdv = mk(0, 0, 0);
   if (!m.uv || !m.P) return;
   const int i0 = m.idx[3 * (size_t)h.prim], i1 = m.idx[3 * (size_t)h.prim + 1], i2 = m.idx[3 * (size_t)h.prim + 2];
-  const D3 P0 = mk(m.P[3 * (size_t)i0], m.P[3 * (size_t)i0 + 1], m.P[3 * (size_t)i0 + 2]);
-  const D3 P1 = mk(m.P[3 * (size_t)i1], m.P[3 * (size_t)i1 + 1], m.P[3 * (size_t)i1 + 2]);
-  const D3 P2 = mk(m.P[3 * (size_t)i2], m.P[3 * (size_t)i2 + 1], m.P[3 * (size_t)i2 + 2]);
+  D3 P0 = mk(m.P[3 * (size_t)i0], m.P[3 * (size_t)i0 + 1], m.P[3 * (size_t)i0 + 2]);
+  D3 P1 = mk(m.P[3 * (size_t)i1], m.P[3 * (size_t)i1 + 1], m.P[3 * (size_t)i1 + 2]);
+  D3 P2 = mk(m.P[3 * (size_t)i2], m.P[3 * (size_t)i2 + 1], m.P[3 * (size_t)i2 + 2]);
+  if (m.vel) {                  // TriComputeDerivatives sees the vertices where the ray's time put them (fj_mesh.cc:252-259,287-290)
+    const double tm = sc.time_tab[tidx];
+    P0 = P0 + tm * mk(m.vel[3 * (size_t)i0], m.vel[3 * (size_t)i0 + 1], m.vel[3 * (size_t)i0 + 2]);
+    P1 = P1 + tm * mk(m.vel[3 * (size_t)i1], m.vel[3 * (size_t)i1 + 1], m.vel[3 * (size_t)i1 + 2]);
+    P2 = P2 + tm * mk(m.vel[3 * (size_t)i2], m.vel[3 * (size_t)i2 + 1], m.vel[3 * (size_t)i2 + 2]);
+  }
   const float2 t0 = reinterpret_cast<const float2 *>(m.uv)[i0], t1 = reinterpret_cast<const float2 *>(m.uv)[i1], t2 = reinterpret_cast<const float2 *>(m.uv)[i2];
   const D3 dP1 = P1 - P0, dP2 = P2 - P0;
   const float du1 = __fsub_rn(t1.x, t0.x), du2 = __fsub_rn(t2.x, t0.x), dv1 = __fsub_rn(t1.y, t0.y), dv2 = __fsub_rn(t2.y, t0.y);

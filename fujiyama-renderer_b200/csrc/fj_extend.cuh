@@ -1,5 +1,5 @@
 // fj_extend.cuh — k_extend2: the closest-hit kernel of the wavefront with the exact (FP64) half of every ray's state
-// in shared memory.
+// and the traversal stack in shared memory.
 //
 // Same algorithm and results as k_extend (fj_kernels.cuh): persistent threads, one ray per lane, warp-synchronous
 // phases (refill / 4-wide node steps with speculative leaf parking / exact FP64 triangle tests / transitions).
@@ -7,8 +7,19 @@
 // at 5 CTAs/SM) and is bound by latency x occupancy: 5 warps per scheduler cannot cover the dependent-issue latency
 // of the node step, let alone the node fetch.  Here the node loop only carries the FP32 box ray, the
 // stack pointer and the node reference; object-space origin/direction, tmin, the best hit and the triangle pointer
-// (104 B per lane) sit in shared memory, SoA so that a warp's accesses are conflict-free, and are touched only by the
-// triangle and transition phases.  That fits the kernel in 64 registers: 8 CTAs (32 warps) per SM.
+// (84 B per lane) sit in shared memory, SoA so that a warp's accesses are conflict-free, and are touched only by the
+// triangle and transition phases.
+//
+// Round 2: the traversal stack left local memory.  The round-1 kernel kept `int stack[96]` per lane in local memory; ncu
+// counted 150 M local loads + 217 M local stores per launch against 533 M global loads, on an L1 data pipe at 65 % — every
+// lane of a warp sits at a different stack depth, so one STL/LDL touches up to 32 different 128-B lines, and those lines
+// compete with the BVH nodes for L1.  The first SD entries of every lane's stack now live in shared memory as
+// sstack[entry][thread]: whatever the depths, a warp's push or pop is one conflict-free wavefront (bank = lane).  Deeper
+// entries (rare: SD covers the depths a nearest-first walk of a SAH tree reaches) spill to a local array as before.
+//
+// TOP: the first `top_count` nodes of one tree (the BLAS with the most nodes, laid out breadth-first at the front of its
+// node array by fj_bvh.cc) are staged in shared memory once per CTA by ONE bulk copy (cp.async.bulk + mbarrier, SASS
+// UBLKCP): the first levels of every ray's walk through that tree are then LDS instead of L1/L2 round trips.
 #pragma once
 
 #include "fj_kernels.cuh"
@@ -36,6 +47,17 @@ __device__ __forceinline__ F8 ldg256(const void *p) {
   asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
       : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
   return r;
+}
+
+// mbarrier + bulk-copy primitives (TMA, non-tensor form) for the staged tree top
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase) {
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(bar), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // Box ray of the min/max slab test: per axis 1/d and the two FMA constants of the lo and the hi plane,
@@ -72,11 +94,43 @@ __device__ __forceinline__ bool tri_intersect_smem(const D3 &v0, const D3 &v1, c
 }
 
 // Lane state word: what the node loop has to know about the exact half of the state.
-enum { XS_BLAS = 1, XS_WORLD = 2, XS_TRI64 = 4, XS_LEAF = 8, XS_FOUND = 16 };
+enum { XS_BLAS = 1, XS_WORLD = 2, XS_TRI64 = 4, XS_LEAF = 8, XS_FOUND = 16,
+       XS_VEL = 32,      // moving triangles: 160-B packets with per-vertex velocity (Mesh::ray_intersect, src/fj_mesh.cc:252-259)
+       XS_TOP = 64 };    // the tree being walked is the one whose first nodes are staged in shared memory
 
-template <int MINB, bool STATS, bool QUANT, bool COOP = false>
+// One triangle of a leaf for the exact test: 48-B FP32 packet, 80-B FP64 packet, or the 160-B packet of a mesh with vertex
+// velocity, moved to the ray's time as the reference does (`P0 += time * velocity0`, src/fj_mesh.cc:252-259).
+__device__ __forceinline__ void load_leaf_triangle(const RenderArgs &a, const RayRec *rays, const void *tp_, unsigned fmt, unsigned ridx, int index,
+                                                   D3 *v0, D3 *v1, D3 *v2, int *prim) {
+  if (!(fmt & (XS_TRI64 | XS_VEL))) {
+    // 48-B packet, 16-B aligned: one 32-B and one 16-B load, which comes first depends on the packet's parity
+    const unsigned ti = (unsigned)index;
+    const char *tb = (const char *)tp_ + 48 * (size_t)ti;
+    const bool odd = ti & 1u;
+    const float4 s4 = __ldg((const float4 *)(tb + (odd ? 0 : 32)));
+    const F8 w8 = ldg256(tb + (odd ? 16 : 0));
+    const float4 p0 = odd ? s4 : w8.a, p1 = odd ? w8.a : w8.b, p2 = odd ? w8.b : s4;
+    *v0 = mk(p0.x, p0.y, p0.z); *v1 = mk(p1.x, p1.y, p1.z); *v2 = mk(p2.x, p2.y, p2.z); *prim = __float_as_int(p0.w);
+  } else if (!(fmt & XS_VEL)) {
+    const double *q = (const double *)tp_ + 10 * (size_t)index;
+    *v0 = mk(__ldg(q), __ldg(q + 1), __ldg(q + 2)); *v1 = mk(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)); *v2 = mk(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
+    *prim = (int)__double_as_longlong(__ldg(q + 9));
+  } else {
+    const double *q = (const double *)tp_ + 20 * (size_t)index;
+    const double tm = a.sc.time_tab[rays[ridx].key];                  // the ray's time (TraceContext::time): entry `key` of the frame's table
+    *v0 = mk(__ldg(q), __ldg(q + 1), __ldg(q + 2)) + tm * mk(__ldg(q + 10), __ldg(q + 11), __ldg(q + 12));
+    *v1 = mk(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)) + tm * mk(__ldg(q + 13), __ldg(q + 14), __ldg(q + 15));
+    *v2 = mk(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8)) + tm * mk(__ldg(q + 16), __ldg(q + 17), __ldg(q + 18));
+    *prim = (int)__double_as_longlong(__ldg(q + 9));
+  }
+}
+
+template <int MINB, bool STATS, bool QUANT, bool COOP = false, int SD = 12, bool TOP = false>
 __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   __shared__ ExtShared S;
+  __shared__ int sstack[SD][FJ_XT];             // the first SD stack entries of every lane (entry-major: bank = lane)
+  extern __shared__ __align__(128) unsigned char top_smem[];      // TOP: a.top_count staged nodes (64 B each)
+  __shared__ unsigned long long top_bar;
   // COOP: (owner lane | triangle k << 5) of every (ray, triangle) pair of the warp's parked leaves, in owner order
   __shared__ unsigned char pairmap[COOP ? FJ_XT / 32 : 1][COOP ? 256 : 1];
   const unsigned FULL = 0xffffffffu;
@@ -85,7 +139,20 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->count[a.cur ^ 1] = 0;      // the queue k_shade fills next: nobody touches it during this kernel
   const unsigned count = min(a.ctl->count[a.cur], a.capacity);
   const DScene &sc = a.sc;
-  int stack[FJ_STACK4];
+  int lstack[FJ_STACK4 - SD];                   // entries beyond SD (local memory; rarely reached)
+#define XPUSH(V) do { const int v_ = (V); if (sp < SD) sstack[sp][tid] = v_; else lstack[sp - SD] = v_; sp++; } while (0)
+#define XPOP() (--sp, sp < SD ? sstack[sp][tid] : lstack[sp - SD])
+  if (TOP) {                                    // stage the tree top: one bulk copy per CTA, completion on an mbarrier
+    const unsigned bar = smem_u32(&top_bar);
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)a.top_count * 64u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(smem_u32(top_smem), a.top_src, bytes, bar);
+    }
+    mbar_wait(bar, 0);
+  }
   // negative node references that are not leaves: end of a BLAS, end of the traversal, lane without a ray
   const int SENTINEL = (int)0x80000000, DONE = (int)0x80000001, IDLE = (int)0x80000002;
   const unsigned MISS = 0xffffffffu;
@@ -152,8 +219,14 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
         if (QUANT) {
           // 64-B node with 8-bit planes (fj_bvh.h NodeQ64): plane = p + q s, so t(plane) = fma(q, s/d, fma(p, 1/d, c)) — two more
           // roundings of at most 2^-24 (|o| + B) |1/d| each, inside the 2^-20 widening c already carries
-          const char *np = nodes + 64 * (size_t)node;
-          const F8 A = ldg256(np), Q = ldg256(np + 32);
+          F8 A, Q;
+          if (TOP && (st & XS_TOP) && node < a.top_count) {       // staged: four 16-B shared-memory loads
+            const float4 *sn = reinterpret_cast<const float4 *>(top_smem + 64 * (size_t)node);
+            A.a = sn[0]; A.b = sn[1]; Q.a = sn[2]; Q.b = sn[3];
+          } else {
+            const char *np = nodes + 64 * (size_t)node;
+            A = ldg256(np); Q = ldg256(np + 32);
+          }
           const unsigned sw = __float_as_uint(A.a.w);
           const float six = __fmul_rn(__uint_as_float(sw & 0xffff0000u), br.ix), siy = __fmul_rn(__uint_as_float(sw << 16), br.iy);
           const float siz = __fmul_rn(Q.b.z, br.iz);
@@ -201,10 +274,10 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
         if (kmin != MISS) {
           const unsigned w = kmin & 3u;
           int top = -1;
-          if (key0 != MISS && w != 0u) { stack[sp++] = ch.x; top = ch.x; }
-          if (key1 != MISS && w != 1u) { stack[sp++] = ch.y; top = ch.y; }
-          if (key2 != MISS && w != 2u) { stack[sp++] = ch.z; top = ch.z; }
-          if (key3 != MISS && w != 3u) { stack[sp++] = ch.w; top = ch.w; }
+          if (key0 != MISS && w != 0u) { XPUSH(ch.x); top = ch.x; }
+          if (key1 != MISS && w != 1u) { XPUSH(ch.y); top = ch.y; }
+          if (key2 != MISS && w != 2u) { XPUSH(ch.z); top = ch.z; }
+          if (key3 != MISS && w != 3u) { XPUSH(ch.w); top = ch.w; }
           node = (w & 2u) ? ((w & 1u) ? ch.w : ch.z) : ((w & 1u) ? ch.y : ch.x);
           // the traversal is bound by the latency of dependent node fetches: start the fetch of the node that will be popped
           // next (the new stack top) while the nearest child is walked
@@ -213,10 +286,10 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
             if (a.prefetch == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(pa));
             else asm volatile("prefetch.global.L2 [%0];" :: "l"(pa));
           }
-        } else node = sp > 0 ? stack[--sp] : DONE;
+        } else { if (sp > 0) node = XPOP(); else node = DONE; }
         // speculative traversal: park the first triangle leaf and keep descending.  Inside a BLAS the bottom stack entry is
         // SENTINEL, so a negative reference there is SENTINEL or a triangle leaf and the pop below cannot underflow.
-        if (node < 0 && (st & (XS_BLAS | XS_LEAF)) == XS_BLAS && node != SENTINEL) { S.leaf[tid] = node; st |= XS_LEAF; node = stack[--sp]; }
+        if (node < 0 && (st & (XS_BLAS | XS_LEAF)) == XS_BLAS && node != SENTINEL) { S.leaf[tid] = node; st |= XS_LEAF; node = XPOP(); }
       }
     }
 
@@ -248,21 +321,8 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
         bool hit = false; double t = 0, u = 0, v = 0; int prim = 0;
         if (want) {
           const int first = (~S.leaf[otid]) >> 3;
-          const void *tp_ = S.tri[otid];
           D3 v0, v1, v2;
-          if (!(ost & XS_TRI64)) {
-            const unsigned ti = (unsigned)(first + k);
-            const char *tb = (const char *)tp_ + 48 * (size_t)ti;
-            const bool odd = ti & 1u;
-            const float4 s4 = __ldg((const float4 *)(tb + (odd ? 0 : 32)));
-            const F8 w8 = ldg256(tb + (odd ? 16 : 0));
-            const float4 p0 = odd ? s4 : w8.a, p1 = odd ? w8.a : w8.b, p2 = odd ? w8.b : s4;
-            v0 = mk(p0.x, p0.y, p0.z); v1 = mk(p1.x, p1.y, p1.z); v2 = mk(p2.x, p2.y, p2.z); prim = __float_as_int(p0.w);
-          } else {
-            const double *q = (const double *)tp_ + 10 * (size_t)(first + k);
-            v0 = mk(__ldg(q), __ldg(q + 1), __ldg(q + 2)); v1 = mk(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)); v2 = mk(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
-            prim = (int)__double_as_longlong(__ldg(q + 9));
-          }
+          load_leaf_triangle(a, rays, S.tri[otid], ost, S.ridx[otid], first + k, &v0, &v1, &v2, &prim);
           hit = tri_intersect_smem(v0, v1, v2, S, otid, &t, &u, &v);
         }
         // owners fold the hits among their pairs of this round, lowest triangle first
@@ -320,20 +380,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
         if (STATS) n_tris += __popc(wm);
         if (want) {
           D3 v0, v1, v2; int prim;
-          if (!(st & XS_TRI64)) {
-            // 48-B packet, 16-B aligned: one 32-B and one 16-B load, which comes first depends on the packet's parity
-            const unsigned ti = (unsigned)(first + k);
-            const char *tb = (const char *)tp_ + 48 * (size_t)ti;
-            const bool odd = ti & 1u;
-            const float4 s4 = __ldg((const float4 *)(tb + (odd ? 0 : 32)));
-            const F8 w8 = ldg256(tb + (odd ? 16 : 0));
-            const float4 p0 = odd ? s4 : w8.a, p1 = odd ? w8.a : w8.b, p2 = odd ? w8.b : s4;
-            v0 = mk(p0.x, p0.y, p0.z); v1 = mk(p1.x, p1.y, p1.z); v2 = mk(p2.x, p2.y, p2.z); prim = __float_as_int(p0.w);
-          } else {
-            const double *p = (const double *)tp_ + 10 * (size_t)(first + k);
-            v0 = mk(__ldg(p), __ldg(p + 1), __ldg(p + 2)); v1 = mk(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5)); v2 = mk(__ldg(p + 6), __ldg(p + 7), __ldg(p + 8));
-            prim = (int)__double_as_longlong(__ldg(p + 9));
-          }
+          load_leaf_triangle(a, rays, tp_, st, S.ridx[tid], first + k, &v0, &v1, &v2, &prim);
           double t, u, v;
           // RayInRange (src/fj_ray.h:29-32): tmin <= t <= tmax; best_t starts at tmax, so `t <= best_t` is the upper test
           if (tri_intersect_smem(v0, v1, v2, S, tid, &t, &u, &v) && tmin <= t && t <= best_t) {
@@ -368,13 +415,13 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           node = IDLE;
         } else if (node == SENTINEL) {             // the instance's BLAS is done: back to the instance tree (its nodes and box
           st &= ~(XS_BLAS | XS_WORLD);             // ray are fetched again only if an inner node of that tree is still to be visited)
-          node = sp > 0 ? stack[--sp] : DONE;
+          if (sp > 0) node = XPOP(); else node = DONE;
         } else if (st & XS_BLAS) {                 // a second triangle leaf: park it now that the slot is free
-          S.leaf[tid] = node; st |= XS_LEAF; node = stack[--sp];
+          S.leaf[tid] = node; st |= XS_LEAF; node = XPOP();
         } else {                                   // TLAS leaf: enter the first instance, re-queue the others
           const int ref = ~node;
           const int first = ref >> 3, cnt = (ref & 7) + 1;
-          for (int k = cnt - 1; k >= 1; k--) stack[sp++] = ~(((first + k) << 3) | 0);
+          for (int k = cnt - 1; k >= 1; k--) XPUSH(~(((first + k) << 3) | 0));
           const RayRec &r = rays[S.ridx[tid]];
           const DInstRec &in = sc.groups[r.target].irec[first];          // one record: matrix, tree, packets (no order[] -> instance -> mesh chain)
           S.cur_inst[tid] = in.inst;
@@ -384,10 +431,10 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           S.ox[tid] = o.x; S.oy[tid] = o.y; S.oz[tid] = o.z; S.dx[tid] = d.x; S.dy[tid] = d.y; S.dz[tid] = d.z;
           make_box_ray_mm(o, d, QUANT ? in.bmagq : in.bmag, br);
           nodes = QUANT ? in.nodesq : in.nodes4;
-          const bool t64 = in.tri64 != 0;
           S.tri[tid] = in.tri;
-          st = (st & XS_FOUND) | XS_BLAS | (t64 ? XS_TRI64 : 0);
-          stack[sp++] = SENTINEL;
+          st = (st & XS_FOUND) | XS_BLAS | (in.tri64 == 1 ? XS_TRI64 : 0) | (in.tri64 == 2 ? XS_VEL : 0);
+          if (TOP && QUANT && (const void *)in.nodesq == (const void *)a.top_src) st |= XS_TOP;
+          XPUSH(SENTINEL);
           node = 0;
         }
       }
@@ -395,6 +442,8 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   }
   // traversal statistics (4-wide node steps and exact triangle tests) for DESIGN.md / bench.py
   if (STATS && (tid & 31) == 0 && a.counters) { atomicAdd(&a.counters->node_steps, (unsigned long long)n_steps); atomicAdd(&a.counters->tri_tests, (unsigned long long)n_tris); }
+#undef XPUSH
+#undef XPOP
 }
 
 }  // namespace fj

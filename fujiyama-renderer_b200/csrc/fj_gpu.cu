@@ -11,7 +11,6 @@
 #include "fj_build.h"
 #include "fj_kernels.cuh"
 #include "fj_extend.cuh"
-#include "fj_extend_quad.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -34,12 +33,13 @@ struct DevBuf {
 };
 
 struct MeshRec {
-  DevBuf nodes, nodes4, nodes4q, nodesq, tri, N, idx, group, uv, P;
+  DevBuf nodes, nodes4, nodesq, tri, N, idx, group, uv, P, vel;
   std::vector<double> hostP;     // vertex positions kept until fjgpu_mesh_set_uv decides whether the device needs them
   fj::DMesh d;
   double bmin[3], bmax[3];      // exact FP64 bounds of the mesh (Mesh::ComputeBounds, fj_mesh.cc:235-244)
-  int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0, max_depth4 = 0, nnodes4 = 0, stack_need4 = 0;
-  void release() { uv.release(); P.release(); nodes.release(); nodes4.release(); nodes4q.release(); nodesq.release(); tri.release(); N.release(); idx.release(); group.release(); }
+  int32_t nfaces = 0, nverts = 0, nnodes = 0, max_depth = 0, max_depth4 = 0, nnodes4 = 0, stack_need4 = 0, top4 = 0;
+  std::vector<double> hostVel;   // per-vertex velocities (empty: static mesh)
+  void release() { uv.release(); P.release(); vel.release(); nodes.release(); nodes4.release(); nodesq.release(); tri.release(); N.release(); idx.release(); group.release(); }
 };
 
 }  // namespace
@@ -69,14 +69,17 @@ struct fjgpu_context {
 
   // device scene
   DevBuf d_meshes, d_inst, d_groups, d_shaders, d_lights;
-  std::vector<DevBuf> d_group_nodes, d_group_nodes4, d_group_nodes4q, d_group_nodesq, d_group_order, d_group_irec, d_dome;
+  std::vector<DevBuf> d_group_nodes, d_group_nodes4, d_group_nodesq, d_group_order, d_group_irec, d_dome;
   fj::DScene sc;
   std::vector<int> mesh_slot_of_id;   // dense slot per mesh id (map order)
   uint64_t tlas_nodes = 0;
   int tlas_depth4 = 0;
   size_t ctl_off = 0;             // offset of the live QueueCtl inside d_ctl
   bool quant_ok = true;        // every tree of the committed scene has a quantised (NodeQ64) copy
-  int stack_need = 0;          // worst-case traversal stack of k_extend3 for the committed scene (entries)
+  int stack_need = 0;          // worst-case traversal stack of the committed scene (entries)
+  const void *top_src = nullptr; int top_avail = 0;     // NodeQ64 array of the largest tree and the length of its breadth-first front (k_extend2<TOP>)
+  double shutter[2] = {0., 1.};                         // Renderer::SetSampleTimeRange (fjgpu_shutter_set)
+  DevBuf d_timetab; size_t timetab_count = 0; double timetab_range[2] = {0., 0.};
   double build_seconds = 0;
   double device_build_seconds = 0;    // part of build_seconds spent inside fj_device_build (CUDA events)
 
@@ -136,6 +139,7 @@ inline void xpoint(const double *m, const double p[3], double out[3]) {
   for (int r = 0; r < 3; r++) out[r] = m[4 * r] * p[0] + m[4 * r + 1] * p[1] + m[4 * r + 2] * p[2] + m[4 * r + 3];
 }
 
+#define FJGPU_TOP_NODES_DEFAULT 0
 int env_int(const char *name, int def) { const char *s = getenv(name); return s && *s ? atoi(s) : def; }
 
 // ---- scene commit: instances, TLAS per object group, shader/light tables ------------------------
@@ -215,15 +219,16 @@ int commit_scene(fjgpu_context *ctx) {
   const int ngroups = (int)ctx->group_off.size() - 1;
   for (auto &b : ctx->d_group_nodes) b.release();
   for (auto &b : ctx->d_group_nodes4) b.release();
-  for (auto &b : ctx->d_group_nodes4q) b.release();
   for (auto &b : ctx->d_group_nodesq) b.release();
   for (auto &b : ctx->d_group_order) b.release();
   for (auto &b : ctx->d_group_irec) b.release();
   ctx->d_group_irec.assign(std::max(ngroups, 0), DevBuf());
-  ctx->d_group_nodes4q.assign(std::max(ngroups, 0), DevBuf());
   ctx->d_group_nodesq.assign(std::max(ngroups, 0), DevBuf());
   ctx->quant_ok = true;
   for (auto &kv : ctx->meshes) ctx->quant_ok = ctx->quant_ok && kv.second.d.nodesq != nullptr;
+  // the tree whose top k_extend2<TOP> stages in shared memory: the one with the most nodes that has a breadth-first front
+  ctx->top_src = nullptr; ctx->top_avail = 0;
+  { int best = 0; for (auto &kv : ctx->meshes) { const MeshRec &m = kv.second; if (m.top4 > 0 && m.d.nodesq && m.nnodes4 > best) { best = m.nnodes4; ctx->top_src = m.d.nodesq; ctx->top_avail = m.top4; } } }
   ctx->d_group_nodes.assign(std::max(ngroups, 0), DevBuf());
   ctx->d_group_nodes4.assign(std::max(ngroups, 0), DevBuf());
   ctx->d_group_order.assign(std::max(ngroups, 0), DevBuf());
@@ -248,10 +253,6 @@ int commit_scene(fjgpu_context *ctx) {
     if (int rc = dev_upload(ctx, ctx->d_group_nodes4[g], br.nodes4.data(), br.nodes4.size() * sizeof(fjb::Node128), true)) return rc;
     dg[g].nodes4 = (const float4 *)ctx->d_group_nodes4[g].p;
     {
-      std::vector<fjb::Node4Q> q(br.nodes4.size());
-      fjb::to_quad_layout(br.nodes4.data(), br.nodes4.size(), q.data());
-      if (int rc = dev_upload(ctx, ctx->d_group_nodes4q[g], q.data(), q.size() * sizeof(fjb::Node4Q), true)) return rc;
-      dg[g].nodes4q = (const float4 *)ctx->d_group_nodes4q[g].p;
       tlas_need = std::max(tlas_need, br.stack_need4);
       std::vector<fjb::NodeQ64> nq(br.nodes4.size());
       float bq = 0;
@@ -272,7 +273,8 @@ int commit_scene(fjgpu_context *ctx) {
         fj::DInstRec &r = rec[k];
         memcpy(r.inv, in.inv, sizeof r.inv);
         r.nodes4 = (const char *)me.nodes4; r.nodesq = (const char *)me.nodesq;
-        r.tri64 = me.tri32 == nullptr; r.tri = r.tri64 ? (const void *)me.tri64 : (const void *)me.tri32;
+        r.tri64 = me.tri64v ? 2 : (me.tri32 == nullptr ? 1 : 0);
+        r.tri = me.tri64v ? (const void *)me.tri64v : (r.tri64 ? (const void *)me.tri64 : (const void *)me.tri32);
         r.bmag = me.bmag; r.bmagq = me.bmagq; r.inst = order[k]; r.motion = in.motion;
       }
       if (int rc = dev_upload(ctx, ctx->d_group_irec[g], rec.data(), rec.size() * sizeof(fj::DInstRec), true)) return rc;
@@ -343,6 +345,7 @@ struct FramePlan {
   fj::DFrame fr; fj::DCamera cam;
   uint32_t wstride = 0; int bw = 0, bh = 0;
   int tiles_per_batch = 0;
+  size_t budget = 0;                  // bytes the per-batch buffers may take (plan_frame)
   int waves = 1; double peak = 1;     // wavefront: number of extend/shade rounds, worst-case queue records per camera sample in one round
   double factor0 = 1;                 // queue capacity per sample slot the first attempt allocates
 };
@@ -462,13 +465,41 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
     }
     pl->cam.motion = (const double *)ctx->d_cam_motion.p;
   }
+  // meshes with vertex velocity read the time VALUE of a ray's table entry: the frame's table over the shutter, on the device
+  {
+    bool any_vel = false;
+    for (auto &kv : ctx->meshes) any_vel = any_vel || kv.second.d.tri64v != nullptr;
+    if (any_vel) {
+      const size_t need = (size_t)fr.max_ns;
+      if (ctx->timetab_count < need || ctx->timetab_range[0] != ctx->shutter[0] || ctx->timetab_range[1] != ctx->shutter[1]) {
+        std::vector<double> tab(need);
+        fjgpu_tile whole; whole.id = 0; whole.xmin = 0; whole.ymin = 0; whole.xmax = tw; whole.ymax = th;
+        if (fjgpu_time_table(p, &whole, 1, ctx->shutter[0], ctx->shutter[1], tab.data(), (int32_t)need) != (int32_t)need)
+          return fail(ctx, FJGPU_ERR_INVALID, "cannot build the frame's time table");
+        if (int rc = dev_upload(ctx, ctx->d_timetab, tab.data(), need * sizeof(double))) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->timetab_count = need; ctx->timetab_range[0] = ctx->shutter[0]; ctx->timetab_range[1] = ctx->shutter[1];
+      }
+      ctx->sc.time_tab = (const double *)ctx->d_timetab.p;
+    } else ctx->sc.time_tab = nullptr;
+  }
   // batch so the per-batch buffers (accumulators + two ray queues + hit records) stay bounded
   double block = 0;
   frontier(ctx, p, &pl->waves, &pl->peak, &block);
   if (block > 254) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "more than 253 light samples per shading point");
   // ray trees that can branch start optimistic (grown on overflow); shadow-ray blocks are sized for the worst case at once
   pl->factor0 = block > 0 ? pl->peak : std::min(pl->peak, 2.0);
-  const size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 16384) << 20;
+  // budget of the per-batch buffers: FJGPU_SAMPLE_MB (default 16 GiB), never more than 80 % of what the device has free
+  // now plus what this context already holds for the purpose
+  size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 16384) << 20;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t avail = (size_t)(0.8 * (double)(free_b + ctx->d_samples.bytes + ctx->d_queue[0].bytes));
+      cap = std::min(cap, std::max<size_t>(avail, (size_t)64 << 20));
+    }
+  }
+  pl->budget = cap;
   const size_t per_slot = sizeof(fj::Accum) + (size_t)std::ceil(pl->factor0 * (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec)));
   long per = (long)(cap / ((size_t)pl->wstride * per_slot));
   per = std::max(1l, std::min<long>(per, std::max(ntiles, 1)));
@@ -479,77 +510,66 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
 
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
-template <int MINB, bool QUANT, bool COOP = false>
+template <int MINB, bool QUANT, bool COOP, int SD, bool TOP>
 void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
-  // shared-memory carveout: MINB CTAs x (static shared memory + 1 KB the driver reserves per CTA), the rest stays L1
-  static bool configured = false;
-  if (!configured) {
-    int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * (sizeof(fj::ExtShared) + (COOP ? 1024 : 0) + 1024) / (228.0 * 1024)));
+  // shared-memory carveout: MINB CTAs x (static + dynamic shared memory + 1 KB the driver reserves per CTA), the rest stays L1
+  const size_t dyn = TOP ? (size_t)a.top_count * 64 : 0;
+  const size_t per_cta = sizeof(fj::ExtShared) + (size_t)SD * FJ_XT * sizeof(int) + (COOP ? 1024 : 0) + 64 + dyn + 1024;
+  static size_t configured[64] = {0};      // function attributes are per device: one process may drive several GPUs
+  size_t &done = configured[ctx->device & 63];
+  if (done != per_cta) {
+    int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * per_cta / (228.0 * 1024)));
     pct = env_int("FJGPU_CARVEOUT_PCT", pct);
-    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    configured = true;
+    if (dyn) cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    done = per_cta;
   }
-  fj::k_extend2<MINB, true, QUANT, COOP><<<blocks, FJ_XT, 0, ctx->stream>>>(a);
-}
-
-template <int MINB>
-void launch_extend3(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks, int stride) {
-  const size_t dyn = (size_t)FJ_QR * stride * sizeof(int);
-  static size_t configured = 0;
-  if (configured < dyn + 1) {
-    const int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * (sizeof(fj::QuadShared) + dyn + 1024) / (228.0 * 1024)));
-    cudaFuncSetAttribute(fj::k_extend3<MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(fj::k_extend3<MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    configured = dyn + 1;
-  }
-  fj::k_extend3<MINB, true><<<blocks, FJ_QT, dyn, ctx->stream>>>(a, stride);
+  fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP><<<blocks, FJ_XT, dyn, ctx->stream>>>(a);
 }
 
 // The closest-hit kernel of one wavefront round.  FJGPU_EXTEND=1 selects the register-resident first version (kept as
-// a cross-check), 2 (default) the shared-memory-state version, 3 the quad-per-ray experiment; FJGPU_EXTEND_MINBLOCKS = resident CTAs per SM.
+// a cross-check), 2 (default) the shared-memory-state version; FJGPU_EXTEND_MINBLOCKS = resident CTAs per SM,
+// FJGPU_STACK_SMEM = stack entries per lane kept in shared memory (8 / 12 / 16), FJGPU_TOP_NODES = nodes of the largest
+// tree staged in shared memory by one bulk copy per CTA (0 = off).
 void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
   a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
   a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 16)));
   a.park = env_int("FJGPU_PARK", 1);
   a.prefetch = env_int("FJGPU_PREFETCH", 0);
-  int version = env_int("FJGPU_EXTEND", 2);
-  const int stride = std::max(15, ctx->stack_need) | 1;             // odd: the ray stacks start in different banks
-  if (version >= 3 && (size_t)FJ_QR * stride * sizeof(int) > 40 * 1024) version = 2;     // tree too deep for the shared-memory stacks
-  if (version >= 3) {
-    const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 8);
-    const int cap = std::max(1, grid / 4 * minb);
-    if (minb >= 12) launch_extend3<12>(ctx, a, cap, stride);
-    else if (minb >= 10) launch_extend3<10>(ctx, a, cap, stride);
-    else if (minb >= 8) launch_extend3<8>(ctx, a, cap, stride);
-    else launch_extend3<6>(ctx, a, cap, stride);
-    return;
-  }
+  const int version = env_int("FJGPU_EXTEND", 2);
   if (version >= 2) {
     const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 7);
-    const int sms = std::max(1, grid / 4);
     const int cap = std::max(1, grid / 4 * minb);      // `grid` is 4 CTAs per SM worth of work (or fewer for small probes)
-    (void)sms;
     const bool quant = ctx->quant_ok && env_int("FJGPU_QUANT", 1) != 0;
-    if (quant && env_int("FJGPU_COOP", 1) != 0) {       // warp-cooperative exact triangle tests (fj_extend.cuh, phase B1)
-      if (minb >= 8) launch_extend2<8, true, true>(ctx, a, cap);
-      else if (minb == 7) launch_extend2<7, true, true>(ctx, a, cap);
-      else launch_extend2<6, true, true>(ctx, a, cap);
+    const bool coop = quant && env_int("FJGPU_COOP", 1) != 0;       // warp-cooperative exact triangle tests (fj_extend.cuh, phase B1)
+    const int sd = env_int("FJGPU_STACK_SMEM", 12);
+    a.top_src = nullptr; a.top_count = 0;
+    if (quant && coop && ctx->top_src) {
+      const int want = std::min(env_int("FJGPU_TOP_NODES", FJGPU_TOP_NODES_DEFAULT), ctx->top_avail);
+      if (want > 0) { a.top_src = (const char *)ctx->top_src; a.top_count = want; }
+    }
+    if (a.top_count > 0) {                               // staged tree top (TMA bulk copy): 7 or 6 CTAs per SM
+      if (minb >= 7) launch_extend2<7, true, true, 12, true>(ctx, a, cap);
+      else launch_extend2<6, true, true, 16, true>(ctx, a, cap);
+    } else if (coop) {
+      if (minb >= 8) launch_extend2<8, true, true, 8, false>(ctx, a, cap);
+      else if (minb == 7 && sd >= 16) launch_extend2<7, true, true, 16, false>(ctx, a, cap);
+      else if (minb == 7 && sd <= 8) launch_extend2<7, true, true, 8, false>(ctx, a, cap);
+      else if (minb == 7) launch_extend2<7, true, true, 12, false>(ctx, a, cap);
+      else launch_extend2<6, true, true, 16, false>(ctx, a, cap);
     } else if (quant) {
-      if (minb >= 8) launch_extend2<8, true>(ctx, a, cap);
-      else if (minb == 7) launch_extend2<7, true>(ctx, a, cap);
-      else launch_extend2<6, true>(ctx, a, cap);
+      if (minb >= 8) launch_extend2<8, true, false, 8, false>(ctx, a, cap);
+      else if (minb == 7) launch_extend2<7, true, false, 12, false>(ctx, a, cap);
+      else launch_extend2<6, true, false, 16, false>(ctx, a, cap);
     } else {
-      if (minb >= 8) launch_extend2<8, false>(ctx, a, cap);
-      else if (minb == 7) launch_extend2<7, false>(ctx, a, cap);
-      else if (minb == 6) launch_extend2<6, false>(ctx, a, cap);
-      else launch_extend2<5, false>(ctx, a, cap);
+      if (minb >= 7) launch_extend2<7, false, false, 12, false>(ctx, a, cap);
+      else launch_extend2<6, false, false, 16, false>(ctx, a, cap);
     }
     return;
   }
   const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 5);
   const int g = std::max(1, (grid * minb + 3) / 4);
-  if (minb >= 8) fj::k_extend<8><<<g, 128, 0, ctx->stream>>>(a);
-  else if (minb >= 6) fj::k_extend<6><<<g, 128, 0, ctx->stream>>>(a);
+  if (minb >= 6) fj::k_extend<6><<<g, 128, 0, ctx->stream>>>(a);
   else if (minb == 5) fj::k_extend<5><<<g, 128, 0, ctx->stream>>>(a);
   else fj::k_extend<4><<<grid, 128, 0, ctx->stream>>>(a);
 }
@@ -577,7 +597,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
 
   if (int rc = dev_upload(ctx, ctx->d_tiles, tiles, (size_t)ntiles * sizeof(fjgpu_tile))) return rc;
   if (int rc = dev_alloc(ctx, ctx->d_samples, (size_t)pl.tiles_per_batch * pl.wstride * sizeof(fj::Accum))) return rc;
-  if (int rc = dev_alloc(ctx, ctx->d_counters, sizeof(fj::DCounters) + 64)) return rc;
+  if (int rc = dev_alloc(ctx, ctx->d_counters, 2 * sizeof(fj::DCounters) + 64)) return rc;      // live counters, work counter, snapshot at the batch start
   if (int rc = dev_alloc(ctx, ctx->d_ctl, (size_t)4 << 20)) return rc;      // own 2-MB pages; the live QueueCtl sits at ctl_off inside
   // The queue counters get an allocation of their own and sit at its start.  Measured, not yet explained: k_shade, whose
   // every warp takes its output slots with one atomicAdd on QueueCtl::count, runs the north-star frame in 61.5-62.8 ms when
@@ -613,8 +633,9 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   // ray-queue capacity: optimistic when the ray tree can branch, grown on overflow up to the worst case
   double factor = pl.factor0;
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  for (int b0 = 0; b0 < ntiles; b0 += pl.tiles_per_batch) {
-    const int nb = std::min(pl.tiles_per_batch, ntiles - b0);
+  int per_batch = pl.tiles_per_batch;           // shrinks when an overflowed ray queue is grown (the budget stays)
+  for (int b0 = 0, nb = 0; b0 < ntiles; b0 += nb) {
+    nb = std::min(per_batch, ntiles - b0);
     fj::RenderArgs a;
     memset(&a, 0, sizeof a);
     a.sc = ctx->sc; a.cam = pl.cam; a.fr = pl.fr;
@@ -622,6 +643,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
     a.accum = (fj::Accum *)ctx->d_samples.p;
     a.counters = (fj::DCounters *)ctx->d_counters.p;
     a.work = (unsigned long long *)((char *)ctx->d_counters.p + sizeof(fj::DCounters));
+    void *const counters_snapshot = (char *)ctx->d_counters.p + sizeof(fj::DCounters) + 64;
     if (mega) {
       CK(cudaMemsetAsync(a.work, 0, 8, ctx->stream));
       cudaEvent_t e0 = pool_event(ctx, &evn), e1 = pool_event(ctx, &evn);
@@ -633,12 +655,18 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
       CK(cudaEventRecord(e1, ctx->stream));
       ev_extend.push_back(e0); ev_extend.push_back(e1);
     } else {
+      // what the earlier batches counted: restored if this batch has to be rendered again with a larger queue
+      if (factor < pl.peak) CK(cudaMemcpyAsync(counters_snapshot, ctx->d_counters.p, sizeof(fj::DCounters), cudaMemcpyDeviceToDevice, ctx->stream));
       for (;;) {      // retried with a larger queue only if a branching ray tree overflowed the optimistic capacity
         const double want = (double)nb * pl.wstride * factor;
         if (want > 4.0e9) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray tree too wide for one tile's ray queue");
         // chunked slot reservation (fj_kernels.cuh, QueueSink): every k_shade warp may leave up to FJ_QCHUNK + FJ_QRESERVE
         // reserved slots as fillers, on top of the records the ray tree can produce
-        const bool chunked = !has_plastic && env_int("FJGPU_QUEUE_CHUNK", 1) != 0;
+        bool moving = !ctx->cam_motion.empty();            // RayRec::key carries the time-table entry then: no sorting
+        for (auto &kv : ctx->inst_motion) moving = moving || !kv.second.empty();
+        const int sort_bits = pl.waves > 1 && !moving ? std::min(7, std::max(0, env_int("FJGPU_SORT_BITS", 0))) : 0;
+        // (the RAY_DEAD fillers of a chunked queue are not filed under a sort key: sorting takes one atomic per spawn)
+        const bool chunked = !has_plastic && sort_bits == 0 && env_int("FJGPU_QUEUE_CHUNK", 1) != 0;
         // grid of the k_shade variant without plastic shaders: resident CTAs per SM (template parameter) x CTAs per slot
         const int shade_env = env_int("FJGPU_SHADE_MINBLOCKS", 5), shade_per = std::max(1, env_int("FJGPU_SHADE_CTAS", 2));
         const int shade_smb = shade_env >= 8 ? 8 : (shade_env >= 6 ? 6 : 5);
@@ -655,9 +683,6 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         a.queue[0] = (fj::RayRec *)ctx->d_queue[0].p; a.queue[1] = (fj::RayRec *)((char *)ctx->d_queue[0].p + qbytes + pad);
         a.hits = (fj::HitRec *)((char *)ctx->d_queue[0].p + 2 * (qbytes + pad));
         a.ctl = (fj::QueueCtl *)ctl_p; a.capacity = (uint32_t)capacity; a.cur = 0;
-        bool moving = !ctx->cam_motion.empty();            // RayRec::key carries the time-table entry then: no sorting
-        for (auto &kv : ctx->inst_motion) moving = moving || !kv.second.empty();
-        const int sort_bits = pl.waves > 1 && !moving ? std::min(7, std::max(0, env_int("FJGPU_SORT_BITS", 0))) : 0;
         a.hist = nullptr; a.perm = nullptr; a.sort_bits = sort_bits; a.sort_bins = 8u << (3 * sort_bits);
         if (sort_bits > 0) {
           if (int rc = dev_alloc(ctx, ctx->d_hist, ((size_t)a.sort_bins + 1) * 4)) return rc;
@@ -715,9 +740,14 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         CK(cudaStreamSynchronize(ctx->stream));
         if (!hctl.overflow) break;
         factor = std::min(pl.peak, factor * 4.0);
-        // the batch is rendered again from scratch: discard what the overflowed attempt counted
-        CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(fj::DCounters), ctx->stream));
-        if (b0 > 0) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray queue overflow after the first batch");
+        {
+          const size_t per_slot = sizeof(fj::Accum) + (size_t)std::ceil(factor * (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec)));
+          per_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)per_batch, pl.budget / ((size_t)pl.wstride * per_slot)));
+          nb = std::min(per_batch, ntiles - b0); a.ntiles = nb;
+        }
+        // this batch is rendered again from scratch with the larger queue (later batches keep it): discard what the
+        // overflowed attempt counted, keep what the batches before it did
+        CK(cudaMemcpyAsync(ctx->d_counters.p, counters_snapshot, sizeof(fj::DCounters), cudaMemcpyDeviceToDevice, ctx->stream));
       }
     }
     if (mode != OUT_SAMPLES_ONLY) {
@@ -803,7 +833,6 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &kv : ctx->meshes) kv.second.release();
   for (auto &b : ctx->d_group_nodes) b.release();
   for (auto &b : ctx->d_group_nodes4) b.release();
-  for (auto &b : ctx->d_group_nodes4q) b.release();
   for (auto &b : ctx->d_group_nodesq) b.release();
   for (auto &b : ctx->d_group_order) b.release();
   for (auto &b : ctx->d_group_irec) b.release();
@@ -813,7 +842,7 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &kv : ctx->d_inst_motion) kv.second.release();
   ctx->d_cam_motion.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
-                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl, &ctx->d_hist, &ctx->d_perm};
+                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_timetab, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl, &ctx->d_hist, &ctx->d_perm};
   for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
   for (DevBuf *b : all) b->release();
   if (ctx->h_blocks) cudaFreeHost(ctx->h_blocks);
@@ -822,19 +851,47 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   delete ctx;
 }
 
+static int mesh_upload_impl(fjgpu_context *ctx, int32_t mesh_id, const double *P, const double *N, int32_t nverts,
+                            const int32_t *idx3, const int32_t *face_group_id, int32_t nfaces, const double *vel);
+
 int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, const double *N, int32_t nverts,
                       const int32_t *idx3, const int32_t *face_group_id, int32_t nfaces) {
+  return fjgpu_mesh_upload_velocity(ctx, mesh_id, P, N, nverts, idx3, face_group_id, nfaces, nullptr);
+}
+
+int fjgpu_shutter_set(fjgpu_context *ctx, double time_start, double time_end) {
+  if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
+  if (!(time_start <= time_end)) return fail(ctx, FJGPU_ERR_INVALID, "shutter: time_start must not exceed time_end");      // assert of src/fj_renderer.cc:528
+  ctx->shutter[0] = time_start; ctx->shutter[1] = time_end;
+  return FJGPU_OK;
+}
+
+int fjgpu_mesh_upload_velocity(fjgpu_context *ctx, int32_t mesh_id, const double *P, const double *N, int32_t nverts,
+                               const int32_t *idx3, const int32_t *face_group_id, int32_t nfaces, const double *vel) {
   if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
   if (nverts < 0 || nfaces < 0 || (nverts > 0 && !P) || (nfaces > 0 && !idx3)) return fail(ctx, FJGPU_ERR_INVALID, "bad mesh arrays");
   if (nfaces >= (1 << 28)) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "more than 2^28 faces in one mesh");
   for (size_t i = 0; i < 3 * (size_t)nfaces; i++)
     if (idx3[i] < 0 || idx3[i] >= nverts) return fail(ctx, FJGPU_ERR_INVALID, "face index out of range");
+  const int rc = mesh_upload_impl(ctx, mesh_id, P, N, nverts, idx3, face_group_id, nfaces, vel);
+  if (rc != FJGPU_OK) {      // no half-built record stays behind: a later commit would hand freed or null arrays to the kernels
+    auto it = ctx->meshes.find(mesh_id);
+    if (it != ctx->meshes.end()) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); it->second.release(); ctx->meshes.erase(it); }
+    ctx->dirty = true;
+  }
+  return rc;
+}
+
+static int mesh_upload_impl(fjgpu_context *ctx, int32_t mesh_id, const double *P, const double *N, int32_t nverts,
+                            const int32_t *idx3, const int32_t *face_group_id, int32_t nfaces, const double *vel) {
   CK(cudaSetDevice(ctx->device));
   const auto t0 = std::chrono::steady_clock::now();
   MeshRec &m = ctx->meshes[mesh_id];
   m.release();
   m.nfaces = nfaces; m.nverts = nverts;
   m.hostP.assign(P, P + 3 * (size_t)nverts);
+  m.hostVel.clear(); m.top4 = 0;
+  if (vel && nverts > 0) m.hostVel.assign(vel, vel + 3 * (size_t)nverts);
   bool f32ok = true;
   for (size_t i = 0; i < 3 * (size_t)nverts && f32ok; i++) f32ok = ((double)(float)P[i] == P[i]);
   if (env_int("FJGPU_FORCE_TRI64", 0)) f32ok = false;
@@ -842,7 +899,7 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
   // default because its trees are walked faster; the device builder is for time-to-first-pixel on large meshes.
   {
     const char *bm = getenv("FJGPU_BUILD");
-    if (bm && std::string(bm) == "device" && nfaces >= env_int("FJGPU_BUILD_DEVICE_MIN", 1024)) {
+    if (bm && std::string(bm) == "device" && nfaces >= env_int("FJGPU_BUILD_DEVICE_MIN", 1024) && !vel) {      // (moving triangles: host builder)
       DevBuf dP;
       if (int rc = dev_upload(ctx, dP, P, (size_t)nverts * 24)) return rc;
       if (int rc = dev_upload(ctx, m.idx, idx3, (size_t)nfaces * 12, true)) { dP.release(); return rc; }
@@ -851,15 +908,15 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
                                       (float)env_int("FJGPU_LEAF_COST_X10", 15) / 10.f, env_int("FJGPU_FORCE_TRI64", 0) != 0, &db, &berr);
       dP.release();
       if (brc == 0 && (db.max_depth + 8 > FJ_STACK || 3 * db.max_depth4 + 16 > FJ_STACK4)) {     // too deep for the traversal stacks: host build
-        for (void *q : {db.nodes, db.nodes4, db.nodes4q, db.nodesq, db.tri}) cudaFree(q);
+        for (void *q : {db.nodes, db.nodes4, db.nodesq, db.tri}) cudaFree(q);
       } else if (brc == 0) {
         m.nodes.p = db.nodes; m.nodes.bytes = db.nodes_bytes; m.nodes4.p = db.nodes4; m.nodes4.bytes = db.nodes4_bytes;
-        m.nodes4q.p = db.nodes4q; m.nodes4q.bytes = db.nodes4q_bytes; m.nodesq.p = db.nodesq; m.nodesq.bytes = db.nodesq_bytes;
+        m.nodesq.p = db.nodesq; m.nodesq.bytes = db.nodesq_bytes;
         m.tri.p = db.tri; m.tri.bytes = db.tri_bytes;
         for (int a = 0; a < 3; a++) { m.bmin[a] = db.bmin[a]; m.bmax[a] = db.bmax[a]; }
         m.nnodes = db.nnodes; m.max_depth = db.max_depth; m.max_depth4 = db.max_depth4; m.nnodes4 = db.nnodes4; m.stack_need4 = db.stack_need4;
         memset(&m.d, 0, sizeof m.d);
-        m.d.nodes = (const float4 *)m.nodes.p; m.d.nodes4 = (const float4 *)m.nodes4.p; m.d.nodes4q = (const float4 *)m.nodes4q.p;
+        m.d.nodes = (const float4 *)m.nodes.p; m.d.nodes4 = (const float4 *)m.nodes4.p;
         if (db.quant_ok) { m.d.nodesq = (const float4 *)m.nodesq.p; m.d.bmagq = db.bmagq; }
         if (db.tri64) m.d.tri64 = (const double *)m.tri.p; else m.d.tri32 = (const float4 *)m.tri.p;
         if (N) { if (int rc = dev_upload(ctx, m.N, N, (size_t)nverts * 24, true)) return rc; m.d.N = (const double *)m.N.p; }
@@ -883,6 +940,10 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
     for (int a = 0; a < 3; a++) {
       const double x = P[3 * (size_t)idx3[3 * f] + a], y = P[3 * (size_t)idx3[3 * f + 1] + a], z = P[3 * (size_t)idx3[3 * f + 2] + a];
       lo[a] = std::min(x, std::min(y, z)); hi[a] = std::max(x, std::max(y, z));
+      if (vel) {      // Mesh::get_primitive_bounds, src/fj_mesh.cc:420-439: the bounds also hold the vertices at time 1 (`P + velocity`);
+                      // a vertex moves on a straight line, so every time in [0, 1] — the shutter the reference bounds for — is inside
+        for (int v = 0; v < 3; v++) { const size_t vi = 3 * (size_t)idx3[3 * f + v] + a; const double q = P[vi] + vel[vi]; lo[a] = std::min(lo[a], q); hi[a] = std::max(hi[a], q); }
+      }
       m.bmin[a] = std::min(m.bmin[a], lo[a]); m.bmax[a] = std::max(m.bmax[a], hi[a]);
     }
     pad_box(lo, hi, &boxes[f]);
@@ -893,16 +954,10 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
   if (br.max_depth + 8 > FJ_STACK || 3 * br.max_depth4 + 16 > FJ_STACK4) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
   if (int rc = dev_upload(ctx, m.nodes, br.nodes.data(), br.nodes.size() * sizeof(fjb::Node64), true)) return rc;
   if (int rc = dev_upload(ctx, m.nodes4, br.nodes4.data(), br.nodes4.size() * sizeof(fjb::Node128), true)) return rc;
-  m.max_depth4 = br.max_depth4; m.nnodes4 = (int32_t)br.nodes4.size(); m.stack_need4 = br.stack_need4;
-  {
-    std::vector<fjb::Node4Q> q(br.nodes4.size());
-    fjb::to_quad_layout(br.nodes4.data(), br.nodes4.size(), q.data());
-    if (int rc = dev_upload(ctx, m.nodes4q, q.data(), q.size() * sizeof(fjb::Node4Q), true)) return rc;
-  }
+  m.max_depth4 = br.max_depth4; m.nnodes4 = (int32_t)br.nodes4.size(); m.stack_need4 = br.stack_need4; m.top4 = br.top_count4;
   memset(&m.d, 0, sizeof m.d);
   m.d.nodes = (const float4 *)m.nodes.p;
   m.d.nodes4 = (const float4 *)m.nodes4.p;
-  m.d.nodes4q = (const float4 *)m.nodes4q.p;
   {
     std::vector<fjb::NodeQ64> nq(br.nodes4.size());
     float bq = 0;
@@ -912,7 +967,20 @@ int fjgpu_mesh_upload(fjgpu_context *ctx, int32_t mesh_id, const double *P, cons
     }
   }
   const size_t nt = br.order.size();
-  if (f32ok) {
+  if (vel) {      // moving triangles: v0 v1 v2, face id, velocity0 velocity1 velocity2, pad (20 doubles, fj_device.cuh DMesh::tri64v)
+    std::vector<double> tri(std::max<size_t>(nt, 1) * 20, 0.);
+    for (size_t k = 0; k < nt; k++) {
+      const int f = br.order[k];
+      for (int v = 0; v < 3; v++) for (int a = 0; a < 3; a++) {
+        tri[20 * k + 3 * v + a] = P[3 * (size_t)idx3[3 * f + v] + a];
+        tri[20 * k + 10 + 3 * v + a] = vel[3 * (size_t)idx3[3 * f + v] + a];
+      }
+      const long long fl = f; memcpy(&tri[20 * k + 9], &fl, 8);
+    }
+    if (int rc = dev_upload(ctx, m.tri, tri.data(), tri.size() * 8, true)) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    m.d.tri64v = (const double *)m.tri.p;
+  } else if (f32ok) {
     std::vector<float> tri(std::max<size_t>(nt, 1) * 12, 0.f);
     for (size_t k = 0; k < nt; k++) {
       const int f = br.order[k];
@@ -1076,13 +1144,18 @@ int fjgpu_mesh_set_uv(fjgpu_context *ctx, int32_t mesh_id, const float *uv2, int
   if (it == ctx->meshes.end()) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_mesh_set_uv: unknown mesh_id");
   MeshRec &m = it->second;
   CK(cudaSetDevice(ctx->device));
-  if (!uv2) { m.uv.release(); m.P.release(); m.d.uv = nullptr; m.d.P = nullptr; ctx->dirty = true; return FJGPU_OK; }
+  if (!uv2) { m.uv.release(); m.P.release(); m.vel.release(); m.d.uv = nullptr; m.d.P = nullptr; m.d.vel = nullptr; ctx->dirty = true; return FJGPU_OK; }
   if (nverts != m.nverts) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_mesh_set_uv: vertex count differs from the uploaded mesh");
   if (int rc = dev_upload(ctx, m.uv, uv2, (size_t)nverts * 8, true)) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   if (int rc = dev_upload(ctx, m.P, m.hostP.data(), m.hostP.size() * 8, true)) return rc;       // dPdu / dPdv of bump maps need the vertices by index
   CK(cudaStreamSynchronize(ctx->stream));
   m.d.uv = (const float *)m.uv.p; m.d.P = (const double *)m.P.p;
+  if (!m.hostVel.empty()) {
+    if (int rc = dev_upload(ctx, m.vel, m.hostVel.data(), m.hostVel.size() * 8, true)) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    m.d.vel = (const double *)m.vel.p;
+  }
   ctx->dirty = true;
   return FJGPU_OK;
 }
@@ -1191,7 +1264,7 @@ int fjgpu_scene_info_get(fjgpu_context *ctx, fjgpu_scene_info *info) {
   memset(info, 0, sizeof *info);
   for (auto &kv : ctx->meshes) {
     const MeshRec &m = kv.second;
-    info->hbm_bytes += m.nodes.bytes + m.nodes4.bytes + m.nodes4q.bytes + m.nodesq.bytes + m.tri.bytes + m.N.bytes + m.idx.bytes + m.group.bytes;
+    info->hbm_bytes += m.nodes.bytes + m.nodes4.bytes + m.nodesq.bytes + m.tri.bytes + m.N.bytes + m.idx.bytes + m.group.bytes;
     info->blas_nodes += m.nnodes; info->blas_tris += m.nfaces;
     info->blas_max_depth = std::max<uint32_t>(info->blas_max_depth, (uint32_t)m.max_depth);
   }
@@ -1208,12 +1281,11 @@ int fjgpu_scene_resend(fjgpu_context *ctx, uint64_t *bytes_sent) {
   CK(cudaSetDevice(ctx->device));
   if (int rc = commit_scene(ctx)) return rc;
   std::vector<DevBuf *> all = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights};
-  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.nodes4q, &m.nodesq, &m.tri, &m.N, &m.idx, &m.group, &m.uv, &m.P}) all.push_back(b); }
+  for (auto &kv : ctx->meshes) { MeshRec &m = kv.second; for (DevBuf *b : {&m.nodes, &m.nodes4, &m.nodesq, &m.tri, &m.N, &m.idx, &m.group, &m.uv, &m.P, &m.vel}) all.push_back(b); }
   for (auto &b : ctx->d_tex_tiles) all.push_back(&b);
   all.push_back(&ctx->d_textures);
   for (auto &b : ctx->d_group_nodes) all.push_back(&b);
   for (auto &b : ctx->d_group_nodes4) all.push_back(&b);
-  for (auto &b : ctx->d_group_nodes4q) all.push_back(&b);
   for (auto &b : ctx->d_group_nodesq) all.push_back(&b);
   for (auto &b : ctx->d_group_order) all.push_back(&b);
   for (auto &b : ctx->d_group_irec) all.push_back(&b);

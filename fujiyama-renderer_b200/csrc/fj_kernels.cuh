@@ -399,6 +399,7 @@ struct RenderArgs {
   RayRec *queue[2]; HitRec *hits; QueueCtl *ctl; uint32_t capacity; int cur;     // wavefront
   int refill, phase_a_min, park;          // k_extend scheduling: refill / phase-A thresholds (lanes), speculative leaf parking
   int prefetch;                           // k_extend2: 1 = prefetch the new stack top into L1, 2 = into L2, 0 = off
+  const char *top_src; int top_count;     // k_extend2<TOP>: the NodeQ64 array whose first top_count nodes are staged in shared memory
   int chunked;                            // k_shade without plastic shaders: warps reserve queue slots in chunks (QueueSink)
   // ray sorting between bounces: counting sort of the next queue by (direction octant | origin cell)
   unsigned int *hist;                     // sort_bins + 1 counters (null = no sorting)
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
   BoxRay32 br; br.ix = br.iy = br.iz = br.nx = br.ny = br.nz = br.fx = br.fy = br.fz = 0.f;
   int oct = 0;                                  // direction signs of the current box ray (bit a: 1/d[a] < 0)
   const float4 *nodes = nullptr, *tlas = nullptr; const int32_t *order = nullptr; float tlas_B = 0;
-  const float4 *tri32 = nullptr; const double *tri64 = nullptr;
+  const float4 *tri32 = nullptr; const double *tri64 = nullptr, *tri64v = nullptr;
 
   for (;;) {
     // ---- refill idle lanes from the queue head
@@ -658,6 +659,11 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
             const float4 *tp = tri32 + 3 * (size_t)(first + k);
             const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
             v0 = mk(p0.x, p0.y, p0.z); v1 = mk(p1.x, p1.y, p1.z); v2 = mk(p2.x, p2.y, p2.z); prim = __float_as_int(p0.w);
+          } else if (tri64v) {                                       // `P0 += time * velocity0`, src/fj_mesh.cc:252-259
+            const double *p = tri64v + 20 * (size_t)(first + k);
+            const double tm = sc.time_tab[rays[ridx].key];
+            v0 = mk(p[0], p[1], p[2]) + tm * mk(p[10], p[11], p[12]); v1 = mk(p[3], p[4], p[5]) + tm * mk(p[13], p[14], p[15]);
+            v2 = mk(p[6], p[7], p[8]) + tm * mk(p[16], p[17], p[18]); prim = (int)__double_as_longlong(p[9]);
           } else {
             const double *p = tri64 + 10 * (size_t)(first + k);
             v0 = mk(p[0], p[1], p[2]); v1 = mk(p[3], p[4], p[5]); v2 = mk(p[6], p[7], p[8]); prim = (int)__double_as_longlong(p[9]);
@@ -698,7 +704,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const RenderArgs a) {
           const DMesh &m = sc.meshes[in.mesh];
           make_box_ray32(o, d, m.bmag, br); oct = box_octant(br);
           br_world = false;
-          nodes = m.nodes4; tri32 = m.tri32; tri64 = m.tri64;
+          nodes = m.nodes4; tri32 = m.tri32; tri64 = m.tri64; tri64v = m.tri64v;
           in_blas = true;
           stack[sp++] = SENTINEL;
           node = 0;
@@ -845,6 +851,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
     const unsigned i = i0 + lane;
     const bool valid = i < count;
     if (wc) {                               // top the warp's slot reservation up to FJ_QRESERVE free slots
+      __syncwarp();                         // every lane has finished the spawns of the previous iteration (they bump wc->used)
       if (lane == 0 && wc->alloc - wc->used < FJ_QRESERVE) {
         wc->base[(wc->alloc / FJ_QCHUNK) & 1u] = atomicAdd(&a.ctl->count[a.cur ^ 1], FJ_QCHUNK);
         wc->alloc += FJ_QCHUNK;

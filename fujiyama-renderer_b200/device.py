@@ -60,7 +60,7 @@ class Device:
             raise FjGpuError(rc, (self.lib.fjgpu_last_error(self.ctx) or b"").decode())
 
     # ---- scene
-    def mesh(self, mesh_id, P, N, idx, group=None):
+    def mesh(self, mesh_id, P, N, idx, group=None, velocity=None):
         P = np.ascontiguousarray(P, np.float64)
         idx = np.ascontiguousarray(idx, np.int32).reshape(-1)
         Np = None
@@ -71,14 +71,23 @@ class Device:
         if group is not None:
             group = np.ascontiguousarray(group, np.int32)
             gp = _ip(group)
+        if velocity is not None:      # Mesh::velocity_: moving triangles (fjgpu_mesh_upload_velocity)
+            velocity = np.ascontiguousarray(velocity, np.float64)
+            assert velocity.shape == P.shape
+            self._ck(self.lib.fjgpu_mesh_upload_velocity(self.ctx, mesh_id, _dp(P), Np, len(P), _ip(idx), gp, len(idx) // 3, _dp(velocity)))
+            return
         self._ck(self.lib.fjgpu_mesh_upload(self.ctx, mesh_id, _dp(P), Np, len(P), _ip(idx), gp, len(idx) // 3))
 
     def load_structs(self, st):
         """`st`: the flat struct dict (meshes, instances, group_offsets/ids, shaders, lights, camera)."""
-        if st.get("velocity_meshes"):
-            raise FjGpuError(-1, "per-vertex velocity (mesh motion blur) has no device implementation yet")
+        vel = st.get("mesh_velocity", {})
+        for mid in st.get("velocity_meshes", []):
+            if mid not in vel:
+                raise FjGpuError(-1, "mesh %d is marked as moving but carries no velocities (st['mesh_velocity'])" % mid)
         for mid, P, N, idx in st["meshes"]:
-            self.mesh(mid, P, N, idx)
+            self.mesh(mid, P, N, idx, velocity=vel.get(mid))
+        t0, t1 = st.get("time_range", (0.0, 1.0))
+        self._ck(self.lib.fjgpu_shutter_set(self.ctx, float(t0), float(t1)))
         for mid, uv in st.get("mesh_uv", {}).items():
             uv = np.ascontiguousarray(uv, np.float32)
             self._ck(self.lib.fjgpu_mesh_set_uv(self.ctx, mid, uv.ctypes.data_as(C.POINTER(C.c_float)), len(uv)))

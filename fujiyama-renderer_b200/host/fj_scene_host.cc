@@ -551,7 +551,6 @@ Status flatten(Scene &sc, const Renderer &r, Flat *f) {
     const Instance &o = sc.instances[i]; fjgpu_instance &d = f->inst[i];
     memset(&d, 0, sizeof d);
     int t, mi; decode_id(o.mesh, &t, &mi); d.mesh_id = mi;
-    if (!sc.meshes[mi].vel.empty()) return failmsg("per-vertex velocity (mesh motion blur) has no device implementation yet");
     for (int g = 0; g < FJGPU_MAX_SHADING_GROUPS; g++) d.shader_of_group[g] = -1;
     // ObjectInstance::AddShader / GetShader, src/fj_object_instance.cc:160-191: the mesh of this path has one
     // shading group ("" = DEFAULT_SHADING_GROUP -> slot 0)
@@ -621,8 +620,10 @@ Status render(Scene &sc, Renderer &r) {
   for (size_t i = 0; i < sc.meshes.size(); i++) {
     Mesh &m = sc.meshes[i];
     if (!m.dirty) continue;
-    if (fjgpu_mesh_upload(sc.gpu, (int32_t)i, m.P.data(), m.N.empty() ? nullptr : m.N.data(), (int32_t)(m.P.size() / 3), m.idx.data(), nullptr,
-                          (int32_t)(m.idx.size() / 3)) != FJGPU_OK) return failmsg(std::string("fjgpu_mesh_upload: ") + fjgpu_last_error(sc.gpu));
+    // a mesh VelocityGeneratorProcedure ran on carries its velocities: moving triangles (Mesh::ray_intersect, src/fj_mesh.cc:252-259)
+    if (fjgpu_mesh_upload_velocity(sc.gpu, (int32_t)i, m.P.data(), m.N.empty() ? nullptr : m.N.data(), (int32_t)(m.P.size() / 3), m.idx.data(), nullptr,
+                                   (int32_t)(m.idx.size() / 3), m.vel.empty() ? nullptr : m.vel.data()) != FJGPU_OK)
+      return failmsg(std::string("fjgpu_mesh_upload: ") + fjgpu_last_error(sc.gpu));
     if (!m.uv.empty() && fjgpu_mesh_set_uv(sc.gpu, (int32_t)i, m.uv.data(), (int32_t)(m.uv.size() / 2)) != FJGPU_OK)
       return failmsg(std::string("fjgpu_mesh_set_uv: ") + fjgpu_last_error(sc.gpu));
     m.dirty = false;
@@ -634,6 +635,7 @@ Status render(Scene &sc, Renderer &r) {
     sc.textures_dirty = false;
   }
   int rc = fjgpu_shaders_set(sc.gpu, (int32_t)f.shaders.size(), f.shaders.data());
+  if (!rc) rc = fjgpu_shutter_set(sc.gpu, r.time_range[0], r.time_range[1]);      // Renderer::SetSampleTimeRange
   if (!rc) rc = fjgpu_groups_set(sc.gpu, (int32_t)f.goff.size() - 1, f.goff.data(), f.gids.data());
   if (!rc) rc = fjgpu_instances_set(sc.gpu, (int32_t)f.inst.size(), f.inst.data());
   if (!rc) rc = fjgpu_lights_set(sc.gpu, (int32_t)f.lights.size(), f.lights.data());

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FJGPU_API_VERSION 1
+#define FJGPU_API_VERSION 2
 
 enum {
   FJGPU_OK = 0,
@@ -191,6 +191,20 @@ int fjgpu_time_table(const fjgpu_render_params *params, const fjgpu_tile *tiles,
                      double time_start, double time_end, double *times, int32_t cap);
 int fjgpu_instance_motion_set(fjgpu_context *ctx, int32_t instance, int32_t ntimes, const double *fwd16, const double *inv16);
 int fjgpu_camera_motion_set(fjgpu_context *ctx, int32_t ntimes, const double *fwd16);
+
+/* ---- motion blur, second half: per-vertex velocity ----------------------------------------
+ * Mesh::velocity_ (src/fj_mesh.h:210; written by VelocityGeneratorProcedure): Mesh::ray_intersect tests the triangle where
+ * the ray's time puts it, `P0 += time * velocity0` (src/fj_mesh.cc:252-259), the primitive and mesh bounds also hold the
+ * vertices at time 1 (src/fj_mesh.cc:420-439) and the shading normal stays the mesh's (:273-276).
+ * fjgpu_mesh_upload_velocity = fjgpu_mesh_upload + `velocity` (nverts*3 doubles; NULL = static mesh): the triangle packets
+ * carry the velocities, the BVH bounds both ends (host builder), and rays read the time VALUE of their table entry.
+ * fjgpu_shutter_set = Renderer::SetSampleTimeRange (src/fj_renderer.cc:526-532; default 0, 1): the range the frame's time
+ * table (fjgpu_time_table) is drawn over.  The reference's bounds — and therefore these — cover times in [0, 1]. */
+int fjgpu_mesh_upload_velocity(fjgpu_context *ctx, int32_t mesh_id,
+                               const double *P, const double *N, int32_t nverts,
+                               const int32_t *idx3, const int32_t *face_group_id, int32_t nfaces,
+                               const double *velocity);
+int fjgpu_shutter_set(fjgpu_context *ctx, double time_start, double time_end);
 
 typedef struct fjgpu_stats {
   uint64_t rays_camera, rays_shadow, rays_diffuse, rays_reflect, rays_refract;

@@ -191,7 +191,7 @@ class SceneDesc:
     def __init__(self):
         self.meshes = []      # (name, P float32 [V,3], idx int32 [F,3], ply_path or None)
         self.mesh_uv = {}     # name -> uv float32 [V,2] (PLY properties uv1 / uv2)
-        self.mesh_velocity = set()   # names of meshes the reference's VelocityGeneratorProcedure runs on (oracle-only so far)
+        self.mesh_velocity = set()   # names of meshes the reference's VelocityGeneratorProcedure runs on
         self.textures = []    # (name, image float32 [H,W,C]) written as .mip; shaders refer to them by name in the
                               # `texture` (constant) / `diffuse_map` (plastic, pathtracing) property
         self.shaders = []     # (name, kind str, props dict)
@@ -384,6 +384,17 @@ class SceneDesc:
             meshes.append((mid, P64, N64, idx))
         out["meshes"] = meshes
         out["velocity_meshes"] = sorted(mesh_ids[n] for n in self.mesh_velocity)
+        # what VelocityGeneratorProcedure writes on those meshes: from the oracle's restatement of the generator, which is
+        # pinned on vectors dumped from the reference (tests/test_oracle_golden.py); libfjscene's own copy is held to it too
+        out["mesh_velocity"] = {}
+        for mid in out["velocity_meshes"]:
+            _, P64, N64, idx = meshes[mid]
+            tmp = o.fjo_scene_new()
+            o.fjo_mesh(tmp, mid, dptr(P64), dptr(N64), len(P64), iptr(idx), None, len(idx) // 3)
+            vel = np.zeros_like(P64)
+            assert o.fjo_mesh_generate_velocity(tmp, mid, dptr(vel)) == 0
+            o.fjo_scene_free(tmp)
+            out["mesh_velocity"][mid] = vel
         out["mesh_uv"] = {mesh_ids[n]: uv for n, uv in self.mesh_uv.items()}
         # textures: the tile arrays a .mip file of the image holds (synth.write_mip), as fjgpu_texture structs
         tex_ids = {}
@@ -530,12 +541,13 @@ def oracle_scene(st):
     return sc
 
 
-def oracle_render(desc, rng_mode=0, threads=8, region=None, st=None):
-    """Renders with the oracle.  Returns (image [H,W,4] float32, Stats)."""
+def oracle_render(desc, rng_mode=0, threads=8, region=None, st=None, tiles=None):
+    """Renders with the oracle.  Returns (image [H,W,4] float32, Stats).  `tiles`: explicit (id, xmin, ymin, xmax, ymax)
+    list — e.g. a subset of the full frame's tiles WITH their full-frame ids (the counter RNG is keyed by tile id)."""
     a = _abi()
     st = st or desc.to_structs()
     sc = oracle_scene(st)
-    tiles = desc.tiles(region)
+    tiles = tiles if tiles is not None else desc.tiles(region)
     ta = SceneDesc.tile_array(tiles)
     p = st["params"]
     img = np.zeros((p.yres, p.xres, 4), np.float32)

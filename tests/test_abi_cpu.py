@@ -67,7 +67,7 @@ def test_no_cpu_fallback(lib):
     rc = lib.fjgpu_create(0, C.byref(ctx))
     assert rc == -3 and not ctx.value                  # FJGPU_ERR_NO_DEVICE
     assert b"no CPU fallback" in lib.fjgpu_last_error(None)
-    assert lib.fjgpu_api_version() == 1
+    assert lib.fjgpu_api_version() == 2
     from fujiyama_renderer_b200 import device
     with pytest.raises(device.FjGpuError):
         device.Device(0)

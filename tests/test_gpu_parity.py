@@ -140,7 +140,7 @@ def test_sample_positions_bit_exact(sk, device):
     dev.close()
 
 
-@pytest.mark.parametrize("name", ["plastic", "pt_branching", "grid_light", "sphere_light", "motion_blur"])
+@pytest.mark.parametrize("name", ["plastic", "pt_branching", "grid_light", "sphere_light", "motion_blur", "velocity_blur"])
 def test_tile_samples_match_oracle(sk, device, name):
     """Per-sample radiance before the pixel filter (Sample::data), same counter RNG on both sides."""
     desc = golden_scenes.SCENES[name]()
@@ -178,7 +178,7 @@ def test_frame_matches_oracle(sk, device, name):
     assert stats.kernel_launches >= 2
 
 
-@pytest.mark.parametrize("name", ["plastic_4l", "multi", "pt_branching", "sphere_light", "motion_blur"])
+@pytest.mark.parametrize("name", ["plastic_4l", "multi", "pt_branching", "sphere_light", "motion_blur", "velocity_blur"])
 @pytest.mark.parametrize("flags", [1, 2])
 def test_megakernel_cross_check(sk, device, name, flags):
     """The two independent device implementations (wavefront rounds over ray queues vs one sample per lane with a
@@ -250,6 +250,48 @@ def test_batching_is_invisible(sk, device, monkeypatch):
     b, sb = gpu_render(device, desc, st)
     assert np.array_equal(a, b)
     assert sb.kernel_launches > 2
+
+
+def test_queue_overflow_in_a_later_batch_grows_and_retries(sk, device, monkeypatch):
+    """A branching ray tree (diffuse + mirror + refracted lobes: up to 3 children per hit) starts with an optimistic queue of
+    2 records per sample slot.  With tiny tile batches the first batches see only background — they fit — and the overflow
+    happens in a LATER batch: that batch alone is rendered again with a larger queue, the earlier batches' ray counts are
+    kept, and the frame equals the single-batch frame bit for bit (round 1 failed such frames)."""
+    desc = sk.scene_blob_pathtracing(n=24, res=(128, 160), rate=4, reflect=(.3, .3, .3), refract=(.4, .4, .4))
+    desc.cam.update(T=(0, 1.6, 4.5))                   # the blob sits in the lower half of the frame: the top tile rows are background
+    st = desc.to_structs()
+    a, sa = gpu_render(device, desc, st)
+    ref, rstats = sk.oracle_render(desc, rng_mode=0, threads=8, st=st)
+    _, tstats = sk.oracle_render(desc, rng_mode=0, threads=8, st=st, tiles=desc.tiles()[:4])
+    assert tstats.rays_reflect == 0 and tstats.rays_refract == 0      # the first tile row sees only the shell: one child per hit, no overflow
+    assert rstats.rays_reflect > 0 and rstats.rays_refract > 0
+    monkeypatch.setenv("FJGPU_SAMPLE_MB", "1")         # one or two tiles per batch
+    b, sb = gpu_render(device, desc, st)
+    assert np.array_equal(a, b)
+    for k in ("rays_camera", "rays_diffuse", "rays_reflect", "rays_refract", "camera_samples", "rays_hit"):
+        assert getattr(sa, k) == getattr(sb, k) == getattr(rstats, k), k
+    assert sb.kernel_launches > sa.kernel_launches
+    assert rmse(b, ref).max() < RMSE_BAR
+
+
+def test_failed_mesh_upload_leaves_no_record(sk, device):
+    """A mesh upload that fails (face index out of range is caught before anything is touched; a too-deep tree after the
+    record exists) must not leave a half-built mesh behind: the scene still renders and the id can be uploaded again."""
+    desc = golden_scenes.SCENES["cube_c1"]()
+    st = desc.to_structs()
+    dev = device.Device(0)
+    dev.load_structs(st)
+    ref, _ = dev.render(st["params"], desc.tiles())
+    mid, P, N, idx = st["meshes"][0]
+    bad = idx.copy(); bad[0] = len(P) + 5
+    with pytest.raises(device.FjGpuError):
+        dev.mesh(mid, P, N, bad)
+    img, _ = dev.render(st["params"], desc.tiles())     # the earlier, valid upload is untouched
+    assert np.array_equal(img, ref)
+    dev.mesh(mid, P, N, idx)
+    img, _ = dev.render(st["params"], desc.tiles())
+    assert np.array_equal(img, ref)
+    dev.close()
 
 
 def test_resident_and_device_block_outputs(sk, device):
@@ -355,10 +397,20 @@ EXTEND_VARIANTS = {
     "v2_quantised_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "0", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
     "v2_cooperative_leaves": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "1"},
     "v2_cooperative_leaves_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "1", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
+    # shared-memory traversal stack of 8 / 16 entries per lane (default 12; deeper entries spill to local memory: the soup's
+    # overlapping boxes do reach them)
+    "v2_stack_smem_8": {"FJGPU_STACK_SMEM": "8"},
+    "v2_stack_smem_16": {"FJGPU_STACK_SMEM": "16"},
+    # the top of the largest tree staged in shared memory by one cp.async.bulk per CTA (7 and 6 CTAs per SM)
+    "v2_top_staged_64": {"FJGPU_TOP_NODES": "64"},
+    "v2_top_staged_341": {"FJGPU_TOP_NODES": "341", "FJGPU_EXTEND_MINBLOCKS": "6"},
     "v2_unchunked_queue": {"FJGPU_QUEUE_CHUNK": "0"},
-    "v3_quad_per_ray": {"FJGPU_EXTEND": "3"},
-    "v3_quad_per_ray_12": {"FJGPU_EXTEND": "3", "FJGPU_EXTEND_MINBLOCKS": "12", "FJGPU_REFILL": "32", "FJGPU_PHASE_A_MIN": "32"},
+    # rays of the next queue sorted by (direction octant, origin cell) between bounces (frames only; the probe has no bounces)
+    "v2_sorted_rays": {"FJGPU_SORT_BITS": "4"},
+    "v2_sorted_rays_unchunked": {"FJGPU_SORT_BITS": "3", "FJGPU_QUEUE_CHUNK": "0"},
 }
+VARIANT_KEYS = ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK",
+                "FJGPU_STACK_SMEM", "FJGPU_TOP_NODES", "FJGPU_SORT_BITS")
 
 
 @pytest.mark.parametrize("scene", ["multi", "instanced16", "soup"])
@@ -386,7 +438,7 @@ def test_extend_variants_bit_exact(sk, device, scene, monkeypatch):
     dev.load_structs(st)
     try:
         for name, env in EXTEND_VARIANTS.items():
-            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK"):
+            for k in VARIANT_KEYS:
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
@@ -400,14 +452,14 @@ def test_extend_variants_bit_exact(sk, device, scene, monkeypatch):
         dev.close()
 
 
-@pytest.mark.parametrize("name", ["multi", "pt_branching", "motion_blur"])
+@pytest.mark.parametrize("name", ["multi", "pt_branching", "motion_blur", "velocity_blur"])
 def test_extend_variants_same_frame(sk, device, name, monkeypatch):
     """Whole frames (shadow rays, mirror bounces, branching path trees) are bit-identical whichever extend kernel traces
     them, and so are the ray counts."""
     desc = golden_scenes.SCENES[name]()
     frames = {}
     for vname, env in EXTEND_VARIANTS.items():
-        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK"):
+        for k in VARIANT_KEYS:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -467,13 +519,13 @@ def test_device_built_bvh_gives_the_same_hits_and_frames(sk, device, scene, monk
             assert same.mean() > 0.999
             assert np.array_equal(u[same], ru[same]) and np.array_equal(v[same], rv[same])
         for name, env in EXTEND_VARIANTS.items():
-            for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK"):
+            for k in VARIANT_KEYS:
                 monkeypatch.delenv(k, raising=False)
             for k, v_ in env.items():
                 monkeypatch.setenv(k, v_)
             t, u, v, p, i = dev.trace_closest(0, o, d, tmin, tmax, 0)
             assert np.array_equal(i, ri) and np.array_equal(t, rt), name
-        for k in ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK"):
+        for k in VARIANT_KEYS:
             monkeypatch.delenv(k, raising=False)
         img_dev, stats_dev = dev.render(st["params"], desc.tiles())
     finally:

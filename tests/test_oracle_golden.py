@@ -179,13 +179,12 @@ def test_frames_match_reference(sk, images, name):
     assert stats.rays_camera == stats.camera_samples
 
 
-@pytest.mark.parametrize("name", list(golden_scenes.ORACLE_ONLY))
-def test_oracle_only_frames_match_reference(sk, images, name):
-    """Rows the device does not render yet (per-vertex velocity): the oracle's restatement is already pinned on the
-    reference's frame, in both RNG modes (the scenes are deterministic)."""
-    ref = images[name]
+def test_velocity_frames_match_reference(sk, images):
+    """Per-vertex velocity: the oracle's restatement (moving triangles, swept grid cells, Perlin-noise velocities) against
+    the reference's frame in both RNG modes (the scene is deterministic), and the velocities do move the picture."""
+    ref = images["velocity_blur"]
     for mode, threads in ((1, 1), (0, 4)):
-        img, stats = sk.oracle_render(golden_scenes.ORACLE_ONLY[name](), rng_mode=mode, threads=threads)
+        img, stats = sk.oracle_render(golden_scenes.SCENES["velocity_blur"](), rng_mode=mode, threads=threads)
         assert img.shape == ref.shape
         assert np.all(np.abs(img - ref) <= _fb_tol(ref)), float(np.abs(img - ref).max())
     static, _ = sk.oracle_render(golden_scenes.SCENES["multi"](), rng_mode=0, threads=4)
