@@ -76,7 +76,9 @@ class Stats(C.Structure):
                 ("node_steps", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("trace_launches", C.c_uint64),
                 ("ms_trace", C.c_float), ("ms_resolve", C.c_float),
-                ("ms_total", C.c_float), ("ms_shade", C.c_float)]
+                ("ms_total", C.c_float), ("ms_shade", C.c_float),
+                ("batches", C.c_uint32), ("queue_regrows", C.c_uint32),
+                ("first_regrow_batch", C.c_int32), ("_pad", C.c_uint32)]
 
     @property
     def rays(self):

@@ -634,8 +634,10 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   double factor = pl.factor0;
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   int per_batch = pl.tiles_per_batch;           // shrinks when an overflowed ray queue is grown (the budget stays)
+  uint32_t n_batches = 0, n_regrows = 0; int32_t first_regrow = -1;
   for (int b0 = 0, nb = 0; b0 < ntiles; b0 += nb) {
     nb = std::min(per_batch, ntiles - b0);
+    n_batches++;
     fj::RenderArgs a;
     memset(&a, 0, sizeof a);
     a.sc = ctx->sc; a.cam = pl.cam; a.fr = pl.fr;
@@ -740,6 +742,8 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         CK(cudaStreamSynchronize(ctx->stream));
         if (!hctl.overflow) break;
         factor = std::min(pl.peak, factor * 4.0);
+        if (first_regrow < 0) first_regrow = (int32_t)n_batches - 1;
+        n_regrows++;
         {
           const size_t per_slot = sizeof(fj::Accum) + (size_t)std::ceil(factor * (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec)));
           per_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)per_batch, pl.budget / ((size_t)pl.wstride * per_slot)));
@@ -789,6 +793,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
     for (size_t i = 0; i + 1 < ev_shade.size(); i += 2) { cudaEventElapsedTime(&t, ev_shade[i], ev_shade[i + 1]); ms_shade += t; }
     for (size_t i = 0; i + 1 < ev_resolve.size(); i += 2) { cudaEventElapsedTime(&t, ev_resolve[i], ev_resolve[i + 1]); ms_resolve += t; }
     stats->kernel_launches = launches; stats->trace_launches = ev_extend.size() / 2;
+    stats->batches = n_batches; stats->queue_regrows = n_regrows; stats->first_regrow_batch = first_regrow;
     stats->ms_trace = ms_trace; stats->ms_shade = ms_shade; stats->ms_resolve = ms_resolve; stats->ms_total = tot;
   }
   return 0;

@@ -219,6 +219,10 @@ typedef struct fjgpu_stats {
   float    ms_resolve;              /* device time of the pixel-filter kernels */
   float    ms_total;                /* device time of the whole call incl. copies */
   float    ms_shade;                /* device time of the generate + shade kernels */
+  uint32_t batches;                 /* tile batches the frame was rendered in (per-batch buffers are bounded: FJGPU_SAMPLE_MB) */
+  uint32_t queue_regrows;           /* batches rendered again because a branching ray tree overflowed the optimistic ray queue */
+  int32_t  first_regrow_batch;      /* index of the first such batch, -1 if none */
+  uint32_t _pad;
 } fjgpu_stats;
 
 /* Renders `ntiles` tiles (sampler -> camera rays -> trace/shade -> Gaussian resolve), i.e. the

@@ -262,15 +262,14 @@ def test_queue_overflow_in_a_later_batch_grows_and_retries(sk, device, monkeypat
     st = desc.to_structs()
     a, sa = gpu_render(device, desc, st)
     ref, rstats = sk.oracle_render(desc, rng_mode=0, threads=8, st=st)
-    _, tstats = sk.oracle_render(desc, rng_mode=0, threads=8, st=st, tiles=desc.tiles()[:4])
-    assert tstats.rays_reflect == 0 and tstats.rays_refract == 0      # the first tile row sees only the shell: one child per hit, no overflow
     assert rstats.rays_reflect > 0 and rstats.rays_refract > 0
+    assert sa.batches == 1 and sa.queue_regrows == 1 and sa.first_regrow_batch == 0      # one batch: the overflow is in batch 0
     monkeypatch.setenv("FJGPU_SAMPLE_MB", "1")         # one or two tiles per batch
     b, sb = gpu_render(device, desc, st)
     assert np.array_equal(a, b)
     for k in ("rays_camera", "rays_diffuse", "rays_reflect", "rays_refract", "camera_samples", "rays_hit"):
         assert getattr(sa, k) == getattr(sb, k) == getattr(rstats, k), k
-    assert sb.kernel_launches > sa.kernel_launches
+    assert sb.batches > 4 and sb.queue_regrows >= 1 and sb.first_regrow_batch > 0        # the case round 1 refused
     assert rmse(b, ref).max() < RMSE_BAR
 
 
