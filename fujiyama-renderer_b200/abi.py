@@ -102,7 +102,7 @@ FJGPU_SYMBOLS = [
     "fjgpu_render_tiles_resident", "fjgpu_trace_closest", "fjgpu_render_tile_samples",
     "fjgpu_scene_info_get", "fjgpu_scene_resend", "fjgpu_textures_set", "fjgpu_mesh_set_uv",
     "fjgpu_time_table", "fjgpu_instance_motion_set", "fjgpu_camera_motion_set",
-    "fjgpu_mesh_upload_velocity", "fjgpu_shutter_set",
+    "fjgpu_mesh_upload_velocity", "fjgpu_shutter_set", "fjgpu_assemble_frame", "fjgpu_render_frame_multi",
 ]
 
 _P = C.POINTER
@@ -133,6 +133,8 @@ def _proto(lib):
     lib.fjgpu_camera_motion_set.argtypes = [vp, i32, f64p]
     lib.fjgpu_mesh_upload_velocity.argtypes = [vp, i32, f64p, f64p, i32, i32p, i32p, i32, f64p]
     lib.fjgpu_shutter_set.argtypes = [vp, C.c_double, C.c_double]
+    lib.fjgpu_assemble_frame.argtypes = [vp, vp, i32, i32, i32, _P(Tile), i32, i32, i32, vp]
+    lib.fjgpu_render_frame_multi.argtypes = [_P(vp), i32, _P(RenderParams), _P(Tile), i32, _P(C.c_float), _P(Stats)]
     return lib
 
 

@@ -125,7 +125,21 @@ __device__ __forceinline__ void load_leaf_triangle(const RenderArgs &a, const Ra
   }
 }
 
-template <int MINB, bool STATS, bool QUANT, bool COOP = false, int SD = 12, bool TOP = false>
+// MAGIC: the 24 byte -> float conversions of a quantised node step without the conversion unit.  `I2F.U8` issues to the XU
+// pipe (16 lanes per clock per SM; ncu: the busiest execution pipe of this kernel at 45 %); here one PRMT drops the byte into
+// the mantissa of 0.5 (bits 16-23: 0.5 + q / 256, exact) and the node's FMA constants absorb the offset:
+//   q s' + b  =  (0.5 + q / 256) (256 s') + (b - 128 s'),   b' = fma(-128, s', b) rounded once: <= 2^-24 (|b| + 128 |s'|)
+// — one more rounding of the size the 2^-20 widening of the box ray already covers (fj_kernels.cuh box_axis).
+// pop: the shared-memory load is unconditional (clamped index), the local-memory entry replaces it in the rare deep case
+template <int SD>
+__device__ __forceinline__ int xpop_(const int (*sstack)[FJ_XT], const int *lstack, int &sp, int tid) {
+  --sp;
+  int v = sstack[min(sp, SD - 1)][tid];
+  if (sp >= SD) v = lstack[sp - SD];
+  return v;
+}
+
+template <int MINB, bool STATS, bool QUANT, bool COOP = false, int SD = 12, bool TOP = false, bool MAGIC = false>
 __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   __shared__ ExtShared S;
   __shared__ int sstack[SD][FJ_XT];             // the first SD stack entries of every lane (entry-major: bank = lane)
@@ -141,7 +155,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   const DScene &sc = a.sc;
   int lstack[FJ_STACK4 - SD];                   // entries beyond SD (local memory; rarely reached)
 #define XPUSH(V) do { const int v_ = (V); if (sp < SD) sstack[sp][tid] = v_; else lstack[sp - SD] = v_; sp++; } while (0)
-#define XPOP() (--sp, sp < SD ? sstack[sp][tid] : lstack[sp - SD])
+#define XPOP() xpop_<SD>(sstack, lstack, sp, tid)
   if (TOP) {                                    // stage the tree top: one bulk copy per CTA, completion on an mbarrier
     const unsigned bar = smem_u32(&top_bar);
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -228,29 +242,36 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
             A = ldg256(np); Q = ldg256(np + 32);
           }
           const unsigned sw = __float_as_uint(A.a.w);
-          const float six = __fmul_rn(__uint_as_float(sw & 0xffff0000u), br.ix), siy = __fmul_rn(__uint_as_float(sw << 16), br.iy);
-          const float siz = __fmul_rn(Q.b.z, br.iz);
+          float six = __fmul_rn(__uint_as_float(sw & 0xffff0000u), br.ix), siy = __fmul_rn(__uint_as_float(sw << 16), br.iy);
+          float siz = __fmul_rn(Q.b.z, br.iz);
           // near / far plane by direction sign, resolved once per node on the packed words (not per child, and not by min/max:
           // unused slots hold an inverted box that must stay a miss).  br.l* / br.h* are the constants of the lo / hi plane.
           const bool gx = br.ix < 0.f, gy = br.iy < 0.f, gz = br.iz < 0.f;
-          const float bnx = fmaf(A.a.x, br.ix, gx ? br.hx : br.lx), bfx = fmaf(A.a.x, br.ix, gx ? br.lx : br.hx);
-          const float bny = fmaf(A.a.y, br.iy, gy ? br.hy : br.ly), bfy = fmaf(A.a.y, br.iy, gy ? br.ly : br.hy);
-          const float bnz = fmaf(A.a.z, br.iz, gz ? br.hz : br.lz), bfz = fmaf(A.a.z, br.iz, gz ? br.lz : br.hz);
+          float bnx = fmaf(A.a.x, br.ix, gx ? br.hx : br.lx), bfx = fmaf(A.a.x, br.ix, gx ? br.lx : br.hx);
+          float bny = fmaf(A.a.y, br.iy, gy ? br.hy : br.ly), bfy = fmaf(A.a.y, br.iy, gy ? br.ly : br.hy);
+          float bnz = fmaf(A.a.z, br.iz, gz ? br.hz : br.lz), bfz = fmaf(A.a.z, br.iz, gz ? br.lz : br.hz);
+          if (MAGIC) {      // bytes enter as 0.5 + q / 256: scale by 256, take 128 s' off the bases
+            bnx = fmaf(-128.f, six, bnx); bfx = fmaf(-128.f, six, bfx); six = __fmul_rn(six, 256.f);
+            bny = fmaf(-128.f, siy, bny); bfy = fmaf(-128.f, siy, bfy); siy = __fmul_rn(siy, 256.f);
+            bnz = fmaf(-128.f, siz, bnz); bfz = fmaf(-128.f, siz, bfz); siz = __fmul_rn(siz, 256.f);
+          }
           const unsigned qlx = __float_as_uint(A.b.x), qhx = __float_as_uint(A.b.y), qly = __float_as_uint(A.b.z), qhy = __float_as_uint(A.b.w);
           const unsigned qlz = __float_as_uint(Q.a.x), qhz = __float_as_uint(Q.a.y);
           const unsigned qnx = gx ? qhx : qlx, qfx = gx ? qlx : qhx, qny = gy ? qhy : qly, qfy = gy ? qly : qhy, qnz = gz ? qhz : qlz, qfz = gz ? qlz : qhz;
           ch = make_int4(__float_as_int(Q.a.z), __float_as_int(Q.a.w), __float_as_int(Q.b.x), __float_as_int(Q.b.y));
+#define FJ_Q2F(W, K) (MAGIC ? __uint_as_float(__byte_perm((W), 0x3F000000u, 0x7044u + 0x100u * K)) : (float)(((W) >> (8 * K)) & 255u))
 #define FJ_CHILD(KEY, K)                                                                                                        \
           {                                                                                                                        \
-            const float nx_ = fmaf((float)((qnx >> (8 * K)) & 255u), six, bnx), fx_ = fmaf((float)((qfx >> (8 * K)) & 255u), six, bfx); \
-            const float ny_ = fmaf((float)((qny >> (8 * K)) & 255u), siy, bny), fy_ = fmaf((float)((qfy >> (8 * K)) & 255u), siy, bfy); \
-            const float nz_ = fmaf((float)((qnz >> (8 * K)) & 255u), siz, bnz), fz_ = fmaf((float)((qfz >> (8 * K)) & 255u), siz, bfz); \
+            const float nx_ = fmaf(FJ_Q2F(qnx, K), six, bnx), fx_ = fmaf(FJ_Q2F(qfx, K), six, bfx);                               \
+            const float ny_ = fmaf(FJ_Q2F(qny, K), siy, bny), fy_ = fmaf(FJ_Q2F(qfy, K), siy, bfy);                               \
+            const float nz_ = fmaf(FJ_Q2F(qnz, K), siz, bnz), fz_ = fmaf(FJ_Q2F(qfz, K), siz, bfz);                               \
             const float nr = fmaxf(fmaxf(nx_, ny_), fmaxf(nz_, tn));                                                              \
             const float fr_ = fminf(fminf(fx_, fy_), fminf(fz_, tf));                                                             \
             KEY = nr <= fr_ ? ((__float_as_uint(nr) & ~3u) | K##u) : MISS;                                                        \
           }
           FJ_CHILD(key0, 0) FJ_CHILD(key1, 1) FJ_CHILD(key2, 2) FJ_CHILD(key3, 3)
 #undef FJ_CHILD
+#undef FJ_Q2F
         } else {
         // 4-wide node: lo.x[4] hi.x[4] | lo.y[4] hi.y[4] | lo.z[4] hi.z[4] | child[4] — three 32-B loads and one 16-B load
         const char *np = nodes + 128 * (size_t)node;
@@ -273,19 +294,23 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
         const unsigned kmin = min(min(key0, key1), min(key2, key3));
         if (kmin != MISS) {
           const unsigned w = kmin & 3u;
-          int top = -1;
-          if (key0 != MISS && w != 0u) { XPUSH(ch.x); top = ch.x; }
-          if (key1 != MISS && w != 1u) { XPUSH(ch.y); top = ch.y; }
-          if (key2 != MISS && w != 2u) { XPUSH(ch.z); top = ch.z; }
-          if (key3 != MISS && w != 3u) { XPUSH(ch.w); top = ch.w; }
-          node = (w & 2u) ? ((w & 1u) ? ch.w : ch.z) : ((w & 1u) ? ch.y : ch.x);
-          // the traversal is bound by the latency of dependent node fetches: start the fetch of the node that will be popped
-          // next (the new stack top) while the nearest child is walked
-          if (a.prefetch && top >= 0) {
-            const char *pa = nodes + (QUANT ? 64 : 128) * (size_t)top;
-            if (a.prefetch == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(pa));
-            else asm volatile("prefetch.global.L2 [%0];" :: "l"(pa));
+          const bool p0 = key0 != MISS && w != 0u, p1 = key1 != MISS && w != 1u, p2 = key2 != MISS && w != 2u, p3 = key3 != MISS && w != 3u;
+          if (sp + 3 <= SD) {                    // (almost always) up to three predicated shared-memory stores, no branches
+            if (p0) sstack[sp][tid] = ch.x;
+            sp += p0;
+            if (p1) sstack[sp][tid] = ch.y;
+            sp += p1;
+            if (p2) sstack[sp][tid] = ch.z;
+            sp += p2;
+            if (p3) sstack[sp][tid] = ch.w;
+            sp += p3;
+          } else {
+            if (p0) XPUSH(ch.x);
+            if (p1) XPUSH(ch.y);
+            if (p2) XPUSH(ch.z);
+            if (p3) XPUSH(ch.w);
           }
+          node = (w & 2u) ? ((w & 1u) ? ch.w : ch.z) : ((w & 1u) ? ch.y : ch.x);
         } else { if (sp > 0) node = XPOP(); else node = DONE; }
         // speculative traversal: park the first triangle leaf and keep descending.  Inside a BLAS the bottom stack entry is
         // SENTINEL, so a negative reference there is SENTINEL or a triangle leaf and the pop below cannot underflow.

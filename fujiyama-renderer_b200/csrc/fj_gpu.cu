@@ -18,8 +18,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -89,6 +91,7 @@ struct fjgpu_context {
   std::vector<cudaEvent_t> evpool;
   size_t jitter_count = 0;
   float *h_blocks = nullptr; size_t h_blocks_bytes = 0;
+  DevBuf d_multi_send, d_multi_recv;     // fjgpu_render_frame_multi: this context's tile blocks / the all-gathered blocks of every rank
 };
 
 namespace {
@@ -140,6 +143,7 @@ inline void xpoint(const double *m, const double p[3], double out[3]) {
 }
 
 #define FJGPU_TOP_NODES_DEFAULT 0
+#define FJGPU_MAGIC_DEFAULT 0
 int env_int(const char *name, int def) { const char *s = getenv(name); return s && *s ? atoi(s) : def; }
 
 // ---- scene commit: instances, TLAS per object group, shader/light tables ------------------------
@@ -510,7 +514,7 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
 
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
-template <int MINB, bool QUANT, bool COOP, int SD, bool TOP>
+template <int MINB, bool QUANT, bool COOP, int SD, bool TOP, bool MAGIC = false>
 void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   // shared-memory carveout: MINB CTAs x (static + dynamic shared memory + 1 KB the driver reserves per CTA), the rest stays L1
   const size_t dyn = TOP ? (size_t)a.top_count * 64 : 0;
@@ -520,11 +524,11 @@ void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   if (done != per_cta) {
     int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * per_cta / (228.0 * 1024)));
     pct = env_int("FJGPU_CARVEOUT_PCT", pct);
-    if (dyn) cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (dyn) cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, MAGIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, MAGIC>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     done = per_cta;
   }
-  fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP><<<blocks, FJ_XT, dyn, ctx->stream>>>(a);
+  fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, MAGIC><<<blocks, FJ_XT, dyn, ctx->stream>>>(a);
 }
 
 // The closest-hit kernel of one wavefront round.  FJGPU_EXTEND=1 selects the register-resident first version (kept as
@@ -535,7 +539,6 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
   a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
   a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 16)));
   a.park = env_int("FJGPU_PARK", 1);
-  a.prefetch = env_int("FJGPU_PREFETCH", 0);
   const int version = env_int("FJGPU_EXTEND", 2);
   if (version >= 2) {
     const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 7);
@@ -555,6 +558,7 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
       if (minb >= 8) launch_extend2<8, true, true, 8, false>(ctx, a, cap);
       else if (minb == 7 && sd >= 16) launch_extend2<7, true, true, 16, false>(ctx, a, cap);
       else if (minb == 7 && sd <= 8) launch_extend2<7, true, true, 8, false>(ctx, a, cap);
+      else if (minb == 7 && env_int("FJGPU_MAGIC", FJGPU_MAGIC_DEFAULT) != 0) launch_extend2<7, true, true, 12, false, true>(ctx, a, cap);
       else if (minb == 7) launch_extend2<7, true, true, 12, false>(ctx, a, cap);
       else launch_extend2<6, true, true, 16, false>(ctx, a, cap);
     } else if (quant) {
@@ -799,6 +803,56 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   return 0;
 }
 
+// ---- single-process multi-GPU: NCCL, bound at first use with dlopen so that libfjgpu itself has no link-time dependency on it
+// (a torch process brings its own NCCL; this path is for `fjscene` and other C / C++ hosts that drive several contexts)
+struct Nccl {
+  void *lib = nullptr;
+  int (*CommInitAll)(void **, int, const int *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  std::vector<int> devices; std::vector<void *> comms;      // the communicators of the last device list
+};
+Nccl g_nccl;
+
+int multi_all_gather(fjgpu_context *const *ctxs, int nranks, size_t send_bytes) {
+  fjgpu_context *ctx = ctxs[0];
+  Nccl &N = g_nccl;
+  if (!N.lib) {
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) if ((N.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!N.lib) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "fjgpu_render_frame_multi: libnccl.so.2 cannot be loaded");
+    N.CommInitAll = (int (*)(void **, int, const int *))dlsym(N.lib, "ncclCommInitAll");
+    N.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(N.lib, "ncclAllGather");
+    N.GroupStart = (int (*)())dlsym(N.lib, "ncclGroupStart");
+    N.GroupEnd = (int (*)())dlsym(N.lib, "ncclGroupEnd");
+    N.GetErrorString = (const char *(*)(int))dlsym(N.lib, "ncclGetErrorString");
+    if (!N.CommInitAll || !N.AllGather || !N.GroupStart || !N.GroupEnd) { N.lib = nullptr; return fail(ctx, FJGPU_ERR_UNSUPPORTED, "fjgpu_render_frame_multi: NCCL symbols missing"); }
+  }
+  auto nerr = [&](const char *what, int rc) { return fail(ctx, FJGPU_ERR_CUDA, std::string(what) + ": " + (N.GetErrorString ? N.GetErrorString(rc) : "NCCL error")); };
+  std::vector<int> devs(nranks);
+  for (int r = 0; r < nranks; r++) devs[r] = ctxs[r]->device;
+  if (devs != N.devices) {
+    N.comms.assign(nranks, nullptr);
+    if (int rc = N.CommInitAll(N.comms.data(), nranks, devs.data())) return nerr("ncclCommInitAll", rc);
+    N.devices = devs;
+  }
+  if (int rc = N.GroupStart()) return nerr("ncclGroupStart", rc);
+  for (int r = 0; r < nranks; r++) {
+    fjgpu_context *c = ctxs[r];
+    cudaSetDevice(c->device);
+    if (int rc = N.AllGather(c->d_multi_send.p, c->d_multi_recv.p, send_bytes, /* ncclChar */ 0, N.comms[r], c->stream)) { N.GroupEnd(); return nerr("ncclAllGather", rc); }
+  }
+  if (int rc = N.GroupEnd()) return nerr("ncclGroupEnd", rc);
+  for (int r = 0; r < nranks; r++) {
+    cudaSetDevice(ctxs[r]->device);
+    cudaError_t e = cudaStreamSynchronize(ctxs[r]->stream);
+    if (e != cudaSuccess) return fail(ctx, FJGPU_ERR_CUDA, std::string("all-gather: ") + cudaGetErrorString(e));
+  }
+  cudaSetDevice(ctx->device);
+  return 0;
+}
+
 }  // namespace
 
 // ================================================================================== extern "C"
@@ -847,7 +901,7 @@ void fjgpu_destroy(fjgpu_context *ctx) {
   for (auto &kv : ctx->d_inst_motion) kv.second.release();
   ctx->d_cam_motion.release();
   DevBuf *all[] = {&ctx->d_meshes, &ctx->d_inst, &ctx->d_groups, &ctx->d_shaders, &ctx->d_lights, &ctx->d_samples,
-                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_timetab, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl, &ctx->d_hist, &ctx->d_perm};
+                   &ctx->d_tiles, &ctx->d_blocks, &ctx->d_jitter, &ctx->d_timetab, &ctx->d_multi_send, &ctx->d_multi_recv, &ctx->d_counters, &ctx->d_frame, &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_hits, &ctx->d_ctl, &ctx->d_hist, &ctx->d_perm};
   for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
   for (DevBuf *b : all) b->release();
   if (ctx->h_blocks) cudaFreeHost(ctx->h_blocks);
@@ -1081,6 +1135,9 @@ int fjgpu_camera_motion_set(fjgpu_context *ctx, int32_t ntimes, const double *fw
 
 int fjgpu_groups_set(fjgpu_context *ctx, int32_t ngroups, const int32_t *group_offsets, const int32_t *instance_ids) {
   if (!ctx || ngroups < 0 || (ngroups > 0 && !group_offsets)) return fail(ctx, FJGPU_ERR_INVALID, "bad group arrays");
+  if (ngroups > 0 && group_offsets[0] == 0 && (size_t)ngroups + 1 == ctx->group_off.size() &&
+      memcmp(ctx->group_off.data(), group_offsets, ((size_t)ngroups + 1) * 4) == 0 && (size_t)group_offsets[ngroups] == ctx->group_ids.size() &&
+      (ctx->group_ids.empty() || (instance_ids && memcmp(ctx->group_ids.data(), instance_ids, ctx->group_ids.size() * 4) == 0))) return FJGPU_OK;   // unchanged
   ctx->group_off.assign(1, 0); ctx->group_ids.clear();
   if (ngroups > 0) {
     if (group_offsets[0] != 0) return fail(ctx, FJGPU_ERR_INVALID, "group_offsets[0] must be 0");
@@ -1097,12 +1154,25 @@ int fjgpu_shaders_set(fjgpu_context *ctx, int32_t n, const fjgpu_shader *shaders
   if (!ctx || n < 0 || (n > 0 && !shaders)) return fail(ctx, FJGPU_ERR_INVALID, "bad shader array");
   for (int i = 0; i < n; i++) if (shaders[i].kind < FJGPU_SHADER_NONE || shaders[i].kind > FJGPU_SHADER_GLASS)
     return fail(ctx, FJGPU_ERR_UNSUPPORTED, "shader kind has no device implementation");
+  if ((size_t)n == ctx->shaders.size() && (n == 0 || memcmp(ctx->shaders.data(), shaders, (size_t)n * sizeof(fjgpu_shader)) == 0)) return FJGPU_OK;   // unchanged
   ctx->shaders.assign(shaders, shaders + n); ctx->dirty = true;
   return FJGPU_OK;
 }
 
 int fjgpu_lights_set(fjgpu_context *ctx, int32_t n, const fjgpu_light *lights) {
   if (!ctx || n < 0 || (n > 0 && !lights)) return fail(ctx, FJGPU_ERR_INVALID, "bad light array");
+  if ((size_t)n == ctx->lights.size()) {        // unchanged (the dome tables compared by content, the caller's pointers ignored)?
+    bool same = true;
+    for (int i = 0; i < n && same; i++) {
+      fjgpu_light a = lights[i], b = ctx->lights[i];
+      const size_t nd = a.kind == FJGPU_LIGHT_DOME && a.dome_sample_count > 0 ? (size_t)a.dome_sample_count : 0;
+      same = a.dome_sample_count == b.dome_sample_count && ctx->dome_dirs[i].size() == 3 * nd && (nd == 0 || (a.dome_dirs && a.dome_colors &&
+             memcmp(ctx->dome_dirs[i].data(), a.dome_dirs, 24 * nd) == 0 && memcmp(ctx->dome_cols[i].data(), a.dome_colors, 12 * nd) == 0));
+      a.dome_dirs = b.dome_dirs = nullptr; a.dome_colors = b.dome_colors = nullptr;
+      same = same && memcmp(&a, &b, sizeof a) == 0;
+    }
+    if (same) return FJGPU_OK;
+  }
   ctx->lights.assign(lights, lights + n);
   ctx->dome_dirs.assign(n, std::vector<double>()); ctx->dome_cols.assign(n, std::vector<float>());
   for (int i = 0; i < n; i++) {
@@ -1186,6 +1256,91 @@ int fjgpu_render_tiles_device(fjgpu_context *ctx, const fjgpu_render_params *par
 int fjgpu_render_tiles_resident(fjgpu_context *ctx, const fjgpu_render_params *params, const fjgpu_tile *tiles, int32_t ntiles,
                                 fjgpu_stats *stats) {
   return render_impl(ctx, params, tiles, ntiles, OUT_RESIDENT, nullptr, nullptr, 0, 0, stats);
+}
+
+int fjgpu_assemble_frame(fjgpu_context *ctx, const void *d_gathered_blocks, int32_t nranks, int32_t tile_w_max, int32_t tile_h_max,
+                         const fjgpu_tile *tiles, int32_t ntiles, int32_t xres, int32_t yres, float *rgba_frame) {
+  if (!ctx) return fail(nullptr, FJGPU_ERR_INVALID, "null context");
+  if (!d_gathered_blocks || nranks < 1 || tile_w_max < 1 || tile_h_max < 1 || (!tiles && ntiles > 0) || ntiles < 0 || xres < 1 || yres < 1 || !rgba_frame)
+    return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_assemble_frame: bad arguments");
+  for (int i = 0; i < ntiles; i++) {
+    const fjgpu_tile &t = tiles[i];
+    if (t.xmin < 0 || t.ymin < 0 || t.xmax > xres || t.ymax > yres || t.xmax - t.xmin > tile_w_max || t.ymax - t.ymin > tile_h_max || t.xmax <= t.xmin || t.ymax <= t.ymin)
+      return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_assemble_frame: tile outside the frame or larger than a block");
+  }
+  CK(cudaSetDevice(ctx->device));
+  const size_t fbytes = (size_t)xres * yres * sizeof(float4);
+  if (int rc = dev_alloc(ctx, ctx->d_frame, fbytes)) return rc;
+  if (int rc = dev_upload(ctx, ctx->d_tiles, tiles, (size_t)ntiles * sizeof(fjgpu_tile))) return rc;
+  CK(cudaMemsetAsync(ctx->d_frame.p, 0, fbytes, ctx->stream));      // pixels outside the tiles (render_region) stay zero
+  const int per = (ntiles + nranks - 1) / nranks;
+  if (ntiles > 0)
+    fj::k_gathered_to_frame<<<ntiles, 256, 0, ctx->stream>>>((const fj::DTile *)ctx->d_tiles.p, ntiles, nranks, per, (const float4 *)d_gathered_blocks,
+                                                             tile_w_max, tile_h_max, (float4 *)ctx->d_frame.p, xres);
+  CK(cudaGetLastError());
+  // ONE device -> host copy of the frame: straight into the caller's buffer when it is pinned, through the context's pinned
+  // staging buffer otherwise
+  cudaPointerAttributes at; memset(&at, 0, sizeof at);
+  const bool pinned = cudaPointerGetAttributes(&at, rgba_frame) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (pinned) {
+    CK(cudaMemcpyAsync(rgba_frame, ctx->d_frame.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  } else {
+    if (ctx->h_blocks_bytes < fbytes) {
+      if (ctx->h_blocks) cudaFreeHost(ctx->h_blocks);
+      ctx->h_blocks = nullptr; ctx->h_blocks_bytes = 0;
+      CK(cudaMallocHost((void **)&ctx->h_blocks, fbytes));
+      ctx->h_blocks_bytes = fbytes;
+    }
+    CK(cudaMemcpyAsync(ctx->h_blocks, ctx->d_frame.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(rgba_frame, ctx->h_blocks, fbytes);
+  }
+  return FJGPU_OK;
+}
+
+int fjgpu_render_frame_multi(fjgpu_context *const *ctxs, int32_t nranks, const fjgpu_render_params *params, const fjgpu_tile *tiles, int32_t ntiles,
+                             float *rgba_frame, fjgpu_stats *stats) {
+  if (!ctxs || nranks < 1 || !ctxs[0]) return fail(nullptr, FJGPU_ERR_INVALID, "fjgpu_render_frame_multi: no contexts");
+  fjgpu_context *ctx = ctxs[0];
+  if (!params || (!tiles && ntiles > 0) || ntiles < 0 || !rgba_frame) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_render_frame_multi: bad arguments");
+  for (int r = 0; r < nranks; r++) {
+    if (!ctxs[r]) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_render_frame_multi: null context");
+    for (int q = 0; q < r; q++) if (ctxs[q]->device == ctxs[r]->device) return fail(ctx, FJGPU_ERR_INVALID, "fjgpu_render_frame_multi: one context per device");
+  }
+  if (stats) memset(stats, 0, sizeof(fjgpu_stats) * (size_t)nranks);
+  if (nranks == 1) return fjgpu_render_tiles(ctx, params, tiles, ntiles, rgba_frame, stats);
+  int bw = 1, bh = 1;
+  for (int i = 0; i < ntiles; i++) { bw = std::max(bw, tiles[i].xmax - tiles[i].xmin); bh = std::max(bh, tiles[i].ymax - tiles[i].ymin); }
+  const int per = (ntiles + nranks - 1) / nranks;
+  const size_t block_bytes = (size_t)bw * bh * sizeof(float4), send_bytes = (size_t)per * block_bytes;
+  // tile i -> rank i % nranks (the rule of sharding.py and libfjscene): interleaved, cheap static balance
+  std::vector<std::vector<fjgpu_tile>> mine(nranks);
+  for (int i = 0; i < ntiles; i++) mine[i % nranks].push_back(tiles[i]);
+  for (int r = 0; r < nranks; r++) {
+    fjgpu_context *c = ctxs[r];
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, FJGPU_ERR_CUDA, "cudaSetDevice");
+    if (int rc = dev_alloc(c, c->d_multi_send, send_bytes)) return fail(ctx, rc, c->err);
+    if (int rc = dev_alloc(c, c->d_multi_recv, send_bytes * nranks)) return fail(ctx, rc, c->err);
+  }
+  // one host thread per context renders its tiles into its send buffer (no data-path communication while tracing)
+  std::vector<int> rcs(nranks, 0);
+  {
+    std::vector<std::thread> th;
+    for (int r = 0; r < nranks; r++)
+      th.emplace_back([&, r]() {
+        fjgpu_context *c = ctxs[r];
+        cudaSetDevice(c->device);
+        cudaMemsetAsync(c->d_multi_send.p, 0, send_bytes, c->stream);
+        rcs[r] = render_impl(c, params, mine[r].data(), (int)mine[r].size(), OUT_DEVICE_BLOCKS, nullptr, c->d_multi_send.p, bw, bh, stats ? stats + r : nullptr);
+      });
+    for (auto &t : th) t.join();
+  }
+  for (int r = 0; r < nranks; r++) if (rcs[r]) return fail(ctx, rcs[r], "rank " + std::to_string(r) + ": " + ctxs[r]->err);
+  // ONE all-gather of the packed tile blocks ends the frame (NCCL over NVLink; loaded at first use)
+  if (int rc = multi_all_gather(ctxs, nranks, send_bytes)) return rc;
+  return fjgpu_assemble_frame(ctx, ctx->d_multi_recv.p, nranks, bw, bh, tiles, ntiles, params->xres, params->yres, rgba_frame);
 }
 
 int fjgpu_trace_closest(fjgpu_context *ctx, int32_t group, int32_t n, const double *orig3, const double *dir3,

@@ -398,7 +398,6 @@ struct RenderArgs {
   unsigned long long *work;               // megakernel: global work counter (units of 32 slots)
   RayRec *queue[2]; HitRec *hits; QueueCtl *ctl; uint32_t capacity; int cur;     // wavefront
   int refill, phase_a_min, park;          // k_extend scheduling: refill / phase-A thresholds (lanes), speculative leaf parking
-  int prefetch;                           // k_extend2: 1 = prefetch the new stack top into L1, 2 = into L2, 0 = off
   const char *top_src; int top_count;     // k_extend2<TOP>: the NodeQ64 array whose first top_count nodes are staged in shared memory
   int chunked;                            // k_shade without plastic shaders: warps reserve queue slots in chunks (QueueSink)
   // ray sorting between bounces: counting sort of the next queue by (direction octant | origin cell)
@@ -980,6 +979,19 @@ __global__ void k_blocks_to_frame(const DTile *tiles, int ntiles, const float4 *
   for (int p = threadIdx.x; p < w * h; p += blockDim.x) {
     const int px = p % w, py = p / w;
     frame[(size_t)(t.ymin + py) * xres + t.xmin + px] = blocks[((size_t)ti * bh + py) * bw + px];
+  }
+}
+
+// Un-permutes the all-gathered tile blocks of R ranks into the row-major frame: tile i was rendered by rank i % R as that
+// rank's block i / R; every rank contributed `per` blocks (short ranks pad), so the block sits at (i % R) * per + i / R.
+__global__ void k_gathered_to_frame(const DTile *tiles, int ntiles, int nranks, int per, const float4 *gathered, int bw, int bh, float4 *frame, int xres) {
+  const int ti = blockIdx.x;
+  const DTile t = tiles[ti];
+  const float4 *blk = gathered + ((size_t)(ti % nranks) * per + (size_t)(ti / nranks)) * bw * bh;
+  const int w = t.xmax - t.xmin, h = t.ymax - t.ymin;
+  for (int p = threadIdx.x; p < w * h; p += blockDim.x) {
+    const int px = p % w, py = p / w;
+    frame[(size_t)(t.ymin + py) * xres + t.xmin + px] = blk[(size_t)py * bw + px];
   }
 }
 

@@ -58,6 +58,8 @@ def load_fjscene():
     lib.fjscene_set_device.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.fjscene_set_resident.argtypes = [C.c_int]
     lib.fjscene_set_resend.argtypes = [C.c_int]
+    lib.fjscene_set_gpu_count.argtypes = [C.c_int]
+    lib.fjscene_assemble_gathered.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.fjscene_set_device_blocks.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.fjscene_last_resend_bytes.restype = C.c_uint64
     lib.fjscene_instance_matrices.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -89,6 +91,7 @@ class Session:
         self.lib.fjscene_set_device(device, rank, world_size)
         self.lib.fjscene_set_resident(0)
         self.lib.fjscene_set_resend(0)
+        self.lib.fjscene_set_gpu_count(0)
         self.lib.fjscene_set_device_blocks(None, 0, 0)
         self.p = self.lib.fjscene_parser_new()
         self.lib.fjscene_set_echo(self.p, 1 if echo else 0)
@@ -130,6 +133,15 @@ class Session:
 
     def set_device_blocks(self, dev_ptr, tile_w, tile_h):
         self.lib.fjscene_set_device_blocks(C.c_void_p(dev_ptr) if dev_ptr else None, tile_w, tile_h)
+
+    def set_gpu_count(self, n):
+        """GPUs this ONE process renders a frame on (fjgpu_render_frame_multi); 0 = FJ_GPU_COUNT or 1."""
+        self.lib.fjscene_set_gpu_count(int(n))
+
+    def assemble_gathered(self, gathered_ptr, nranks, tile_w, tile_h, host_ptr):
+        """Rank 0 after the all-gather: blocks -> frame on the device, one copy to `host_ptr` (pinned memory is written directly)."""
+        if self.lib.fjscene_assemble_gathered(C.c_void_p(gathered_ptr), nranks, tile_w, tile_h, C.c_void_p(host_ptr)) != 0:
+            raise SceneError((self.lib.fjscene_last_message() or b"assemble failed").decode())
 
     def resend_bytes(self):
         return int(self.lib.fjscene_last_resend_bytes())

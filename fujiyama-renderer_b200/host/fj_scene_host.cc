@@ -175,15 +175,18 @@ struct Scene {
   std::vector<Instance> instances; std::vector<Group> groups; std::vector<Light> lights; std::vector<Camera> cameras;
   std::vector<FrameBuf> framebuffers; std::vector<Renderer> renderers;
   fjgpu_context *gpu = nullptr; int gpu_device = -1;
+  std::vector<fjgpu_context *> more_gpus;              // FJ_GPU_COUNT > 1: contexts on the devices after gpu_device, same scene on each
   std::vector<fjgpu_instance> flat_inst;
+  std::vector<fjgpu_tile> last_tiles; int last_res[2] = {0, 0};      // the whole tile list of the last frame (fjscene_assemble_gathered)
   std::map<int, std::vector<double>> motion_key;      // what the motion table held by libfjgpu for instance i (-1: camera) was built from
-  ~Scene() { if (gpu) fjgpu_destroy(gpu); }
+  ~Scene() { for (fjgpu_context *c : more_gpus) fjgpu_destroy(c); if (gpu) fjgpu_destroy(gpu); }
 };
 
 Scene *the_scene = nullptr;
 int si_errno = SI_ERR_NONE;
 std::string last_message;
 int g_device = 0, g_rank = 0, g_world = 1, g_resident = 0, g_resend = 0;
+int g_gpu_count = 0;       // GPUs one process renders a frame on (fjscene_set_gpu_count / FJ_GPU_COUNT); 0 = not set
 uint64_t g_resend_bytes = 0;
 void *g_dev_blocks = nullptr; int g_dev_bw = 0, g_dev_bh = 0;
 fjgpu_stats g_stats; fjgpu_scene_info g_info; double g_upload_seconds = 0; int32_t g_frame_id = 0;
@@ -610,41 +613,64 @@ Status render(Scene &sc, Renderer &r) {
   if (flatten(sc, r, &f) != SI_SUCCESS) return SI_FAIL;
   // preprocess_framebuffer, src/fj_renderer.cc:805-815: Resize clears the buffer
   fb->w = r.res[0]; fb->h = r.res[1]; fb->c = 4; fb->px.assign((size_t)fb->w * fb->h * 4, 0.f);
-  if (sc.gpu && sc.gpu_device != g_device) { fjgpu_destroy(sc.gpu); sc.gpu = nullptr; sc.motion_key.clear(); for (Mesh &m : sc.meshes) m.dirty = true; }
+  // GPUs of this process: FJ_GPU_COUNT (or fjscene_set_gpu_count) contexts on consecutive devices from g_device on, the scene
+  // replicated on each; tiles are dealt to them by fjgpu_render_frame_multi (one all-gather ends the frame)
+  int ngpu = g_gpu_count > 0 ? g_gpu_count : 1;
+  if (g_gpu_count <= 0) { const char *e = getenv("FJ_GPU_COUNT"); if (e && atoi(e) > 1) ngpu = atoi(e); }
+  if (g_world > 1 || g_dev_blocks || g_resident) ngpu = 1;      // (one process per GPU under torchrun: the host does the gather)
+  if (sc.gpu && (sc.gpu_device != g_device || (int)sc.more_gpus.size() != ngpu - 1)) {
+    for (fjgpu_context *c : sc.more_gpus) fjgpu_destroy(c);
+    sc.more_gpus.clear();
+    fjgpu_destroy(sc.gpu); sc.gpu = nullptr; sc.motion_key.clear(); for (Mesh &m : sc.meshes) m.dirty = true; sc.textures_dirty = true;
+  }
   if (!sc.gpu) {
     if (fjgpu_create(g_device, &sc.gpu) != FJGPU_OK) return failmsg(std::string("fjgpu_create: ") + fjgpu_last_error(nullptr));
     sc.gpu_device = g_device; sc.motion_key.clear();
+    for (int k = 1; k < ngpu; k++) {
+      fjgpu_context *c = nullptr;
+      if (fjgpu_create(g_device + k, &c) != FJGPU_OK) return failmsg(std::string("fjgpu_create (FJ_GPU_COUNT): ") + fjgpu_last_error(nullptr));
+      sc.more_gpus.push_back(c);
+    }
   }
+  std::vector<fjgpu_context *> gpus{sc.gpu};
+  gpus.insert(gpus.end(), sc.more_gpus.begin(), sc.more_gpus.end());
   const auto t0 = std::chrono::steady_clock::now();
   printf("# Building Accelerators\n");                                  // src/fj_scene_interface.cc:1172-1201
   for (size_t i = 0; i < sc.meshes.size(); i++) {
     Mesh &m = sc.meshes[i];
     if (!m.dirty) continue;
-    // a mesh VelocityGeneratorProcedure ran on carries its velocities: moving triangles (Mesh::ray_intersect, src/fj_mesh.cc:252-259)
-    if (fjgpu_mesh_upload_velocity(sc.gpu, (int32_t)i, m.P.data(), m.N.empty() ? nullptr : m.N.data(), (int32_t)(m.P.size() / 3), m.idx.data(), nullptr,
-                                   (int32_t)(m.idx.size() / 3), m.vel.empty() ? nullptr : m.vel.data()) != FJGPU_OK)
-      return failmsg(std::string("fjgpu_mesh_upload: ") + fjgpu_last_error(sc.gpu));
-    if (!m.uv.empty() && fjgpu_mesh_set_uv(sc.gpu, (int32_t)i, m.uv.data(), (int32_t)(m.uv.size() / 2)) != FJGPU_OK)
-      return failmsg(std::string("fjgpu_mesh_set_uv: ") + fjgpu_last_error(sc.gpu));
+    for (fjgpu_context *g : gpus) {
+      // a mesh VelocityGeneratorProcedure ran on carries its velocities: moving triangles (Mesh::ray_intersect, src/fj_mesh.cc:252-259)
+      if (fjgpu_mesh_upload_velocity(g, (int32_t)i, m.P.data(), m.N.empty() ? nullptr : m.N.data(), (int32_t)(m.P.size() / 3), m.idx.data(), nullptr,
+                                     (int32_t)(m.idx.size() / 3), m.vel.empty() ? nullptr : m.vel.data()) != FJGPU_OK)
+        return failmsg(std::string("fjgpu_mesh_upload: ") + fjgpu_last_error(g));
+      if (!m.uv.empty() && fjgpu_mesh_set_uv(g, (int32_t)i, m.uv.data(), (int32_t)(m.uv.size() / 2)) != FJGPU_OK)
+        return failmsg(std::string("fjgpu_mesh_set_uv: ") + fjgpu_last_error(g));
+    }
     m.dirty = false;
   }
   if (sc.textures_dirty) {
     std::vector<fjgpu_texture> ft(sc.textures.size());
     for (size_t i = 0; i < ft.size(); i++) { const Texture &t = sc.textures[i]; ft[i].width = t.width; ft[i].height = t.height; ft[i].nchannels = t.nch; ft[i].tilesize = t.tilesize; ft[i].tiles = t.tiles.data(); }
-    if (fjgpu_textures_set(sc.gpu, (int32_t)ft.size(), ft.data()) != FJGPU_OK) return failmsg(std::string("fjgpu_textures_set: ") + fjgpu_last_error(sc.gpu));
+    for (fjgpu_context *g : gpus)
+      if (fjgpu_textures_set(g, (int32_t)ft.size(), ft.data()) != FJGPU_OK) return failmsg(std::string("fjgpu_textures_set: ") + fjgpu_last_error(g));
     sc.textures_dirty = false;
   }
-  int rc = fjgpu_shaders_set(sc.gpu, (int32_t)f.shaders.size(), f.shaders.data());
-  if (!rc) rc = fjgpu_shutter_set(sc.gpu, r.time_range[0], r.time_range[1]);      // Renderer::SetSampleTimeRange
-  if (!rc) rc = fjgpu_groups_set(sc.gpu, (int32_t)f.goff.size() - 1, f.goff.data(), f.gids.data());
-  if (!rc) rc = fjgpu_instances_set(sc.gpu, (int32_t)f.inst.size(), f.inst.data());
-  if (!rc) rc = fjgpu_lights_set(sc.gpu, (int32_t)f.lights.size(), f.lights.data());
-  if (!rc) rc = fjgpu_camera_set(sc.gpu, &f.cam);
-  if (rc) return failmsg(std::string("scene upload: ") + fjgpu_last_error(sc.gpu));
+  int rc = 0;
+  for (fjgpu_context *g : gpus) {
+    if (!rc) rc = fjgpu_shaders_set(g, (int32_t)f.shaders.size(), f.shaders.data());
+    if (!rc) rc = fjgpu_shutter_set(g, r.time_range[0], r.time_range[1]);      // Renderer::SetSampleTimeRange
+    if (!rc) rc = fjgpu_groups_set(g, (int32_t)f.goff.size() - 1, f.goff.data(), f.gids.data());
+    if (!rc) rc = fjgpu_instances_set(g, (int32_t)f.inst.size(), f.inst.data());
+    if (!rc) rc = fjgpu_lights_set(g, (int32_t)f.lights.size(), f.lights.data());
+    if (!rc) rc = fjgpu_camera_set(g, &f.cam);
+    if (rc) return failmsg(std::string("scene upload: ") + fjgpu_last_error(g));
+  }
   sc.flat_inst = f.inst;
+  sc.last_tiles = f.tiles; sc.last_res[0] = r.res[0]; sc.last_res[1] = r.res[1];
 
   std::vector<fjgpu_tile> mine;
-  for (size_t i = 0; i < f.tiles.size(); i++) if ((int)(i % (size_t)g_world) == g_rank) mine.push_back(f.tiles[i]);
+  for (size_t i = 0; i < f.tiles.size(); i++) if ((int)(i % (size_t)g_world) == g_rank) mine.push_back(f.tiles[i]);      // (one process per GPU: this rank's share)
   {
     // Motion blur: the frame's time table (one entry per sample of a tile: src/fj_fixed_grid_sampler.cc:42,72-77) and the
     // transform XfmLerpTransformSample would rebuild for a ray of each entry's time, for every time-sampled instance / camera
@@ -668,7 +694,7 @@ Status render(Scene &sc, Renderer &r) {
     for (int i = -1; i < (int)sc.instances.size() && !rc; i++) {                       // -1: the camera
       const Xform &x = i < 0 ? cam->x : sc.instances[i].x;
       if (x.is_static() || n == 0) {
-        rc = i < 0 ? fjgpu_camera_motion_set(sc.gpu, 0, nullptr) : fjgpu_instance_motion_set(sc.gpu, i, 0, nullptr, nullptr);
+        for (fjgpu_context *g : gpus) if (!rc) rc = i < 0 ? fjgpu_camera_motion_set(g, 0, nullptr) : fjgpu_instance_motion_set(g, i, 0, nullptr, nullptr);
         sc.motion_key.erase(i);
         continue;
       }
@@ -677,7 +703,7 @@ Status render(Scene &sc, Renderer &r) {
       if (it != sc.motion_key.end() && it->second == key) continue;
       fwd.resize((size_t)n * 16); inv.resize((size_t)n * 16);
       for (int k = 0; k < n; k++) { const M4 m = x.matrix_at(times[k]), mi = inverse(m); memcpy(&fwd[16 * (size_t)k], m.e, 128); memcpy(&inv[16 * (size_t)k], mi.e, 128); }
-      rc = i < 0 ? fjgpu_camera_motion_set(sc.gpu, n, fwd.data()) : fjgpu_instance_motion_set(sc.gpu, i, n, fwd.data(), inv.data());
+      for (fjgpu_context *g : gpus) if (!rc) rc = i < 0 ? fjgpu_camera_motion_set(g, n, fwd.data()) : fjgpu_instance_motion_set(g, i, n, fwd.data(), inv.data());
       if (!rc) sc.motion_key[i].swap(key);
     }
     if (rc) return failmsg(std::string("motion tables: ") + fjgpu_last_error(sc.gpu));
@@ -688,15 +714,26 @@ Status render(Scene &sc, Renderer &r) {
   info.frame_id = ++g_frame_id; info.worker_count = 1; info.tile_count = (int)mine.size(); info.xres = r.res[0]; info.yres = r.res[1];
   info.frame_region.min[0] = r.region[0]; info.frame_region.min[1] = r.region[1]; info.frame_region.max[0] = r.region[2]; info.frame_region.max[1] = r.region[3];
   info.framebuffer = reinterpret_cast<const FrameBuffer *>(fb);
-  printf("# Rendering Frame\n#   Tile Count: %d\n#   Device: cuda:%d (rank %d of %d)\n", (int)mine.size(), g_device, g_rank, g_world);
+  if (ngpu > 1) printf("# Rendering Frame\n#   Tile Count: %d\n#   Devices: cuda:%d..%d (tiles dealt round-robin, one all-gather)\n", (int)mine.size(), g_device, g_device + ngpu - 1);
+  else printf("# Rendering Frame\n#   Tile Count: %d\n#   Device: cuda:%d (rank %d of %d)\n", (int)mine.size(), g_device, g_rank, g_world);
   if (r.frame_start && r.frame_start(r.frame_data, &info) == CALLBACK_INTERRUPT) {
     if (r.frame_abort) r.frame_abort(r.frame_data, &info);
     return SI_FAIL;
   }
   memset(&g_stats, 0, sizeof g_stats);
   g_resend_bytes = 0;
-  if (g_resend && fjgpu_scene_resend(sc.gpu, &g_resend_bytes) != FJGPU_OK) return failmsg(std::string("fjgpu_scene_resend: ") + fjgpu_last_error(sc.gpu));
-  if (g_dev_blocks) rc = fjgpu_render_tiles_device(sc.gpu, &f.params, mine.data(), (int32_t)mine.size(), g_dev_bw, g_dev_bh, g_dev_blocks, &g_stats);
+  if (g_resend) for (fjgpu_context *g : gpus) if (fjgpu_scene_resend(g, &g_resend_bytes) != FJGPU_OK) return failmsg(std::string("fjgpu_scene_resend: ") + fjgpu_last_error(g));
+  if (ngpu > 1) {
+    std::vector<fjgpu_stats> per(ngpu);
+    rc = fjgpu_render_frame_multi(gpus.data(), ngpu, &f.params, mine.data(), (int32_t)mine.size(), fb->px.data(), per.data());
+    for (const fjgpu_stats &q : per) {      // the frame's totals: counts add up, device times are the slowest rank's
+      g_stats.rays_camera += q.rays_camera; g_stats.rays_shadow += q.rays_shadow; g_stats.rays_diffuse += q.rays_diffuse; g_stats.rays_reflect += q.rays_reflect;
+      g_stats.rays_refract += q.rays_refract; g_stats.camera_samples += q.camera_samples; g_stats.rays_hit += q.rays_hit; g_stats.hit_mesh_levels += q.hit_mesh_levels;
+      g_stats.node_steps += q.node_steps; g_stats.tri_tests += q.tri_tests; g_stats.kernel_launches += q.kernel_launches; g_stats.trace_launches += q.trace_launches;
+      g_stats.ms_trace = std::max(g_stats.ms_trace, q.ms_trace); g_stats.ms_shade = std::max(g_stats.ms_shade, q.ms_shade);
+      g_stats.ms_resolve = std::max(g_stats.ms_resolve, q.ms_resolve); g_stats.ms_total = std::max(g_stats.ms_total, q.ms_total);
+    }
+  } else if (g_dev_blocks) rc = fjgpu_render_tiles_device(sc.gpu, &f.params, mine.data(), (int32_t)mine.size(), g_dev_bw, g_dev_bh, g_dev_blocks, &g_stats);
   else if (g_resident) rc = fjgpu_render_tiles_resident(sc.gpu, &f.params, mine.data(), (int32_t)mine.size(), &g_stats);
   else rc = fjgpu_render_tiles(sc.gpu, &f.params, mine.data(), (int32_t)mine.size(), fb->px.data(), &g_stats);
   if (rc) { if (r.frame_abort) r.frame_abort(r.frame_data, &info); return failmsg(std::string("fjgpu_render_tiles: ") + fjgpu_last_error(sc.gpu)); }
@@ -1106,6 +1143,14 @@ int fjscene_last_stats(fjgpu_stats *stats, fjgpu_scene_info *info, double *uploa
 void fjscene_set_device(int device_ordinal, int rank, int world_size) { g_device = device_ordinal; g_rank = rank; g_world = world_size > 0 ? world_size : 1; }
 void fjscene_set_resident(int resident) { g_resident = resident; }
 void fjscene_set_resend(int resend) { g_resend = resend; }
+void fjscene_set_gpu_count(int count) { g_gpu_count = count; }
+int fjscene_assemble_gathered(const void *d_gathered_blocks, int nranks, int tile_w_max, int tile_h_max, float *rgba_frame) {
+  if (!the_scene || !the_scene->gpu || the_scene->last_tiles.empty()) return -1;
+  Scene &sc = *the_scene;
+  if (fjgpu_assemble_frame(sc.gpu, d_gathered_blocks, nranks, tile_w_max, tile_h_max, sc.last_tiles.data(), (int32_t)sc.last_tiles.size(),
+                           sc.last_res[0], sc.last_res[1], rgba_frame) != FJGPU_OK) { failmsg(std::string("fjgpu_assemble_frame: ") + fjgpu_last_error(sc.gpu)); return -1; }
+  return 0;
+}
 void fjscene_set_device_blocks(void *d_tile_blocks, int tile_w_max, int tile_h_max) { g_dev_blocks = d_tile_blocks; g_dev_bw = tile_w_max; g_dev_bh = tile_h_max; }
 uint64_t fjscene_last_resend_bytes(void) { return g_resend_bytes; }
 

@@ -248,6 +248,26 @@ int fjgpu_render_tiles_device(fjgpu_context *ctx, const fjgpu_render_params *par
 int fjgpu_render_tiles_resident(fjgpu_context *ctx, const fjgpu_render_params *params,
                                 const fjgpu_tile *tiles, int32_t ntiles, fjgpu_stats *stats);
 
+/* ---- multi-GPU: tiles are the independent units of the path (src/fj_renderer.cc:1098-1121; the reference deals them to
+ * its worker threads through MtRunParallelLoop, src/fj_multi_thread.cc:86-100).  Tile i of the frame's tile list goes to rank
+ * i % nranks, every rank renders into packed blocks in its own HBM with the scene replicated, ONE all-gather of the blocks
+ * ends the frame, rank 0 un-permutes on the device and copies the frame to the host once.
+ *
+ * fjgpu_assemble_frame: the last step for hosts that ran the all-gather themselves (bench.py: one process per GPU,
+ * torch.distributed over NCCL).  d_gathered_blocks = nranks x ceil(ntiles / nranks) blocks of tile_w_max x tile_h_max x 4
+ * floats in rank order on ctx's device, `tiles` = the whole frame's tile list; writes xres*yres*4 floats to rgba_frame
+ * (pixels outside the tiles zero).  The copy goes straight into rgba_frame when it is pinned host memory.
+ *
+ * fjgpu_render_frame_multi: the whole frame from ONE process driving one context per GPU (the same scene uploaded to each):
+ * one host thread per context renders its tiles, ncclAllGather over the contexts' streams (libnccl.so.2 is loaded at first
+ * use: FJGPU_ERR_UNSUPPORTED without it), rank 0 assembles.  stats (may be NULL) = nranks entries.  The image is identical
+ * for every nranks (the counter RNG is keyed by tile id). */
+int fjgpu_assemble_frame(fjgpu_context *ctx, const void *d_gathered_blocks, int32_t nranks,
+                         int32_t tile_w_max, int32_t tile_h_max, const fjgpu_tile *tiles, int32_t ntiles,
+                         int32_t xres, int32_t yres, float *rgba_frame);
+int fjgpu_render_frame_multi(fjgpu_context *const *ctxs, int32_t nranks, const fjgpu_render_params *params,
+                             const fjgpu_tile *tiles, int32_t ntiles, float *rgba_frame, fjgpu_stats *stats);
+
 /* ---- probes used by the parity tests (each mirrors one reference function) ------------- */
 
 /* Closest hit of n rays in object group `group` = Accelerator::Intersect of the group's

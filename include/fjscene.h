@@ -9,7 +9,8 @@
  * CPU worker threads.  What differs, by design:
  *   - SiOpenPlugin() does not dlopen: the device shaders are keyed on the plugin NAME
  *     (ConstantShader, PlasticShader, PathtracingShader, GlassShader; StanfordPlyProcedure as the mesh loader,
- *     VelocityGeneratorProcedure — whose meshes SiRenderScene refuses until the kernels have moving triangles).
+ *     VelocityGeneratorProcedure, whose per-vertex velocities reach the device as moving triangles).  The reference's OWN
+ *     host with its dlopen'ed plugin DSOs runs on libfjgpu through host/fj_gpu_bridge.cc.
  *     Any other plugin yields SI_BADID / SI_ERR_PLUGIN_NOT_FOUND — there is no CPU fallback here.
  *   - entity kinds outside the path (Volume, Curve, PointCloud, Turbulence) yield SI_BADID / SI_ERR_FAILNEW; the
  *     adaptive sampler makes SiRenderScene() return SI_FAIL.  Time-sampled transforms of instances and cameras
@@ -136,6 +137,15 @@ void fjscene_set_resident(int resident);
 /* 1 = every SiRenderScene first re-sends the whole scene host -> device (fjgpu_scene_resend); bytes of the last one. */
 void fjscene_set_resend(int resend);
 uint64_t fjscene_last_resend_bytes(void);
+/* GPUs ONE process renders a frame on (default: the environment variable FJ_GPU_COUNT, else 1): contexts on `count`
+ * consecutive devices from fjscene_set_device's ordinal on, the scene uploaded to each, tiles dealt round-robin, one NCCL
+ * all-gather of the tile blocks, rank 0 assembles the host framebuffer (fjgpu_render_frame_multi).  `fjscene file.scn` with
+ * FJ_GPU_COUNT=8 renders on the 8 GPUs of a box without Python. */
+void fjscene_set_gpu_count(int count);
+/* One process per GPU (torchrun): after the host's all-gather of the ranks' tile blocks (fjscene_set_device_blocks), rank 0
+ * un-permutes them on the device into the last frame's layout and copies the frame to `rgba_frame` (xres*yres*4 floats; pinned
+ * memory is written directly) — fjgpu_assemble_frame with the frame's own tile list.  0 or -1. */
+int fjscene_assemble_gathered(const void *d_gathered_blocks, int nranks, int tile_w_max, int tile_h_max, float *rgba_frame);
 /* Non-NULL: SiRenderScene leaves this rank's tiles as packed blocks (tile_w_max*tile_h_max*4 floats per tile, in
  * the rank's tile order) in the caller's DEVICE buffer — the send buffer of the multi-GPU all-gather
  * (fjgpu_render_tiles_device).  NULL restores the host-framebuffer mode. */
@@ -145,7 +155,7 @@ void fjscene_set_device_blocks(void *d_tile_blocks, int tile_w_max, int tile_h_m
 int fjscene_instance_matrices(int32_t index, double *fwd16, double *inv16);
 int fjscene_mesh_normals(long mesh_id, double *N_out, int32_t nverts);
 /* Per-vertex velocities VelocityGeneratorProcedure wrote on a mesh (3 doubles per vertex); -1 if it has none.  The
- * procedure is mirrored bit for bit; rendering such a mesh fails until the device path has moving triangles. */
+ * procedure is mirrored bit for bit; SiRenderScene hands the velocities to fjgpu_mesh_upload_velocity. */
 int fjscene_mesh_velocity(long mesh_id, double *vel_out, int32_t nverts);
 const char *fjscene_last_message(void);
 /* The flat scene description SiRenderScene would hand to libfjgpu for a renderer (instances, lights, shaders, camera,
