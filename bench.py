@@ -113,18 +113,27 @@ def algorithmic_bytes(stats, ninst):
     return hit * (228 + 64 * l_tlas) + 64 * stats.hit_mesh_levels + (rays - hit) * 96 + 32 * stats.camera_samples
 
 
-# ---------------------------------------------------------------------------------------------- reference arm
+# ---------------------------------------------------------------------------------------------- CPU arms
+# Both CPU legs (`--impl reference` and the own arm's `cpu_baseline`) time the UNMODIFIED reference (oracle/_ref, built from
+# /root/reference by oracle/Makefile.ref) on a bounded sample of the SAME frame: tile-row strips drawn from a seeded
+# permutation of ALL tile rows of the frame (a step = one strip; over the steps the sample covers the frame top to bottom,
+# background and object alike — round 1 sampled centre tiles only).  Mrays/s = rays of exactly those tiles / seconds; the
+# reference has no ray counter, so the rays of the sampled tiles are counted after the timed region (libfjgpu's per-type
+# counters for the same tiles when a GPU is present, else the oracle port) — a unit conversion, never part of the timing.
+STRIP_SEED = 20261017
+
+
 def ref_paths():
     ref = os.path.join(REPO, "oracle", "_ref")
     probe = os.path.join(ref, "bin", "ref_probe")
     return ref, probe
 
 
-def run_reference(scene_text, region, frames, threads, timeout=3000):
-    """Runs the unmodified reference on `region` of the frame, `frames` RenderScene calls in one process.
+def run_reference(scene_text, regions, timeout=3000):
+    """Runs the unmodified reference: one RenderScene per entry of `regions` (render_region xmin ymin xmax ymax) in ONE process.
     Returns the per-frame seconds measured between its frame-start and frame-done callbacks."""
     ref, probe = ref_paths()
-    txt = scene_text + "SetProperty4 ren1 render_region %d %d %d %d\n" % tuple(region) + "RenderScene ren1\n" * frames
+    txt = scene_text + "".join("SetProperty4 ren1 render_region %d %d %d %d\nRenderScene ren1\n" % tuple(r) for r in regions)
     scn = os.path.join(workdir(), "ref_%d.scn" % os.getpid())
     with open(scn, "w") as f:
         f.write(txt)
@@ -132,94 +141,180 @@ def run_reference(scene_text, region, frames, threads, timeout=3000):
     res = subprocess.run([probe, "run", scn], env=env, capture_output=True, text=True, timeout=timeout)
     if res.returncode != 0:
         raise RuntimeError("reference failed: " + res.stdout[-1500:] + res.stderr[-1500:])
-    return [float(l.split()[1]) for l in res.stdout.split("\n") if l.startswith("FJ_FRAME_SECONDS")]
+    secs = [float(l.split()[1]) for l in res.stdout.split("\n") if l.startswith("FJ_FRAME_SECONDS")]
+    if len(secs) != len(regions):
+        raise RuntimeError("reference reported %d frames for %d regions" % (len(secs), len(regions)))
+    return secs
 
 
-def oracle_rays_per_sample(builder, kw, threads):
-    """Rays per camera sample of the workload, counted by the oracle port (test infrastructure; the unmodified
-    reference has no ray counter) on the 4 centre tiles — used only to convert the reference's samples/s into Mrays/s."""
+def strip_regions(res, n, tiles_per_strip, tile=32):
+    """`n` tile-row strips of `tiles_per_strip` tiles each: rows from a seeded permutation of all tile rows (cycled), the
+    strip's first column seeded too when it is narrower than the frame."""
+    import random
+    rng = random.Random(STRIP_SEED)
+    tx, ty = -(-res[0] // tile), -(-res[1] // tile)
+    rows = list(range(ty))
+    rng.shuffle(rows)
+    w = max(1, min(tx, tiles_per_strip))
+    out = []
+    for k in range(n):
+        row = rows[k % ty]
+        c0 = rng.randrange(0, tx - w + 1)
+        out.append((c0 * tile, row * tile, min((c0 + w) * tile, res[0]), min((row + 1) * tile, res[1])))
+    return out
+
+
+def tiles_of_regions(res, regions, tile=32):
+    """The frame's tiles (full-frame ids) covered by tile-aligned `regions`, one list per region."""
+    from fujiyama_renderer_b200 import sharding
+    all_tiles = sharding.make_tiles(res[0], res[1], tile)
+    per_row = -(-res[0] // tile)
+    out = []
+    for x0, y0, x1, y1 in regions:
+        out.append([all_tiles[(y0 // tile) * per_row + c] for c in range(x0 // tile, -(-x1 // tile))])
+    return out
+
+
+def count_rays(builder, kw, tile_lists, prefer_gpu=True):
+    """Rays (all types) and camera samples of the given tiles of the workload's frame, per list.  Returns (counts, how)."""
     sys.path.insert(0, os.path.join(REPO, "tests"))
+    import workloads
     import scenekit as sk
-    from fujiyama_renderer_b200 import synth
-    if builder == "pathtracing_blob":
-        d = sk.scene_blob_pathtracing(n=kw["n"], res=kw["res"], rate=kw["rate"], depth=kw.get("depth", 3))
-        d.meshes[1] = ("shell", *synth.blob(64), None)
-        d.shaders = [("sh1", "pathtracing", dict(diffuse=(.8, .6, .4), emission=(.05, .05, .05))),
-                     ("sh2", "pathtracing", dict(diffuse=(.2, .2, .2), emission=(1.0, .9, .8)))]
+    desc = workloads.desc_for(builder, kw)
+    st = desc.to_structs()
+    how = None
+    out = []
+    try:
+        import torch
+        has_gpu = prefer_gpu and torch.cuda.is_available() and os.environ.get("FJ_REF_COUNT", "gpu") != "oracle"
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        from fujiyama_renderer_b200 import device
+        dev = device.Device(int(os.environ.get("LOCAL_RANK", "0")))
+        try:
+            dev.load_structs(st)
+            for tl in tile_lists:
+                s_ = dev.render_resident(st["params"], tl)
+                out.append((s_.rays, s_.camera_samples))
+        finally:
+            dev.close()
+        how = "libfjgpu per-type ray counters for the same tiles"
     else:
-        d = sk.scene_blob_plastic(n=kw["n"], res=kw["res"], rate=kw["rate"])
+        for tl in tile_lists:
+            _, s_ = sk.oracle_render(desc, rng_mode=0, threads=min(os.cpu_count() or 1, 64), st=st, tiles=tl)
+            out.append((s_.rays, s_.camera_samples))
+        how = "oracle port (counter RNG) on the same tiles"
+    return out, how
+
+
+def cpu_sample(builder, kw, nframes, budget_s):
+    """Times the unmodified reference on `nframes` strips sized so that all of them take about `budget_s` seconds.
+    Returns dict(secs, regions, tile_lists, threads, calibration)."""
     from fujiyama_renderer_b200 import scenes
-    region = scenes.center_region(kw["res"], 32, 2, 2)
-    _, st = sk.oracle_render(d, rng_mode=0, threads=threads, region=region)
-    return st.rays / max(st.camera_samples, 1)
+    ref, probe = ref_paths()
+    threads = min(os.cpu_count() or 1, 64)
+    text = getattr(scenes, builder)(workdir(), os.path.join(ref, "lib"), threads=threads, **kw)
+    res = kw["res"]
+    tx = -(-res[0] // 32)
+    # calibrate on one strip of `threads` tiles in the first row of the permutation's middle (>= one tile per worker thread)
+    cal = strip_regions(res, 1, min(tx, max(threads, 4)))
+    t_cal = run_reference(text, cal)[0]
+    cal_tiles = len(tiles_of_regions(res, cal)[0])
+    per_tile = max(t_cal, 1e-3) / cal_tiles
+    want = int(budget_s / max(nframes, 1) / per_tile)
+    width = max(min(tx, max(threads, 4)), min(tx, want))
+    regions = strip_regions(res, nframes, width)
+    secs = run_reference(text, regions)
+    return {"secs": secs, "regions": regions, "tile_lists": tiles_of_regions(res, regions), "threads": threads,
+            "calibration": {"seconds": t_cal, "tiles": cal_tiles}, "strip_tiles": width, "frame_tiles": [tx, -(-res[1] // 32)]}
+
+
+def shared_config(args, desc, world):
+    """`config` is identical in both arms (the driver compares them): the workload, not the measurement."""
+    return {"workload": args.workload, "scene": desc,
+            "l2": "GPU arm: 256 MiB flush between steps; scene + 2.3 GB/frame sample stream exceed L2 (not applicable to the CPU arm)",
+            "parallelism": "GPU arm: tiles round-robin over %d rank(s)%s; CPU arm: the reference's worker threads over the tiles of a strip" % (
+                world, ", one NCCL all_gather of tile blocks" if world > 1 else "")}
 
 
 def reference_arm(args, builder, kw, desc):
-    from fujiyama_renderer_b200 import scenes
     ref, probe = ref_paths()
     base = {"impl": "reference", "metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": args.workload, "scene": desc}}
+            "data": "synthetic", "config": shared_config(args, desc, args.gpus)}
     if not os.path.exists(probe):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (needs /root/reference at build time)"}))
         return
-    if builder not in ("pathtracing_blob", "plastic_blob"):
-        print(json.dumps({"impl": "reference", "unavailable": "the reference arm is wired for the north_star / config2 / profile / small workloads"}))
-        return
-    threads = min(os.cpu_count() or 1, 64)
-    text = getattr(scenes, builder)(workdir(), os.path.join(ref, "lib"), threads=threads, **kw)
-    res, rate = kw["res"], kw["rate"]
-    # calibrate on 2x2 centre tiles, then size the sample so that (warmup + steps) frames fit the budget
-    cal_n = max(2, int(math.ceil(math.sqrt(2 * threads))))       # >= 2 tiles per worker thread
-    cal_region = scenes.center_region(res, 32, cal_n, cal_n)
-    t_cal = run_reference(text, cal_region, 1, threads)[0]
-    cal_samples = scenes.region_camera_samples(cal_region, rate)
-    budget = float(os.environ.get("FJ_REF_BUDGET_S", "150")) / max(1, args.steps + args.warmup)
-    want_tiles = max(threads, int(cal_n * cal_n * budget / max(t_cal, 1e-3)))
-    tx, ty = -(-res[0] // 32), -(-res[1] // 32)
-    ny = max(2, min(ty, int(round(math.sqrt(want_tiles * 9 / 16.)))))
-    nx = max(2, min(tx, want_tiles // ny))
-    region = scenes.center_region(res, 32, nx, ny)
-    secs = run_reference(text, region, args.warmup + args.steps, threads)[args.warmup:]
-    samples = scenes.region_camera_samples(region, rate)
-    rps = oracle_rays_per_sample(builder, kw, threads)
-    t = sum(secs) / len(secs)
-    mrays = samples * rps / t / 1e6
-    sample = "render_region %s (%dx%d tiles of %dx%d), %d camera samples/step, %.3f rays/sample (oracle count), %d threads" % (
-        list(region), nx, ny, tx, ty, samples, rps, threads)
-    out = dict(base, value=mrays, ms_per_step=1e3 * t,
-               cpu_baseline={"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": "reference", "sample": sample,
-                             "camera_samples_per_s": samples / t, "calibration_s": t_cal, "calibration_samples": cal_samples},
+    n = args.warmup + args.steps
+    smp = cpu_sample(builder, kw, n, float(os.environ.get("FJ_REF_BUDGET_S", "150")))
+    secs = smp["secs"][args.warmup:]
+    counts, how = count_rays(builder, kw, smp["tile_lists"][args.warmup:])
+    rays = sum(c[0] for c in counts)
+    samples = sum(c[1] for c in counts)
+    t = sum(secs)
+    mrays = rays / t / 1e6
+    sample = ("%d strips of %d tiles (rows %s of %d, seeded permutation %d) = %d camera samples, %d rays (%s), %d threads" % (
+        len(secs), smp["strip_tiles"], [r[1] // 32 for r in smp["regions"][args.warmup:]], smp["frame_tiles"][1], STRIP_SEED,
+        samples, rays, how, smp["threads"]))
+    out = dict(base, value=mrays, ms_per_step=1e3 * t / len(secs),
+               cpu_baseline={"value": mrays, "unit": "Mrays/s", "cores": smp["threads"], "kind": "reference", "sample": sample,
+                             "camera_samples_per_s": samples / t, "rays_per_sample": rays / max(samples, 1),
+                             "calibration": smp["calibration"]},
                e2e={"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(out))
 
 
 def cpu_baseline_leg(builder, kw):
-    """Bounded sample of the same workload on the host cores (about 10-30 s of CPU work) for the own arm's line."""
-    from fujiyama_renderer_b200 import scenes
-    if builder not in ("pathtracing_blob", "plastic_blob"):
-        return None                       # extra workloads (config3-5 at full size): own arm only
+    """Bounded sample of the same workload on the host cores (about 15 s of CPU work) for the own arm's line."""
     ref, probe = ref_paths()
     if not os.path.exists(probe):
         return None
-    threads = min(os.cpu_count() or 1, 64)
-    text = getattr(scenes, builder)(workdir(), os.path.join(ref, "lib"), threads=threads, **kw)
-    res, rate = kw["res"], kw["rate"]
-    cal_n = max(2, int(math.ceil(math.sqrt(2 * threads))))
-    cal_region = scenes.center_region(res, 32, cal_n, cal_n)
-    t_cal = run_reference(text, cal_region, 1, threads)[0]
-    want = max(threads, int(cal_n * cal_n * 15.0 / max(t_cal, 1e-3)))
-    tx, ty = -(-res[0] // 32), -(-res[1] // 32)
-    ny = max(2, min(ty, int(round(math.sqrt(want * 9 / 16.)))))
-    nx = max(2, min(tx, want // ny))
-    region = scenes.center_region(res, 32, nx, ny)
-    t = run_reference(text, region, 1, threads)[0]
-    samples = scenes.region_camera_samples(region, rate)
-    rps = oracle_rays_per_sample(builder, kw, threads)
-    return {"value": samples * rps / t / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "reference",
-            "sample": "unmodified reference (oracle/_ref), render_region %s = %d camera samples, %.3f rays/sample, %.1f s" % (
-                list(region), samples, rps, t),
-            "camera_samples_per_s": samples / t}
+    nframes = 2
+    smp = cpu_sample(builder, kw, nframes, float(os.environ.get("FJ_CPU_BASELINE_S", "16")))
+    counts, how = count_rays(builder, kw, smp["tile_lists"])
+    rays, samples, t = sum(c[0] for c in counts), sum(c[1] for c in counts), sum(smp["secs"])
+    return {"value": rays / t / 1e6, "unit": "Mrays/s", "cores": smp["threads"], "kind": "reference",
+            "sample": "unmodified reference (oracle/_ref), %d strips of %d tiles (rows %s of %d, seeded) = %d camera samples, %d rays (%s), %.1f s" % (
+                nframes, smp["strip_tiles"], [r[1] // 32 for r in smp["regions"]], smp["frame_tiles"][1], samples, rays, how, t),
+            "camera_samples_per_s": samples / t, "rays_per_sample": rays / max(samples, 1)}
+
+
+# ---------------------------------------------------------------------------------------------- parity leg
+def parity_leg(builder, kw, frame, ntiles=6):
+    """Holds the frame the bench just timed to the oracle: `ntiles` tiles drawn (seeded) from ALL tiles of the frame, rendered by
+    the oracle port with the same counter RNG and the tiles' full-frame ids, compared with the same pixels of the timed GPU
+    frame; the same tiles rendered once more through the C-ABI give the per-type ray counts to compare.  The oracle is the
+    checker here, never the thing measured."""
+    import random
+    import numpy as np
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import workloads
+    import scenekit as sk
+    from fujiyama_renderer_b200 import device
+    desc = workloads.desc_for(builder, kw)
+    st = desc.to_structs()
+    all_tiles = desc.tiles()
+    rng = random.Random(STRIP_SEED + 1)
+    pick = sorted(rng.sample(range(len(all_tiles)), min(ntiles, len(all_tiles))))
+    tiles = [all_tiles[i] for i in pick]
+    ref, rstats = sk.oracle_render(desc, rng_mode=0, threads=min(os.cpu_count() or 1, 64), st=st, tiles=tiles)
+    dev = device.Device(int(os.environ.get("LOCAL_RANK", "0")))
+    try:
+        dev.load_structs(st)
+        sub, gstats = dev.render(st["params"], tiles)
+    finally:
+        dev.close()
+    mask = np.zeros(ref.shape[:2], bool)
+    for _, x0, y0, x1, y1 in tiles:
+        mask[y0:y1, x0:x1] = True
+    d = frame[mask].astype(np.float64) - ref[mask].astype(np.float64)
+    rmse = float(np.sqrt((d * d).mean(0)).max())
+    keys = ("rays_camera", "rays_shadow", "rays_diffuse", "rays_reflect", "rays_refract", "camera_samples")
+    return {"rmse": rmse, "max_abs": float(np.abs(d).max()), "bar": 1e-4, "tiles": [t[0] for t in tiles], "pixels": int(mask.sum()),
+            "rays_equal": all(getattr(gstats, k) == getattr(rstats, k) for k in keys),
+            "timed_frame_equals_subset_render": bool(np.array_equal(frame[mask], sub[mask])),
+            "rays_checked": int(rstats.rays), "against": "oracle port (counter RNG, full-frame tile ids), pinned on the reference's golden vectors"}
 
 
 # ---------------------------------------------------------------------------------------------- own arm
@@ -349,11 +444,15 @@ def own_arm(args, builder, kw, desc):
                     "share_of_step": ms_trace / (dev_ms if world == 1 else max(dev_ms, 1e-9)),
                     "frac_of_8TBs": achieved / 8000.0}
 
-        # e2e: SiRenderScene with host buffers — scene arrays re-sent H2D from pinned memory, pixels D2H
-        e2e = None
+        # e2e: the same frame through SiRenderScene with HOST buffers, the same way at every N — every rank re-sends its copy
+        # of the scene arrays host -> device from pinned memory each step (what a host that edited or re-loaded the scene
+        # pays), renders its tiles, and the frame lands in host memory: N = 1 fjgpu_render_tiles into the host framebuffer;
+        # N > 1 tile blocks -> one NCCL all-gather -> rank 0 un-permutes on the device and copies the frame ONCE into pinned
+        # host memory (fjgpu_assemble_frame)
+        host_frame = None
+        s.set_resend(True)
         if world == 1:
             s.set_resident(False)
-            s.set_resend(True)
             frame()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -363,50 +462,66 @@ def own_arm(args, builder, kw, desc):
                 e_rays += st.rays
                 fb = s.framebuffer("fb1")
             t_e2e = time.perf_counter() - t0
+            host_frame = fb
             e2e = {"value": e_rays / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": s.resend_bytes(),
                    "d2h_bytes_per_step": int(fb.nbytes), "ms_per_step": 1e3 * t_e2e / args.steps,
                    "api": "libfjscene SiRenderScene -> fjgpu_scene_resend + fjgpu_render_tiles (host framebuffer)"}
-            s.set_resend(False)
         else:
-            # N > 1: the all-gathered tile blocks are copied to the host and un-permuted into the frame by rank 0
+            pinned = torch.empty((res[1], res[0], 4), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+
+            def e2e_step():
+                st_ = step()
+                if rank == 0:
+                    s.assemble_gathered(gathered.data_ptr(), world, 32, 32, pinned.data_ptr())
+                return st_
+
+            e2e_step()
             torch.cuda.synchronize()
             dist.barrier()
             t0 = time.perf_counter()
             e_rays = 0
             for _ in range(args.steps):
-                st, _, _ = step()
+                st, _, _ = e2e_step()
                 e_rays += st.rays
-                host = sharding.assemble_frame(gathered.cpu().numpy(), tiles, world, res[0], res[1]) if rank == 0 else None
             torch.cuda.synchronize()
             dist.barrier()
             t_e2e = time.perf_counter() - t0
-            er = torch.tensor([float(e_rays)], dtype=torch.float64, device="cuda")
+            er = torch.tensor([float(e_rays), float(s.resend_bytes())], dtype=torch.float64, device="cuda")
             dist.all_reduce(er, op=dist.ReduceOp.SUM)
-            e2e = {"value": float(er[0]) / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": my_tiles * 20,
-                   "d2h_bytes_per_step": int(gathered.numel() * 4), "ms_per_step": 1e3 * t_e2e / args.steps,
-                   "api": "libfjscene SiRenderScene per rank -> NCCL all_gather of tile blocks -> host frame on rank 0"}
+            if rank == 0:
+                host_frame = pinned.numpy()
+            e2e = {"value": float(er[0]) / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(er[1]),
+                   "d2h_bytes_per_step": int(res[0] * res[1] * 16), "ms_per_step": 1e3 * t_e2e / args.steps,
+                   "api": "libfjscene SiRenderScene per rank (fjgpu_scene_resend + fjgpu_render_tiles_device) -> NCCL all_gather of tile "
+                          "blocks -> fjgpu_assemble_frame on rank 0 (one copy into pinned host memory)"}
+        s.set_resend(False)
     finally:
         os.dup2(saved, 1)
         os.close(devnull)
 
+    parity = None
+    if rank == 0 and not args.no_parity and host_frame is not None:
+        parity = parity_leg(builder, kw, host_frame, ntiles=int(os.environ.get("FJ_PARITY_TILES", "6")))
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cpu = cpu_baseline_leg(builder, kw)
         except Exception as e:      # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+    if rank == 0 and parity is not None and not (parity["rmse"] < parity["bar"] and parity["rays_equal"]):
+        print(json.dumps({"error": "parity check failed", "parity": parity}))
+        raise SystemExit("bench.py: the timed frame differs from the oracle: %r" % (parity,))
     if rank == 0:
         out = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_per_step, "s_per_frame": ms_per_step * 1e-3, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": args.workload, "scene": desc, "l2": "256 MiB flush between steps; scene + 2.3 GB/frame sample stream exceed L2",
-                          "parallelism": "tiles round-robin over %d rank(s)%s" % (world, ", NCCL all_gather of tile blocks" if world > 1 else ""),
-                          "rays_per_frame": total_rays / args.steps, "camera_samples_per_frame": total_samples / args.steps,
-                          "scene_hbm_bytes": int(info.hbm_bytes), "bvh_build_s": info.build_seconds, "scene_upload_s": upload_s,
-                          "blas_nodes": int(info.blas_nodes), "blas_max_depth": int(info.blas_max_depth),
-                          "node_steps_per_ray": tot.node_steps / max(tot.rays, 1), "tri_tests_per_ray": tot.tri_tests / max(tot.rays, 1)},
+               "config": shared_config(args, desc, world),
+               "frame": {"rays_per_frame": total_rays / args.steps, "camera_samples_per_frame": total_samples / args.steps,
+                         "scene_hbm_bytes": int(info.hbm_bytes), "bvh_build_s": info.build_seconds, "scene_upload_s": upload_s,
+                         "blas_nodes": int(info.blas_nodes), "blas_max_depth": int(info.blas_max_depth),
+                         "node_steps_per_ray": tot.node_steps / max(tot.rays, 1), "tri_tests_per_ray": tot.tri_tests / max(tot.rays, 1)},
                "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": total_launches, "clocks": clk,
-               "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+               "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                "kernel_ms_per_step": {"k_extend": ms_trace / args.steps, "k_generate+k_shade": ms_shade / args.steps,
                                       "k_resolve_tiles": ms_resolve / args.steps}}
         print(json.dumps(out))
@@ -423,6 +538,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     builder, kw, desc = WORKLOADS[args.workload]
     if os.environ.get("FJ_BENCH_N"):          # experiment knob: mesh resolution of the blob (not used by the driver)

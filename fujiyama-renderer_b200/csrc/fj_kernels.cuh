@@ -333,6 +333,11 @@ struct Shading {
       }
     } else {                                                       // PathtracingShader::evaluate, pathtracing_shader.cc:125-257
       const DShader &sh = sc.shaders[slot];
+      if (sh.bump_texture) {                                       // :136-144: the integrators see the bumped normal (in_modified.N)
+        float tu, tv; hit_uv(sc, h, &tu, &tv);
+        D3 dPdu, dPdv; hit_derivatives(sc, h, key.sample, &dPdu, &dPdv);
+        N = sl_bump_mapping(sc.textures[sh.bump_texture - 1], dPdu, dPdv, tu, tv, (double)sh.bump_amplitude, N);
+      }
       sink.add(fmul(thr.r, sh.emission[0]), fmul(thr.g, sh.emission[1]), fmul(thr.b, sh.emission[2]));
       if (luminance(sh.diffuse) > 0.f && (int)cur.dd + 1 <= fr.max_diffuse) {       // integrate_diffuse :176-208
         const D3 w = N;
@@ -944,6 +949,11 @@ __global__ void __launch_bounds__(256) k_resolve_tiles(const DFrame fr, const DT
   const int w = t.xmax - t.xmin, h = t.ymax - t.ymin;
   const int npx = fr.xrate + 2 * fr.mx, npy = fr.yrate + 2 * fr.my;
   const Accum *smp = samples + (size_t)ti * wstride;
+  // `2 fx / filterwidth`: when the width is a power of two (the default 2 is) the division equals the multiplication by its
+  // reciprocal bit for bit — one FP64 multiply instead of an FP64 division per axis per (pixel, sample) pair
+  const bool pow2x = (__double_as_longlong(fr.xfw) & 0x000fffffffffffffll) == 0 && fr.xfw > 1e-300 && fr.xfw < 1e300;
+  const bool pow2y = (__double_as_longlong(fr.yfw) & 0x000fffffffffffffll) == 0 && fr.yfw > 1e-300 && fr.yfw < 1e300;
+  const double rxfw = ddiv(1., fr.xfw), ryfw = ddiv(1., fr.yfw);
   for (int p = part * blockDim.x + threadIdx.x; p < w * h; p += FJ_RESOLVE_SPLIT * blockDim.x) {
     const int px = p % w, py = p / w;
     const int x = t.xmin + px, y = t.ymin + py;
@@ -956,7 +966,8 @@ __global__ void __launch_bounds__(256) k_resolve_tiles(const DFrame fr, const DT
         const Accum s = smp[sample_slot(g, gx, gy)];
         const double fx = dsub(dmul((double)fr.xres, u), dadd((double)x, .5));
         const double fy = dsub(dmul((double)fr.yres, dsub(1., v)), dadd((double)y, .5));
-        const double xx = ddiv(dmul(2., fx), fr.xfw), yy = ddiv(dmul(2., fy), fr.yfw);
+        const double xx = pow2x ? dmul(dmul(2., fx), rxfw) : ddiv(dmul(2., fx), fr.xfw);
+        const double yy = pow2y ? dmul(dmul(2., fy), ryfw) : ddiv(dmul(2., fy), fr.yfw);
         const double wgt = exp(dmul(-2., dadd(dmul(xx, xx), dmul(yy, yy))));
         // float accumulators, double products (fj_renderer.cc:953-961: `pixel.r += wgt * sample.data.r`)
         pr = (float)dadd((double)pr, dmul(wgt, (double)from_fix(s.r)));

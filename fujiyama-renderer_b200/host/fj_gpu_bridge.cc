@@ -163,7 +163,9 @@ bool flatten_shader(const ShaderRecord &r, const std::map<const Texture *, int> 
     if (!prop(r, "ior", v)) return false;
     o->ior = (float)std::max(.001, (double)(float)v[0]);
     o->opacity = 1;
-    o->texture = tex_slot("diffuse_map");
+    o->texture = tex_slot("diffuse_map"); o->bump_texture = tex_slot("bump_map");
+    if (!prop(r, "bump_amplitude", v)) return false;
+    o->bump_amplitude = (float)v[0];
   } else return false;
   return true;
 }

@@ -434,8 +434,8 @@ fjgpu_shader flatten_shader(const Scene &sc, const Shader &s) {
   o.kind = kind;
   auto P = [&](const char *n) { return s.props.find(n)->second; };
   { int tt, ti; if (s.texture != SI_BADID && decode_id(s.texture, &tt, &ti) && tt == Type_Texture && kind != FJGPU_SHADER_GLASS) o.texture = ti + 1; }
-  { int tt, ti; if (s.bump != SI_BADID && decode_id(s.bump, &tt, &ti) && tt == Type_Texture && kind == FJGPU_SHADER_PLASTIC) o.bump_texture = ti + 1; }
-  if (kind == FJGPU_SHADER_PLASTIC) o.bump_amplitude = (float)P("bump_amplitude")[0];     // set_bump_amplitude, default 1 (used only with a bump_map)
+  { int tt, ti; if (s.bump != SI_BADID && decode_id(s.bump, &tt, &ti) && tt == Type_Texture && (kind == FJGPU_SHADER_PLASTIC || kind == FJGPU_SHADER_PATHTRACING)) o.bump_texture = ti + 1; }
+  if (kind == FJGPU_SHADER_PLASTIC || kind == FJGPU_SHADER_PATHTRACING) o.bump_amplitude = (float)P("bump_amplitude")[0];     // set_bump_amplitude, default 1 (used only with a bump_map)
   if (kind == FJGPU_SHADER_CONSTANT) {                                      // constant_shader.cc:96-107
     for (int k = 0; k < 3; k++) o.diffuse[k] = clamp0(P("diffuse")[k]);
   } else if (kind == FJGPU_SHADER_PLASTIC) {                                // plastic_shader.cc:183-273
@@ -922,7 +922,7 @@ Status SiAssignTexture(ID id, const char *name, ID texture) {
   const int kind = the_scene->plugins[sh->plugin].kind;
   const std::string n(name);
   const bool okname = (kind == FJGPU_SHADER_CONSTANT && n == "texture") || ((kind == FJGPU_SHADER_PLASTIC || kind == FJGPU_SHADER_PATHTRACING) && n == "diffuse_map");
-  if (kind == FJGPU_SHADER_PLASTIC && n == "bump_map") { sh->bump = texture; return ok(); }      // SlBumpMapping, src/fj_shading.cc:418-465
+  if ((kind == FJGPU_SHADER_PLASTIC || kind == FJGPU_SHADER_PATHTRACING) && n == "bump_map") { sh->bump = texture; return ok(); }      // SlBumpMapping, src/fj_shading.cc:418-465
   if (!okname) return failmsg("AssignTexture " + n + ": no device implementation of this texture property");
   sh->texture = texture;
   return ok();

@@ -109,8 +109,8 @@ typedef struct fjgpu_shader {
   float transmit[3];
   float ior;
   float opacity;
-  int32_t bump_texture;     /* plastic `bump_map`: 1 + texture index, 0 = none (SlBumpMapping, src/fj_shading.cc:418-465) */
-  float bump_amplitude;     /* plastic `bump_amplitude` (plastic_shader.cc:293-300) */
+  int32_t bump_texture;     /* plastic / pathtracing `bump_map`: 1 + texture index, 0 = none (SlBumpMapping, src/fj_shading.cc:418-465) */
+  float bump_amplitude;     /* `bump_amplitude` (plastic_shader.cc:293-300, pathtracing_shader.cc:457-465) */
 } fjgpu_shader;
 
 int fjgpu_shaders_set(fjgpu_context *ctx, int32_t n, const fjgpu_shader *shaders);

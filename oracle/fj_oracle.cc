@@ -863,8 +863,11 @@ void eval_plastic(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, const
   *Os = sh.opacity;
 }
 
-// PathtracingShader::evaluate + integrate_*, shaders/pathtracing_shader/pathtracing_shader.cc:125-257 (no maps)
-void eval_pathtracing(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, const SurfIn &in, Col *Cs, float *Os) {
+// PathtracingShader::evaluate + integrate_*, shaders/pathtracing_shader/pathtracing_shader.cc:125-257 (diffuse_map :132-135,
+// bump_map :136-144: every integrator sees the bumped normal)
+void eval_pathtracing(RenderState &rs, const Cxt &cxt, const fjgpu_shader &sh, const SurfIn &in_, Col *Cs, float *Os) {
+  SurfIn in = in_;
+  if (sh.bump_texture) in.N = SlBumpMapping(rs.s->textures[sh.bump_texture - 1], in_.dPdu, in_.dPdv, in_.tu, in_.tv, sh.bump_amplitude, in_.N);
   const Col diffuse(sh.diffuse[0], sh.diffuse[1], sh.diffuse[2]);
   const Col reflect(sh.reflect[0], sh.reflect[1], sh.reflect[2]);
   const Col refract(sh.refract[0], sh.refract[1], sh.refract[2]);

@@ -47,6 +47,14 @@ def main():
     if sys.argv[1:] == ["config2"]:
         config2_region(os.path.join(REPO, "tests", "golden"))
         return
+    if len(sys.argv) == 3 and sys.argv[1] == "add":        # one more scene into ref_images.npz, the others untouched
+        path = os.path.join(REPO, "tests", "golden", "ref_images.npz")
+        imgs = dict(np.load(path))
+        with tempfile.TemporaryDirectory() as tmp:
+            imgs[sys.argv[2]], secs = sk.reference_render(golden_scenes.SCENES[sys.argv[2]](), os.path.join(tmp, sys.argv[2]), threads=1)
+        np.savez_compressed(path, **imgs)
+        print("%-16s %s  %.3fs  mean %.6f" % (sys.argv[2], imgs[sys.argv[2]].shape, secs, imgs[sys.argv[2]].mean()))
+        return
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(sk.REF_DIR, "lib"))
     txt = subprocess.check_output([os.path.join(sk.REF_DIR, "bin", "ref_probe"), "vectors"], env=env)
     gold = os.path.join(REPO, "tests", "golden")

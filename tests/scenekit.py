@@ -366,6 +366,7 @@ class SceneDesc:
             sh.do_color_filter = 0 if all(x == 1 for x in tr) else 1
             sh.ior = max(float(f32(.001)), float(f32(props.get("ior", 1.4))))
             sh.opacity = 1.0
+            sh.bump_amplitude = float(f32(props.get("bump_amplitude", 1)))
         return sh
 
     def to_structs(self):
@@ -416,7 +417,7 @@ class SceneDesc:
             for k, v in props.items():
                 if isinstance(v, str):
                     assert (kind, k) in (("constant", "texture"), ("plastic", "diffuse_map"), ("pathtracing", "diffuse_map"),
-                                         ("plastic", "bump_map"))
+                                         ("plastic", "bump_map"), ("pathtracing", "bump_map"))
                     if k == "bump_map":
                         shs[i].bump_texture = tex_ids[v] + 1
                     else:
