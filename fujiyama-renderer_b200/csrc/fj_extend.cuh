@@ -125,11 +125,6 @@ __device__ __forceinline__ void load_leaf_triangle(const RenderArgs &a, const Ra
   }
 }
 
-// MAGIC: the 24 byte -> float conversions of a quantised node step without the conversion unit.  `I2F.U8` issues to the XU
-// pipe (16 lanes per clock per SM; ncu: the busiest execution pipe of this kernel at 45 %); here one PRMT drops the byte into
-// the mantissa of 0.5 (bits 16-23: 0.5 + q / 256, exact) and the node's FMA constants absorb the offset:
-//   q s' + b  =  (0.5 + q / 256) (256 s') + (b - 128 s'),   b' = fma(-128, s', b) rounded once: <= 2^-24 (|b| + 128 |s'|)
-// — one more rounding of the size the 2^-20 widening of the box ray already covers (fj_kernels.cuh box_axis).
 // pop: the shared-memory load is unconditional (clamped index), the local-memory entry replaces it in the rare deep case
 template <int SD>
 __device__ __forceinline__ int xpop_(const int (*sstack)[FJ_XT], const int *lstack, int &sp, int tid) {
@@ -139,7 +134,7 @@ __device__ __forceinline__ int xpop_(const int (*sstack)[FJ_XT], const int *lsta
   return v;
 }
 
-template <int MINB, bool STATS, bool QUANT, bool COOP = false, int SD = 12, bool TOP = false, bool MAGIC = false>
+template <int MINB, bool STATS, bool QUANT, bool COOP = false, int SD = 12, bool TOP = false>
 __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   __shared__ ExtShared S;
   __shared__ int sstack[SD][FJ_XT];             // the first SD stack entries of every lane (entry-major: bank = lane)
@@ -250,16 +245,11 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           float bnx = fmaf(A.a.x, br.ix, gx ? br.hx : br.lx), bfx = fmaf(A.a.x, br.ix, gx ? br.lx : br.hx);
           float bny = fmaf(A.a.y, br.iy, gy ? br.hy : br.ly), bfy = fmaf(A.a.y, br.iy, gy ? br.ly : br.hy);
           float bnz = fmaf(A.a.z, br.iz, gz ? br.hz : br.lz), bfz = fmaf(A.a.z, br.iz, gz ? br.lz : br.hz);
-          if (MAGIC) {      // bytes enter as 0.5 + q / 256: scale by 256, take 128 s' off the bases
-            bnx = fmaf(-128.f, six, bnx); bfx = fmaf(-128.f, six, bfx); six = __fmul_rn(six, 256.f);
-            bny = fmaf(-128.f, siy, bny); bfy = fmaf(-128.f, siy, bfy); siy = __fmul_rn(siy, 256.f);
-            bnz = fmaf(-128.f, siz, bnz); bfz = fmaf(-128.f, siz, bfz); siz = __fmul_rn(siz, 256.f);
-          }
           const unsigned qlx = __float_as_uint(A.b.x), qhx = __float_as_uint(A.b.y), qly = __float_as_uint(A.b.z), qhy = __float_as_uint(A.b.w);
           const unsigned qlz = __float_as_uint(Q.a.x), qhz = __float_as_uint(Q.a.y);
           const unsigned qnx = gx ? qhx : qlx, qfx = gx ? qlx : qhx, qny = gy ? qhy : qly, qfy = gy ? qly : qhy, qnz = gz ? qhz : qlz, qfz = gz ? qlz : qhz;
           ch = make_int4(__float_as_int(Q.a.z), __float_as_int(Q.a.w), __float_as_int(Q.b.x), __float_as_int(Q.b.y));
-#define FJ_Q2F(W, K) (MAGIC ? __uint_as_float(__byte_perm((W), 0x3F000000u, 0x7044u + 0x100u * K)) : (float)(((W) >> (8 * K)) & 255u))
+#define FJ_Q2F(W, K) ((float)(((W) >> (8 * K)) & 255u))
 #define FJ_CHILD(KEY, K)                                                                                                        \
           {                                                                                                                        \
             const float nx_ = fmaf(FJ_Q2F(qnx, K), six, bnx), fx_ = fmaf(FJ_Q2F(qfx, K), six, bfx);                               \

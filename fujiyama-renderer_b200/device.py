@@ -145,6 +145,15 @@ class Device:
                                                     C.c_void_p(dev_ptr), C.byref(stats)))
         return stats
 
+    def assemble_frame(self, gathered_ptr, nranks, tile_w, tile_h, tiles, xres, yres, frame=None):
+        """fjgpu_assemble_frame: all-gathered tile blocks (device pointer, rank order) -> host frame [yres, xres, 4]."""
+        ta = tiles if not isinstance(tiles, (list, tuple)) else tile_array(tiles)
+        if frame is None:
+            frame = np.zeros((yres, xres, 4), np.float32)
+        self._ck(self.lib.fjgpu_assemble_frame(self.ctx, C.c_void_p(gathered_ptr), nranks, tile_w, tile_h, ta, len(tiles),
+                                               xres, yres, frame.ctypes.data_as(C.c_void_p)))
+        return frame
+
     def trace_closest(self, group, orig, dirs, tmin, tmax, flags=0):
         orig = np.ascontiguousarray(orig, np.float64)
         dirs = np.ascontiguousarray(dirs, np.float64)
@@ -166,3 +175,18 @@ class Device:
         self._ck(self.lib.fjgpu_render_tile_samples(self.ctx, C.byref(params), C.byref(t), n.value, _dp(uv), _fp(rgba),
                                                     C.byref(n)))
         return uv, rgba
+
+
+def render_frame_multi(devices, params, tiles, frame=None):
+    """fjgpu_render_frame_multi: ONE process, one Device per GPU with the same scene loaded on each; tiles dealt round-robin,
+    one NCCL all-gather, rank 0 assembles.  Returns (frame [yres, xres, 4], [Stats per device])."""
+    lib = devices[0].lib
+    ta = tiles if not isinstance(tiles, (list, tuple)) else tile_array(tiles)
+    if frame is None:
+        frame = np.zeros((params.yres, params.xres, 4), np.float32)
+    ctxs = (C.c_void_p * len(devices))(*[d.ctx for d in devices])
+    stats = (abi.Stats * len(devices))()
+    rc = lib.fjgpu_render_frame_multi(ctxs, len(devices), C.byref(params), ta, len(tiles), _fp(frame), stats)
+    if rc != 0:
+        raise FjGpuError(rc, (lib.fjgpu_last_error(devices[0].ctx) or b"").decode())
+    return frame, list(stats)

@@ -81,8 +81,8 @@ def test_fallbacks_live_in_the_reference(tmp_path):
     assert "without a device kind; rendering on the CPU workers" in res.stderr
     # the adaptive sampler: CPU workers
     d = golden_scenes.SCENES["cube_3x3"]()
-    txt = d.to_scn(str(tmp_path / "c"), os.path.join(str(tmp_path / "c"), "out.fb"), threads=2, plugin_dir=os.path.join(BR, "lib"))
     os.makedirs(str(tmp_path / "c"), exist_ok=True)
+    txt = d.to_scn(str(tmp_path / "c"), os.path.join(str(tmp_path / "c"), "out.fb"), threads=2, plugin_dir=os.path.join(BR, "lib"))
     txt = txt.replace("RenderScene ren1", "SetProperty1 ren1 sampler_type 1\nRenderScene ren1")
     scn = os.path.join(str(tmp_path / "c"), "scene.scn")
     open(scn, "w").write(txt)
