@@ -394,7 +394,7 @@ def own_arm(args, builder, kw, desc):
             st, info, _ = step()
             flush.zero_()                   # L2 flush between timed iterations (256 MiB > 126 MB L2)
             for f, _t in abi.Stats._fields_:
-                if f.startswith("rays_") or f in ("camera_samples", "hit_mesh_levels", "node_steps", "tri_tests"):
+                if f.startswith("rays_") or f in ("camera_samples", "hit_mesh_levels", "node_steps", "tri_tests", "leaf_phases", "leaf_rounds"):
                     setattr(tot, f, getattr(tot, f) + getattr(st, f))
             ms_trace += st.ms_trace
             ms_resolve += st.ms_resolve
@@ -519,7 +519,8 @@ def own_arm(args, builder, kw, desc):
                "frame": {"rays_per_frame": total_rays / args.steps, "camera_samples_per_frame": total_samples / args.steps,
                          "scene_hbm_bytes": int(info.hbm_bytes), "bvh_build_s": info.build_seconds, "scene_upload_s": upload_s,
                          "blas_nodes": int(info.blas_nodes), "blas_max_depth": int(info.blas_max_depth),
-                         "node_steps_per_ray": tot.node_steps / max(tot.rays, 1), "tri_tests_per_ray": tot.tri_tests / max(tot.rays, 1)},
+                         "node_steps_per_ray": tot.node_steps / max(tot.rays, 1), "tri_tests_per_ray": tot.tri_tests / max(tot.rays, 1),
+                         "tri_pairs_per_leaf_phase": tot.tri_tests / max(tot.leaf_phases, 1), "rounds_per_leaf_phase": tot.leaf_rounds / max(tot.leaf_phases, 1)},
                "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": total_launches, "clocks": clk,
                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                "kernel_ms_per_step": {"k_extend": ms_trace / args.steps, "k_generate+k_shade": ms_shade / args.steps,

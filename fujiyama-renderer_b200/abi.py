@@ -78,7 +78,8 @@ class Stats(C.Structure):
                 ("ms_trace", C.c_float), ("ms_resolve", C.c_float),
                 ("ms_total", C.c_float), ("ms_shade", C.c_float),
                 ("batches", C.c_uint32), ("queue_regrows", C.c_uint32),
-                ("first_regrow_batch", C.c_int32), ("_pad", C.c_uint32)]
+                ("first_regrow_batch", C.c_int32), ("_pad", C.c_uint32),
+                ("leaf_phases", C.c_uint64), ("leaf_rounds", C.c_uint64)]
 
     @property
     def rays(self):

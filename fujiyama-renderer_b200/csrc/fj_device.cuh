@@ -134,7 +134,7 @@ struct DFrame {
   const uint32_t *jitter_tab;     // first 2*max_ns draws of a default-seeded XorShift (fj_random.cc:10-43)
 };
 struct DTile { int32_t id, xmin, ymin, xmax, ymax; };
-struct DCounters { unsigned long long rays[5]; unsigned long long samples; unsigned long long hits; unsigned long long levels; unsigned long long node_steps; unsigned long long tri_tests; };
+struct DCounters { unsigned long long rays[5]; unsigned long long samples; unsigned long long hits; unsigned long long levels; unsigned long long node_steps; unsigned long long tri_tests; unsigned long long leaf_phases, leaf_rounds; };
 
 struct Hit { double t, u, v; int32_t prim, inst; };
 

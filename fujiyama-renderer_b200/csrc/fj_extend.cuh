@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   BoxRayMM br; br.ix = br.iy = br.iz = br.lx = br.ly = br.lz = br.hx = br.hy = br.hz = 0.f;
   const char *nodes = nullptr;                  // 4-wide nodes of the tree being walked: Node128, or NodeQ64 when QUANT
   unsigned n_steps = 0, n_tris = 0;             // warp totals (every lane carries the same value)
+  unsigned n_phases = 0, n_rounds = 0;
 
 #pragma unroll 1
   for (;;) {
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
       unsigned char *pm = pairmap[tid >> 5];
       for (int k = 0; k < cnt; k++) pm[off + k] = (unsigned char)(lane | (k << 5));
       __syncwarp();
-      if (STATS) n_tris += (unsigned)total;
+      if (STATS) { n_tris += (unsigned)total; n_phases++; n_rounds += (unsigned)(total + 31) >> 5; }
       const double tmin = S.tmin[tid];
       double best_t = S.best_t[tid]; bool found = (st & XS_FOUND) != 0;       // owner state (unused on lanes without a leaf)
       for (int R = 0; R < total; R += 32) {
@@ -456,7 +457,10 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
     }
   }
   // traversal statistics (4-wide node steps and exact triangle tests) for DESIGN.md / bench.py
-  if (STATS && (tid & 31) == 0 && a.counters) { atomicAdd(&a.counters->node_steps, (unsigned long long)n_steps); atomicAdd(&a.counters->tri_tests, (unsigned long long)n_tris); }
+  if (STATS && (tid & 31) == 0 && a.counters) {
+    atomicAdd(&a.counters->node_steps, (unsigned long long)n_steps); atomicAdd(&a.counters->tri_tests, (unsigned long long)n_tris);
+    atomicAdd(&a.counters->leaf_phases, (unsigned long long)n_phases); atomicAdd(&a.counters->leaf_rounds, (unsigned long long)n_rounds);
+  }
 #undef XPUSH
 #undef XPOP
 }

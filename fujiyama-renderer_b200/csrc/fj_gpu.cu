@@ -790,6 +790,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
     stats->rays_camera = hc.rays[0]; stats->rays_shadow = hc.rays[1]; stats->rays_diffuse = hc.rays[2];
     stats->rays_reflect = hc.rays[3]; stats->rays_refract = hc.rays[4]; stats->camera_samples = hc.samples;
     stats->rays_hit = hc.hits; stats->hit_mesh_levels = hc.levels; stats->node_steps = hc.node_steps; stats->tri_tests = hc.tri_tests;
+    stats->leaf_phases = hc.leaf_phases; stats->leaf_rounds = hc.leaf_rounds;
     float ms_trace = 0, ms_shade = 0, ms_resolve = 0, t = 0;
     for (size_t i = 0; i + 1 < ev_extend.size(); i += 2) { cudaEventElapsedTime(&t, ev_extend[i], ev_extend[i + 1]); ms_trace += t; }
     for (size_t i = 0; i + 1 < ev_shade.size(); i += 2) { cudaEventElapsedTime(&t, ev_shade[i], ev_shade[i + 1]); ms_shade += t; }

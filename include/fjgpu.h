@@ -223,6 +223,7 @@ typedef struct fjgpu_stats {
   uint32_t queue_regrows;           /* batches rendered again because a branching ray tree overflowed the optimistic ray queue */
   int32_t  first_regrow_batch;      /* index of the first such batch, -1 if none */
   uint32_t _pad;
+  uint64_t leaf_phases, leaf_rounds; /* k_extend2: warp-level leaf phases and the rounds of 32 (ray, triangle) pairs they took */
 } fjgpu_stats;
 
 /* Renders `ntiles` tiles (sampler -> camera rays -> trace/shade -> Gaussian resolve), i.e. the
