@@ -245,6 +245,10 @@ void build_bvh(const Aabb *prims, int32_t n, int max_leaf, float leaf_cost, int 
       const BNode c = B.nodes[slots[best]];
       slots[best] = c.left; slots[ns++] = c.right;
     }
+    // slot order = tie-break of the walk (children whose entry distances are equal are visited in slot order — a ray that
+    // starts inside several child boxes): smaller boxes first, they hold the nearer geometry more often (an object inside an
+    // enclosing environment mesh is walked before the environment and cuts its traversal short)
+    std::sort(slots, slots + ns, [&](int32_t x, int32_t y) { return box_area(B.nodes[x].box) < box_area(B.nodes[y].box); });
     Node128 w = empty4;
     for (int k = 0; k < ns; k++) {
       const BNode &c = B.nodes[slots[k]];

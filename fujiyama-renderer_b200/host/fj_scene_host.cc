@@ -612,7 +612,10 @@ Status render(Scene &sc, Renderer &r) {
   Flat f;
   if (flatten(sc, r, &f) != SI_SUCCESS) return SI_FAIL;
   // preprocess_framebuffer, src/fj_renderer.cc:805-815: Resize clears the buffer
-  fb->w = r.res[0]; fb->h = r.res[1]; fb->c = 4; fb->px.assign((size_t)fb->w * fb->h * 4, 0.f);
+  // (the host frame is neither written nor read while the tiles stay on the device — device blocks for the host's all-gather,
+  // resident frame of the bench leg: no 33-MB clear per frame on those paths)
+  fb->w = r.res[0]; fb->h = r.res[1]; fb->c = 4;
+  if (g_dev_blocks || g_resident) fb->px.resize((size_t)fb->w * fb->h * 4); else fb->px.assign((size_t)fb->w * fb->h * 4, 0.f);
   // GPUs of this process: FJ_GPU_COUNT (or fjscene_set_gpu_count) contexts on consecutive devices from g_device on, the scene
   // replicated on each; tiles are dealt to them by fjgpu_render_frame_multi (one all-gather ends the frame)
   int ngpu = g_gpu_count > 0 ? g_gpu_count : 1;

@@ -263,7 +263,7 @@ def test_queue_overflow_in_a_later_batch_grows_and_retries(sk, device, monkeypat
     a, sa = gpu_render(device, desc, st)
     ref, rstats = sk.oracle_render(desc, rng_mode=0, threads=8, st=st)
     assert rstats.rays_reflect > 0 and rstats.rays_refract > 0
-    assert sa.batches == 1 and sa.queue_regrows == 1 and sa.first_regrow_batch == 0      # one batch: the overflow is in batch 0
+    assert sa.batches == 1 and sa.queue_regrows >= 1 and sa.first_regrow_batch == 0      # one batch: the overflow is in batch 0
     monkeypatch.setenv("FJGPU_SAMPLE_MB", "1")         # one or two tiles per batch
     b, sb = gpu_render(device, desc, st)
     assert np.array_equal(a, b)
