@@ -141,8 +141,9 @@ struct Hit { double t, u, v; int32_t prim, inst; };
 // ------------------------------------------------------------------------------------------ RNG
 // Philox-4x32-10 (Salmon et al., SC'11), keyed exactly like oracle/fj_oracle.cc ctr_rand so that the
 // stochastic shaders can be checked sample-for-sample.
-__device__ __forceinline__ double ctr_rand(uint32_t seed, uint32_t tile, uint32_t sample, unsigned long long node, uint32_t dim) {
-  uint32_t c0 = (uint32_t)node, c1 = (uint32_t)(node >> 32), c2 = dim >> 2, c3 = 0x46554a49u;
+// One Philox block = the four draws of dimensions 4 (dim >> 2) .. 4 (dim >> 2) + 3.
+__device__ __forceinline__ void ctr_block(uint32_t seed, uint32_t tile, uint32_t sample, unsigned long long node, uint32_t block, uint32_t out[4]) {
+  uint32_t c0 = (uint32_t)node, c1 = (uint32_t)(node >> 32), c2 = block, c3 = 0x46554a49u;
   uint32_t k0 = seed ^ (tile * 0x9E3779B1u), k1 = sample;
 #pragma unroll
   for (int r = 0; r < 10; r++) {
@@ -152,8 +153,22 @@ __device__ __forceinline__ double ctr_rand(uint32_t seed, uint32_t tile, uint32_
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  const uint32_t pick = (dim & 3) == 0 ? c0 : ((dim & 3) == 1 ? c1 : ((dim & 3) == 2 ? c2 : c3));
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double ctr_rand(uint32_t seed, uint32_t tile, uint32_t sample, unsigned long long node, uint32_t dim) {
+  uint32_t c[4];
+  ctr_block(seed, tile, sample, node, dim >> 2, c);
+  const uint32_t pick = (dim & 3) == 0 ? c[0] : ((dim & 3) == 1 ? c[1] : ((dim & 3) == 2 ? c[2] : c[3]));
   return ddiv((double)pick, 4294967295.0);     // XorShift::NextFloat01 mapping (fj_random.cc:40-43)
+}
+// The draws of dimensions `dim` and `dim + 1`, dim even: both lie in one block — one Philox evaluation instead of two
+// (the same values as two ctr_rand calls).
+__device__ __forceinline__ void ctr_rand2(uint32_t seed, uint32_t tile, uint32_t sample, unsigned long long node, uint32_t dim, double *a, double *b) {
+  uint32_t c[4];
+  ctr_block(seed, tile, sample, node, dim >> 2, c);
+  const bool hi = (dim & 2u) != 0;
+  *a = ddiv((double)(hi ? c[2] : c[0]), 4294967295.0);
+  *b = ddiv((double)(hi ? c[3] : c[1]), 4294967295.0);
 }
 
 // ------------------------------------------------------------------------------------------ traversal

@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           }
           node = IDLE;
         } else if (node == SENTINEL) {             // the instance's BLAS is done: back to the instance tree (its nodes and box
-          st &= ~(XS_BLAS | XS_WORLD);             // ray are fetched again only if an inner node of that tree is still to be visited)
+          st &= ~(XS_BLAS | XS_WORLD | XS_TOP);    // ray are fetched again only if an inner node of that tree is still to be visited)
           if (sp > 0) node = XPOP(); else node = DONE;
         } else if (st & XS_BLAS) {                 // a second triangle leaf: park it now that the slot is free
           S.leaf[tid] = node; st |= XS_LEAF; node = XPOP();

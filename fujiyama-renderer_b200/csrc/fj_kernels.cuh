@@ -156,7 +156,11 @@ struct Shading {
         if (lt.kind == 0) {                                        // fj_point_light.cc:21-39
           ls.P = mk(lt.translate[0], lt.translate[1], lt.translate[2]);
         } else if (lt.kind == 1) {                                 // fj_rectangle_light.cc:26-47
-          const double x = dsub(rnd(node, dim), .5), z = dsub(rnd(node, dim + 1), .5); dim += 2;
+          double rx, rz;
+          if (dim & 1u) { rx = rnd(node, dim); rz = rnd(node, dim + 1); }      // (odd only after a sphere light's 3-draw tries)
+          else ctr_rand2(key.seed, key.tile, key.sample, node, dim, &rx, &rz);
+          dim += 2;
+          const double x = dsub(rx, .5), z = dsub(rz, .5);
           ls.P = mat_point(lt.fwd, mk(x, 0., z)); ls.N = gridN;
         } else if (lt.kind == 2) {                                 // fj_sphere_light.cc:22-46, XorShift::HollowSphereRand
           D3 p; double dd;

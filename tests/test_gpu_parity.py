@@ -267,8 +267,9 @@ def test_queue_overflow_in_a_later_batch_grows_and_retries(sk, device, monkeypat
     monkeypatch.setenv("FJGPU_SAMPLE_MB", "1")         # one or two tiles per batch
     b, sb = gpu_render(device, desc, st)
     assert np.array_equal(a, b)
-    for k in ("rays_camera", "rays_diffuse", "rays_reflect", "rays_refract", "camera_samples", "rays_hit"):
+    for k in ("rays_camera", "rays_diffuse", "rays_reflect", "rays_refract", "camera_samples"):
         assert getattr(sa, k) == getattr(sb, k) == getattr(rstats, k), k
+    assert sa.rays_hit == sb.rays_hit and sa.hit_mesh_levels == sb.hit_mesh_levels
     assert sb.batches > 4 and sb.queue_regrows >= 1 and sb.first_regrow_batch > 0        # the case round 1 refused
     assert rmse(b, ref).max() < RMSE_BAR
 
@@ -499,7 +500,10 @@ def test_extend_variants_bit_exact(sk, device, scene, monkeypatch):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
-            t, u, v, p, i = dev.trace_closest(0, o, d, tmin, tmax, 0)
+            try:
+                t, u, v, p, i = dev.trace_closest(0, o, d, tmin, tmax, 0)
+            except Exception as e:
+                raise AssertionError("variant %s: %s" % (name, e))
             assert np.array_equal(i, ri), name
             assert np.array_equal(t, rt), name
             same = p == rp
