@@ -143,6 +143,7 @@ inline void xpoint(const double *m, const double p[3], double out[3]) {
 }
 
 #define FJGPU_TOP_NODES_DEFAULT 0
+#define FJGPU_FARKEY_DEFAULT 0
 int env_int(const char *name, int def) { const char *s = getenv(name); return s && *s ? atoi(s) : def; }
 
 // ---- scene commit: instances, TLAS per object group, shader/light tables ------------------------
@@ -405,8 +406,8 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
   if (int rc = commit_scene(ctx)) return rc;
   if (p->target_group < 0 || p->target_group >= ctx->sc.ngroups) return fail(ctx, FJGPU_ERR_INVALID, "target_group out of range");
   if (p->max_diffuse_depth < 0 || p->max_reflect_depth < 0 || p->max_refract_depth < 0 ||
-      2 * (p->max_diffuse_depth + p->max_reflect_depth + p->max_refract_depth) + 1 > FJ_PENDING)
-    return fail(ctx, FJGPU_ERR_UNSUPPORTED, "max_*_depth: 2*(diffuse+reflect+refract)+1 exceeds the per-path ray stack");
+      p->max_diffuse_depth + p->max_reflect_depth + p->max_refract_depth > 250)
+    return fail(ctx, FJGPU_ERR_INVALID, "max_*_depth out of range");
   fj::DFrame &fr = pl->fr;
   memset(&fr, 0, sizeof fr);
   fr.xres = p->xres; fr.yres = p->yres; fr.xrate = p->xrate; fr.yrate = p->yrate;
@@ -489,9 +490,10 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
   // batch so the per-batch buffers (accumulators + two ray queues + hit records) stay bounded
   double block = 0;
   frontier(ctx, p, &pl->waves, &pl->peak, &block);
-  if (block > 254) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "more than 253 light samples per shading point");
-  // ray trees that can branch start optimistic (grown on overflow); shadow-ray blocks are sized for the worst case at once
-  pl->factor0 = block > 0 ? pl->peak : std::min(pl->peak, 2.0);
+  if (block > 1023) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "more than 1022 light samples per shading point");
+  // ray trees that can branch start optimistic — two rays per sample slot, each with its shadow-ray block — and the queue is
+  // grown when a batch overflows it (any batch: render_impl); a tree that cannot branch gets its exact worst case at once
+  pl->factor0 = std::min(pl->peak, 2.0 * (1.0 + block));
   // budget of the per-batch buffers: FJGPU_SAMPLE_MB (default 16 GiB), never more than 80 % of what the device has free
   // now plus what this context already holds for the purpose
   size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 16384) << 20;
@@ -513,7 +515,7 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
 
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
-template <int MINB, bool QUANT, bool COOP, int SD, bool TOP>
+template <int MINB, bool QUANT, bool COOP, int SD, bool TOP, bool FARKEY = false>
 void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   // shared-memory carveout: MINB CTAs x (static + dynamic shared memory + 1 KB the driver reserves per CTA), the rest stays L1
   const size_t dyn = TOP ? (size_t)a.top_count * 64 : 0;
@@ -523,11 +525,11 @@ void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   if (done != per_cta) {
     int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * per_cta / (228.0 * 1024)));
     pct = env_int("FJGPU_CARVEOUT_PCT", pct);
-    if (dyn) cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (dyn) cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, FARKEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, FARKEY>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     done = per_cta;
   }
-  fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP><<<blocks, FJ_XT, dyn, ctx->stream>>>(a);
+  fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, FARKEY><<<blocks, FJ_XT, dyn, ctx->stream>>>(a);
 }
 
 // The closest-hit kernel of one wavefront round.  FJGPU_EXTEND=1 selects the register-resident first version (kept as
@@ -557,6 +559,7 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
       if (minb >= 8) launch_extend2<8, true, true, 8, false>(ctx, a, cap);
       else if (minb == 7 && sd >= 16) launch_extend2<7, true, true, 16, false>(ctx, a, cap);
       else if (minb == 7 && sd <= 8) launch_extend2<7, true, true, 8, false>(ctx, a, cap);
+      else if (minb == 7 && env_int("FJGPU_FARKEY", FJGPU_FARKEY_DEFAULT) != 0) launch_extend2<7, true, true, 12, false, true>(ctx, a, cap);
       else if (minb == 7) launch_extend2<7, true, true, 12, false>(ctx, a, cap);
       else launch_extend2<6, true, true, 16, false>(ctx, a, cap);
     } else if (quant) {
@@ -596,6 +599,8 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
   const size_t block_floats = (size_t)pl.bw * pl.bh * 4;
   const bool fp64_boxes = (p->flags & FJGPU_FLAG_FP64_BOXES) != 0;
   const bool mega = fp64_boxes || (p->flags & FJGPU_FLAG_MEGAKERNEL) != 0 || env_int("FJGPU_MEGAKERNEL", 0) != 0;
+  if (mega && 2 * (p->max_diffuse_depth + p->max_reflect_depth + p->max_refract_depth) + 1 > FJ_PENDING)      // (the cross-check path only)
+    return fail(ctx, FJGPU_ERR_UNSUPPORTED, "megakernel: 2*(diffuse+reflect+refract)+1 exceeds the per-path ray stack");
 
   if (int rc = dev_upload(ctx, ctx->d_tiles, tiles, (size_t)ntiles * sizeof(fjgpu_tile))) return rc;
   if (int rc = dev_alloc(ctx, ctx->d_samples, (size_t)pl.tiles_per_batch * pl.wstride * sizeof(fj::Accum))) return rc;
@@ -666,8 +671,8 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         if (want > 4.0e9) return fail(ctx, FJGPU_ERR_UNSUPPORTED, "ray tree too wide for one tile's ray queue");
         // chunked slot reservation (fj_kernels.cuh, QueueSink): every k_shade warp may leave up to FJ_QCHUNK + FJ_QRESERVE
         // reserved slots as fillers, on top of the records the ray tree can produce
-        bool moving = !ctx->cam_motion.empty();            // RayRec::key carries the time-table entry then: no sorting
-        for (auto &kv : ctx->inst_motion) moving = moving || !kv.second.empty();
+        bool moving = !ctx->cam_motion.empty() || ctx->sc.time_tab != nullptr;      // RayRec::key carries the time-table entry then (moving
+        for (auto &kv : ctx->inst_motion) moving = moving || !kv.second.empty();      // transforms, moving triangles): no sorting
         const int sort_bits = pl.waves > 1 && !moving ? std::min(7, std::max(0, env_int("FJGPU_SORT_BITS", 0))) : 0;
         // (the RAY_DEAD fillers of a chunked queue are not filed under a sort key: sorting takes one atomic per spawn)
         const bool chunked = !has_plastic && sort_bits == 0 && env_int("FJGPU_QUEUE_CHUNK", 1) != 0;

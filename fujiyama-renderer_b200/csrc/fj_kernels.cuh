@@ -776,12 +776,12 @@ struct QueueSink {
     base = __shfl_sync(m, base, leader);
     put(base + __popc(m & ((1u << lane) - 1)), c);
   }
-  // `n` (<= 255) contiguous slots for this lane; one atomic for the lanes that arrive together (prefix sums by bit plane)
+  // `n` (<= 1023) contiguous slots for this lane; one atomic for the lanes that arrive together (prefix sums by bit plane)
   __device__ __forceinline__ unsigned reserve(unsigned n) {
     const unsigned m = __activemask(), lt = (1u << lane) - 1u;
     unsigned before = 0, total = 0;
 #pragma unroll
-    for (int b = 0; b < 8; b++) {
+    for (int b = 0; b < 10; b++) {
       const unsigned plane = __ballot_sync(m, (n >> b) & 1u);
       before += (unsigned)__popc(plane & lt) << b; total += (unsigned)__popc(plane) << b;
     }
