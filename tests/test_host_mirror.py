@@ -216,3 +216,32 @@ def test_tile_sharding_ranks_partition_the_frame(fuji, tmp_path):
         assert not (acc.astype(bool) & part.astype(bool)).any()
         acc += part
     assert np.array_equal(acc, full)
+
+
+@pytest.mark.gpu
+def test_fjscene_cli_renders_on_several_gpus_without_python(tmp_path):
+    """`FJ_GPU_COUNT=N fjscene file.scn`: ONE process, one context per GPU, fjgpu_render_frame_multi (tiles round-robin, one
+    ncclAllGather, rank 0 assembles) — the same .fb as one GPU, for a deterministic and a path-traced scene.  Needs >= 2 GPUs."""
+    import subprocess
+    torch = pytest.importorskip("torch")
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from fujiyama_renderer_b200 import fbio
+    exe = os.path.join(sk.REPO, "fujiyama-renderer_b200", "host", "fjscene")
+    for name in ("multi", "pt_branching"):
+        desc = golden_scenes.SCENES[name]()
+        frames = {}
+        for count in (1, 2, min(n, 4)):
+            out = str(tmp_path / ("%s_%d.fb" % (name, count)))
+            scn = str(tmp_path / ("%s_%d.scn" % (name, count)))
+            with open(scn, "w") as f:
+                f.write(desc.to_scn(str(tmp_path), out, threads=1, plugin_dir="/opt/fujiyama/lib"))
+            env = dict(os.environ, FJ_GPU_COUNT=str(count))
+            res = subprocess.run([exe, scn], env=env, capture_output=True, text=True, timeout=600)
+            assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+            if count > 1:
+                assert "one all-gather" in res.stdout
+            frames[count] = fbio.read_fb(out)
+        for count, img in frames.items():
+            assert np.array_equal(img, frames[1]), (name, count)
