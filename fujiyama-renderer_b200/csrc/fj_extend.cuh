@@ -134,7 +134,7 @@ __device__ __forceinline__ int xpop_(const int (*sstack)[FJ_XT], const int *lsta
   return v;
 }
 
-template <int MINB, bool STATS, bool QUANT, bool COOP = false, int SD = 12, bool TOP = false, bool FARKEY = false>
+template <int MINB, bool STATS, bool QUANT, bool COOP = false, int SD = 12, bool TOP = false>
 __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
   __shared__ ExtShared S;
   __shared__ int sstack[SD][FJ_XT];             // the first SD stack entries of every lane (entry-major: bank = lane)
@@ -258,9 +258,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
             const float nz_ = fmaf(FJ_Q2F(qnz, K), siz, bnz), fz_ = fmaf(FJ_Q2F(qfz, K), siz, bfz);                               \
             const float nr = fmaxf(fmaxf(nx_, ny_), fmaxf(nz_, tn));                                                              \
             const float fr_ = fminf(fminf(fx_, fy_), fminf(fz_, tf));                                                             \
-            /* FARKEY: children entered at the same distance (the ray starts inside them) go in order of their EXIT distance */   \
-            const float ord = FARKEY ? fmaf(fr_, 9.5367431640625e-07f, nr) : nr;                                                  \
-            KEY = nr <= fr_ ? ((__float_as_uint(ord) & ~3u) | K##u) : MISS;                                                       \
+            KEY = nr <= fr_ ? ((__float_as_uint(nr) & ~3u) | K##u) : MISS;                                                        \
           }
           FJ_CHILD(key0, 0) FJ_CHILD(key1, 1) FJ_CHILD(key2, 2) FJ_CHILD(key3, 3)
 #undef FJ_CHILD

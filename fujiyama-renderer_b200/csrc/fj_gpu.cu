@@ -143,7 +143,6 @@ inline void xpoint(const double *m, const double p[3], double out[3]) {
 }
 
 #define FJGPU_TOP_NODES_DEFAULT 0
-#define FJGPU_FARKEY_DEFAULT 0
 int env_int(const char *name, int def) { const char *s = getenv(name); return s && *s ? atoi(s) : def; }
 
 // ---- scene commit: instances, TLAS per object group, shader/light tables ------------------------
@@ -515,7 +514,7 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
 
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
-template <int MINB, bool QUANT, bool COOP, int SD, bool TOP, bool FARKEY = false>
+template <int MINB, bool QUANT, bool COOP, int SD, bool TOP>
 void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   // shared-memory carveout: MINB CTAs x (static + dynamic shared memory + 1 KB the driver reserves per CTA), the rest stays L1
   const size_t dyn = TOP ? (size_t)a.top_count * 64 : 0;
@@ -525,11 +524,11 @@ void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   if (done != per_cta) {
     int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * per_cta / (228.0 * 1024)));
     pct = env_int("FJGPU_CARVEOUT_PCT", pct);
-    if (dyn) cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, FARKEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, FARKEY>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (dyn) cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     done = per_cta;
   }
-  fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP, FARKEY><<<blocks, FJ_XT, dyn, ctx->stream>>>(a);
+  fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP><<<blocks, FJ_XT, dyn, ctx->stream>>>(a);
 }
 
 // The closest-hit kernel of one wavefront round.  FJGPU_EXTEND=1 selects the register-resident first version (kept as
@@ -559,7 +558,6 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
       if (minb >= 8) launch_extend2<8, true, true, 8, false>(ctx, a, cap);
       else if (minb == 7 && sd >= 16) launch_extend2<7, true, true, 16, false>(ctx, a, cap);
       else if (minb == 7 && sd <= 8) launch_extend2<7, true, true, 8, false>(ctx, a, cap);
-      else if (minb == 7 && env_int("FJGPU_FARKEY", FJGPU_FARKEY_DEFAULT) != 0) launch_extend2<7, true, true, 12, false, true>(ctx, a, cap);
       else if (minb == 7) launch_extend2<7, true, true, 12, false>(ctx, a, cap);
       else launch_extend2<6, true, true, 16, false>(ctx, a, cap);
     } else if (quant) {
