@@ -96,7 +96,10 @@ __device__ __forceinline__ bool tri_intersect_smem(const D3 &v0, const D3 &v1, c
 // Lane state word: what the node loop has to know about the exact half of the state.
 enum { XS_BLAS = 1, XS_WORLD = 2, XS_TRI64 = 4, XS_LEAF = 8, XS_FOUND = 16,
        XS_VEL = 32,      // moving triangles: 160-B packets with per-vertex velocity (Mesh::ray_intersect, src/fj_mesh.cc:252-259)
-       XS_TOP = 64 };    // the tree being walked is the one whose first nodes are staged in shared memory
+       XS_TOP = 64,      // the tree being walked is the one whose first nodes are staged in shared memory
+       XS_ANY = 128 };   // a shadow ray whose every possible occluder is opaque: the first accepted hit ends the walk.  SlIlluminance
+                         // scales the light by 1 - alpha of the CLOSEST occluder (src/fj_shading.cc:338-355); with alpha = 1 for every
+                         // shader of the scene that is 0 whichever occluder is found, so any hit gives the reference's value
 
 // One triangle of a leaf for the exact test: 48-B FP32 packet, 80-B FP64 packet, or the 160-B packet of a mesh with vertex
 // velocity, moved to the ray's time as the reference does (`P0 += time * velocity0`, src/fj_mesh.cc:252-259).
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           const DGroup grp = sc.groups[r.target];
           nodes = (const char *)(QUANT ? grp.nodesq : grp.nodes4); sp = 0; node = 0;
           make_box_ray_mm(mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), QUANT ? grp.bmagq : grp.bmag, br);
-          st = XS_WORLD;
+          st = XS_WORLD | ((a.shadow_anyhit && r.type == RAY_SHADOW) ? XS_ANY : 0);
         }
       }
       if (STATS && (n_steps | n_tris) > 0x40000000u) {      // keep the 32-bit warp totals from wrapping
@@ -419,6 +422,9 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
       }
     }
 
+    // ---- any-hit shadow rays: an accepted hit ends the walk (B2 below retires the lane; its HitRec is already written)
+    if ((st & (XS_ANY | XS_FOUND)) == (XS_ANY | XS_FOUND)) { node = DONE; sp = 0; st &= ~XS_LEAF; }
+
     // ---- phase B2: transitions of lanes whose next stack entry is not an inner node
     const bool special = node < 0 && node != IDLE;
     if (__any_sync(FULL, special)) {
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend2(const RenderArgs a) {
           make_box_ray_mm(o, d, QUANT ? in.bmagq : in.bmag, br);
           nodes = QUANT ? in.nodesq : in.nodes4;
           S.tri[tid] = in.tri;
-          st = (st & XS_FOUND) | XS_BLAS | (in.tri64 == 1 ? XS_TRI64 : 0) | (in.tri64 == 2 ? XS_VEL : 0);
+          st = (st & (XS_FOUND | XS_ANY)) | XS_BLAS | (in.tri64 == 1 ? XS_TRI64 : 0) | (in.tri64 == 2 ? XS_VEL : 0);
           if (TOP && QUANT && (const void *)in.nodesq == (const void *)a.top_src) st |= XS_TOP;
           XPUSH(SENTINEL);
           node = 0;

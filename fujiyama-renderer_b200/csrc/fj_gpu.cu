@@ -78,6 +78,7 @@ struct fjgpu_context {
   int tlas_depth4 = 0;
   size_t ctl_off = 0;             // offset of the live QueueCtl inside d_ctl
   bool quant_ok = true;        // every tree of the committed scene has a quantised (NodeQ64) copy
+  bool all_opaque = true;      // every shader returns Os = 1 (plastic: opacity 1): shadow rays may stop at any hit
   int stack_need = 0;          // worst-case traversal stack of the committed scene (entries)
   const void *top_src = nullptr; int top_avail = 0;     // NodeQ64 array of the largest tree and the length of its breadth-first front (k_extend2<TOP>)
   double shutter[2] = {0., 1.};                         // Renderer::SetSampleTimeRange (fjgpu_shutter_set)
@@ -302,6 +303,8 @@ int commit_scene(fjgpu_context *ctx) {
     d.ior = s.ior; d.opacity = s.opacity;
   }
   if (int rc = dev_upload(ctx, ctx->d_shaders, ds.data(), ds.size() * sizeof(fj::DShader), true)) return rc;
+  ctx->all_opaque = true;      // constant / glass / pathtracing shaders and NO_SHADER return Os = 1; plastic returns `opacity`
+  for (const fj::DShader &d : ds) if (d.kind == FJGPU_SHADER_PLASTIC && !(d.opacity >= 1.f)) ctx->all_opaque = false;
 
   for (auto &b : ctx->d_dome) b.release();
   ctx->d_dome.assign(2 * ctx->lights.size(), DevBuf());
@@ -547,6 +550,7 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
     const bool coop = quant && env_int("FJGPU_COOP", 1) != 0;       // warp-cooperative exact triangle tests (fj_extend.cuh, phase B1)
     const int sd = env_int("FJGPU_STACK_SMEM", 12);
     a.top_src = nullptr; a.top_count = 0;
+    a.shadow_anyhit = ctx->all_opaque && env_int("FJGPU_ANYHIT", 1) != 0 ? 1 : 0;
     if (quant && coop && ctx->top_src) {
       const int want = std::min(env_int("FJGPU_TOP_NODES", FJGPU_TOP_NODES_DEFAULT), ctx->top_avail);
       if (want > 0) { a.top_src = (const char *)ctx->top_src; a.top_count = want; }
