@@ -20,6 +20,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -98,6 +99,8 @@ struct fjgpu_context {
 namespace {
 
 int fail(fjgpu_context *c, int code, const std::string &msg) {
+  static std::mutex mu;                   // fjgpu_render_frame_multi runs one host thread per context
+  std::lock_guard<std::mutex> lock(mu);
   g_last_error = msg;
   if (c) c->err = msg;
   return code;
