@@ -11,6 +11,7 @@
 #include "fj_build.h"
 #include "fj_kernels.cuh"
 #include "fj_extend.cuh"
+#include "fj_extend_ring.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -520,6 +521,20 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
 
 enum { OUT_HOST = 0, OUT_DEVICE_BLOCKS = 1, OUT_RESIDENT = 2, OUT_SAMPLES_ONLY = 3 };
 
+template <int MINB, int SD, bool F2, bool RING>
+void launch_extend_ring(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
+  const size_t per_cta = (RING ? sizeof(fj::RingShared) : sizeof(fj::ExtShared)) + (size_t)SD * FJ_XT * sizeof(int) + 1024 + 1024;
+  static size_t configured[64] = {0};
+  size_t &done = configured[ctx->device & 63];
+  if (done != per_cta) {
+    int pct = (int)std::min(100.0, std::ceil(100.0 * MINB * per_cta / (228.0 * 1024)));
+    pct = env_int("FJGPU_CARVEOUT_PCT", pct);
+    cudaFuncSetAttribute(fj::k_extend_ring<MINB, SD, F2, RING>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    done = per_cta;
+  }
+  fj::k_extend_ring<MINB, SD, F2, RING><<<blocks, FJ_XT, 0, ctx->stream>>>(a);
+}
+
 template <int MINB, bool QUANT, bool COOP, int SD, bool TOP>
 void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   // shared-memory carveout: MINB CTAs x (static + dynamic shared memory + 1 KB the driver reserves per CTA), the rest stays L1
@@ -554,6 +569,23 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
     const int sd = env_int("FJGPU_STACK_SMEM", 12);
     a.top_src = nullptr; a.top_count = 0;
     a.shadow_anyhit = ctx->all_opaque && env_int("FJGPU_ANYHIT", 1) != 0 ? 1 : 0;
+    if (version >= 3 && coop) {                          // ring of prepared rays (fj_extend_ring.cuh)
+      a.b1_min = std::max(1, env_int("FJGPU_B1_MIN", 1)); a.b2_min = std::max(1, env_int("FJGPU_B2_MIN", 1));
+      const bool ring = env_int("FJGPU_RING", 1) != 0;       // per-warp ring of prepared rays, or the direct refill of k_extend2
+      a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", ring ? 32 : 12)));
+      const bool f2 = env_int("FJGPU_FMA2", 1) != 0;         // packed FP32 FMAs (FFMA2) in the node step
+      if (!ring) {
+        if (minb >= 8) launch_extend_ring<8, 8, true, false>(ctx, a, cap);
+        else if (minb == 7 && sd <= 8) launch_extend_ring<7, 8, true, false>(ctx, a, cap);
+        else if (minb == 7) launch_extend_ring<7, 12, true, false>(ctx, a, cap);
+        else launch_extend_ring<6, 12, true, false>(ctx, a, cap);
+      } else if (minb >= 8) launch_extend_ring<8, 8, true, true>(ctx, a, cap);
+      else if (minb == 7 && sd >= 12) launch_extend_ring<7, 12, true, true>(ctx, a, cap);
+      else if (minb == 7 && f2) launch_extend_ring<7, 8, true, true>(ctx, a, cap);
+      else if (minb == 7) launch_extend_ring<7, 8, false, true>(ctx, a, cap);
+      else launch_extend_ring<6, 12, true, true>(ctx, a, cap);
+      return;
+    }
     if (quant && coop && ctx->top_src) {
       const int want = std::min(env_int("FJGPU_TOP_NODES", FJGPU_TOP_NODES_DEFAULT), ctx->top_avail);
       if (want > 0) { a.top_src = (const char *)ctx->top_src; a.top_count = want; }

@@ -409,6 +409,7 @@ struct RenderArgs {
   int refill, phase_a_min, park;          // k_extend scheduling: refill / phase-A thresholds (lanes), speculative leaf parking
   const char *top_src; int top_count;     // k_extend2<TOP>: the NodeQ64 array whose first top_count nodes are staged in shared memory
   int shadow_anyhit;                      // k_extend2: every shader of the scene is opaque -> shadow rays stop at their first hit
+  int b1_min, b2_min;                     // k_extend_ring: (ray, triangle) pairs / entering lanes that make a heavy phase worth running
   int chunked;                            // k_shade without plastic shaders: warps reserve queue slots in chunks (QueueSink)
   // ray sorting between bounces: counting sort of the next queue by (direction octant | origin cell)
   unsigned int *hist;                     // sort_bins + 1 counters (null = no sorting)
