@@ -560,7 +560,7 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
   a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
   a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 16)));
   a.park = env_int("FJGPU_PARK", 1);
-  const int version = env_int("FJGPU_EXTEND", 2);
+  const int version = env_int("FJGPU_EXTEND", 3);
   if (version >= 2) {
     const int minb = env_int("FJGPU_EXTEND_MINBLOCKS", 7);
     const int cap = std::max(1, grid / 4 * minb);      // `grid` is 4 CTAs per SM worth of work (or fewer for small probes)
@@ -570,9 +570,9 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
     a.top_src = nullptr; a.top_count = 0;
     a.shadow_anyhit = ctx->all_opaque && env_int("FJGPU_ANYHIT", 1) != 0 ? 1 : 0;
     if (version >= 3 && coop) {                          // ring of prepared rays (fj_extend_ring.cuh)
-      a.b1_min = std::max(1, env_int("FJGPU_B1_MIN", 1)); a.b2_min = std::max(1, env_int("FJGPU_B2_MIN", 1));
-      const bool ring = env_int("FJGPU_RING", 1) != 0;       // per-warp ring of prepared rays, or the direct refill of k_extend2
-      a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", ring ? 32 : 12)));
+      a.b1_min = std::max(1, env_int("FJGPU_B1_MIN", 24)); a.b2_min = std::max(1, env_int("FJGPU_B2_MIN", 8));
+      const bool ring = env_int("FJGPU_RING", 0) != 0;       // per-warp ring of prepared rays, or the direct refill of k_extend2
+      a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", ring ? 32 : 8)));
       const bool f2 = env_int("FJGPU_FMA2", 1) != 0;         // packed FP32 FMAs (FFMA2) in the node step
       if (!ring) {
         if (minb >= 8) launch_extend_ring<8, 8, true, false>(ctx, a, cap);
@@ -715,6 +715,7 @@ int render_impl(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_ti
         const bool chunked = !has_plastic && sort_bits == 0 && env_int("FJGPU_QUEUE_CHUNK", 1) != 0;
         // grid of the k_shade variant without plastic shaders: resident CTAs per SM (template parameter) x CTAs per slot
         const int shade_env = env_int("FJGPU_SHADE_MINBLOCKS", 5), shade_per = std::max(1, env_int("FJGPU_SHADE_CTAS", 2));
+        a.shade_prefetch = env_int("FJGPU_SHADE_PREFETCH", 1);
         const int shade_smb = shade_env >= 8 ? 8 : (shade_env >= 6 ? 6 : 5);
         const int shade_ctas = ctx->sm_count * shade_smb * shade_per;
         const size_t shade_warps = (size_t)shade_ctas * 4;      // 128 threads per CTA

@@ -29,6 +29,7 @@ __device__ __forceinline__ void load_ray_cs(RayRec *dst, const RayRec *src) {
 #pragma unroll
   for (int k = 0; k < 7; k++) d[k] = __ldcs(s + k);
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void store_hit_cs(HitRec *dst, const HitRec &h) {
   const uint4 *s = reinterpret_cast<const uint4 *>(&h); uint4 *d = reinterpret_cast<uint4 *>(dst);
   __stcs(d, s[0]); __stcs(d + 1, s[1]);
@@ -409,6 +410,7 @@ struct RenderArgs {
   int refill, phase_a_min, park;          // k_extend scheduling: refill / phase-A thresholds (lanes), speculative leaf parking
   const char *top_src; int top_count;     // k_extend2<TOP>: the NodeQ64 array whose first top_count nodes are staged in shared memory
   int shadow_anyhit;                      // k_extend2: every shader of the scene is opaque -> shadow rays stop at their first hit
+  int shade_prefetch;                     // k_shade: prefetch the warp's next 32 records into L2 (FJGPU_SHADE_PREFETCH)
   int b1_min, b2_min;                     // k_extend_ring: (ray, triangle) pairs / entering lanes that make a heavy phase worth running
   int chunked;                            // k_shade without plastic shaders: warps reserve queue slots in chunks (QueueSink)
   // ray sorting between bounces: counting sort of the next queue by (direction octant | origin cell)
@@ -860,6 +862,15 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const RenderArgs a) {
   for (unsigned i0 = start; i0 < count; i0 += gridDim.x * blockDim.x) {
     const unsigned i = i0 + lane;
     const bool valid = i < count;
+    {                                       // the records of the warp's NEXT group on their way into L2 while this one is shaded: the
+      const unsigned inext = i0 + gridDim.x * blockDim.x;      // kernel waits on these loads more than on anything else (ncu: long scoreboard)
+      if (a.shade_prefetch && inext < count) {
+        const unsigned nrec = min(32u, count - inext);
+        const char *rb = reinterpret_cast<const char *>(rays + inext), *hb = reinterpret_cast<const char *>(a.hits + inext);
+        if (128u * lane < nrec * (unsigned)sizeof(RayRec)) prefetch_l2(rb + 128u * lane);      // 32 x 112 B = 28 lines
+        if (128u * lane < nrec * (unsigned)sizeof(HitRec)) prefetch_l2(hb + 128u * lane);      // 32 x 32 B = 8 lines
+      }
+    }
     if (wc) {                               // top the warp's slot reservation up to FJ_QRESERVE free slots
       __syncwarp();                         // every lane has finished the spawns of the previous iteration (they bump wc->used)
       if (lane == 0 && wc->alloc - wc->used < FJ_QRESERVE) {

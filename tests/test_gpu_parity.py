@@ -459,33 +459,34 @@ EXTEND_VARIANTS = {
     "v2_cooperative_leaves_8": {"FJGPU_EXTEND": "2", "FJGPU_QUANT": "1", "FJGPU_COOP": "1", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "4", "FJGPU_PHASE_A_MIN": "4"},
     # shared-memory traversal stack of 8 / 16 entries per lane (default 12; deeper entries spill to local memory: the soup's
     # overlapping boxes do reach them)
-    "v2_stack_smem_8": {"FJGPU_STACK_SMEM": "8"},
-    "v2_stack_smem_16": {"FJGPU_STACK_SMEM": "16"},
+    "v2_stack_smem_8": {"FJGPU_EXTEND": "2", "FJGPU_STACK_SMEM": "8"},
+    "v2_stack_smem_16": {"FJGPU_EXTEND": "2", "FJGPU_STACK_SMEM": "16"},
     # the top of the largest tree staged in shared memory by one cp.async.bulk per CTA (7 and 6 CTAs per SM)
-    "v2_top_staged_64": {"FJGPU_TOP_NODES": "64"},
-    "v2_top_staged_341": {"FJGPU_TOP_NODES": "341", "FJGPU_EXTEND_MINBLOCKS": "6"},
-    "v2_unchunked_queue": {"FJGPU_QUEUE_CHUNK": "0"},
+    "v2_top_staged_64": {"FJGPU_EXTEND": "2", "FJGPU_TOP_NODES": "64"},
+    "v2_top_staged_341": {"FJGPU_EXTEND": "2", "FJGPU_TOP_NODES": "341", "FJGPU_EXTEND_MINBLOCKS": "6"},
+    "v2_unchunked_queue": {"FJGPU_EXTEND": "2", "FJGPU_QUEUE_CHUNK": "0"},
     # shadow rays walked to their CLOSEST occluder (the default stops at the first hit when every shader is opaque)
-    "v2_closest_hit_shadows": {"FJGPU_ANYHIT": "0"},
+    "v2_closest_hit_shadows": {"FJGPU_EXTEND": "2", "FJGPU_ANYHIT": "0"},
     # rays of the next queue sorted by (direction octant, origin cell) between bounces (frames only; the probe has no bounces)
-    "v2_sorted_rays": {"FJGPU_SORT_BITS": "4"},
-    "v2_sorted_rays_unchunked": {"FJGPU_SORT_BITS": "3", "FJGPU_QUEUE_CHUNK": "0"},
+    "v2_sorted_rays": {"FJGPU_EXTEND": "2", "FJGPU_SORT_BITS": "4"},
+    "v2_sorted_rays_unchunked": {"FJGPU_EXTEND": "2", "FJGPU_SORT_BITS": "3", "FJGPU_QUEUE_CHUNK": "0"},
     # k_extend_ring: a per-warp ring of prepared rays between the queue and the lanes (fj_extend_ring.cuh), at several ring
     # thresholds, stack depths and occupancies; with sorted rays (the ring is filled through `perm`) and closest-hit shadows
-    "v3_ring": {"FJGPU_EXTEND": "3"},
-    "v3_ring_eager": {"FJGPU_EXTEND": "3", "FJGPU_REFILL": "1", "FJGPU_PHASE_A_MIN": "4"},
-    "v3_ring_lazy_sd12": {"FJGPU_EXTEND": "3", "FJGPU_REFILL": "32", "FJGPU_STACK_SMEM": "12"},
-    "v3_ring_8": {"FJGPU_EXTEND": "3", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "8"},
-    "v3_ring_6": {"FJGPU_EXTEND": "3", "FJGPU_EXTEND_MINBLOCKS": "6"},
-    "v3_ring_sorted": {"FJGPU_EXTEND": "3", "FJGPU_SORT_BITS": "4"},
-    "v3_ring_closest_hit_shadows": {"FJGPU_EXTEND": "3", "FJGPU_ANYHIT": "0"},
-    "v3_ring_scalar_fma": {"FJGPU_EXTEND": "3", "FJGPU_FMA2": "0"},
+    "v3_ring": {"FJGPU_EXTEND": "3", "FJGPU_RING": "1", "FJGPU_B1_MIN": "1", "FJGPU_B2_MIN": "1"},
+    "v3_ring_eager": {"FJGPU_EXTEND": "3", "FJGPU_RING": "1", "FJGPU_REFILL": "1", "FJGPU_PHASE_A_MIN": "4"},
+    "v3_ring_lazy_sd12": {"FJGPU_EXTEND": "3", "FJGPU_RING": "1", "FJGPU_REFILL": "32", "FJGPU_STACK_SMEM": "12"},
+    "v3_ring_8": {"FJGPU_EXTEND": "3", "FJGPU_RING": "1", "FJGPU_EXTEND_MINBLOCKS": "8", "FJGPU_REFILL": "8"},
+    "v3_ring_6": {"FJGPU_EXTEND": "3", "FJGPU_RING": "1", "FJGPU_EXTEND_MINBLOCKS": "6"},
+    "v3_default_sorted": {"FJGPU_SORT_BITS": "4"},
+    "v3_default": {},
+    "v3_default_closest_hit_shadows": {"FJGPU_ANYHIT": "0"},
+    "v3_ring_scalar_fma": {"FJGPU_EXTEND": "3", "FJGPU_RING": "1", "FJGPU_FMA2": "0", "FJGPU_STACK_SMEM": "8"},
     # the new node loop with the direct refill of k_extend2 instead of the ring
-    "v3_direct_refill": {"FJGPU_EXTEND": "3", "FJGPU_RING": "0"},
+    "v3_direct_ungated": {"FJGPU_EXTEND": "3", "FJGPU_RING": "0", "FJGPU_B1_MIN": "1", "FJGPU_B2_MIN": "1", "FJGPU_REFILL": "12"},
     "v3_direct_refill_sd8": {"FJGPU_EXTEND": "3", "FJGPU_RING": "0", "FJGPU_STACK_SMEM": "8", "FJGPU_REFILL": "4"},
     # heavy phases (leaf tests / instance entries) deferred until enough lanes wait for them
     "v3_gated": {"FJGPU_EXTEND": "3", "FJGPU_RING": "0", "FJGPU_B1_MIN": "24", "FJGPU_B2_MIN": "8"},
-    "v3_gated_ring": {"FJGPU_EXTEND": "3", "FJGPU_B1_MIN": "28", "FJGPU_B2_MIN": "12"},
+    "v3_gated_ring": {"FJGPU_EXTEND": "3", "FJGPU_RING": "1", "FJGPU_B1_MIN": "28", "FJGPU_B2_MIN": "12"},
     "v3_gated_extreme": {"FJGPU_EXTEND": "3", "FJGPU_RING": "0", "FJGPU_B1_MIN": "200", "FJGPU_B2_MIN": "32", "FJGPU_PHASE_A_MIN": "4"},
 }
 VARIANT_KEYS = ("FJGPU_EXTEND", "FJGPU_QUANT", "FJGPU_EXTEND_MINBLOCKS", "FJGPU_REFILL", "FJGPU_PHASE_A_MIN", "FJGPU_COOP", "FJGPU_QUEUE_CHUNK",
