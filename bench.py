@@ -60,36 +60,55 @@ def workdir():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    nvidia-smi is started BEFORE the warm-up steps and polls once per second: measured on a B200 (profiles/
+    r2b_clock_sampler_period.txt) a sampler started right at the timed region with `-lms 200` cost the 20-step north-star run
+    10-175 ms per 351-ms step (NVML start-up and every poll stall the launching thread), 22 ms at 1000 ms, 0.4 ms at 5000 ms.
+    Only the rows that arrive between mark() and stop() are reported; a region shorter than one period falls back to the last
+    rows of the warm-up (same load) and says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_ms=1000):
         self.rows, self.proc, self.index = [], None, index
+        self.period_ms = int(os.environ.get("FJ_CLOCK_LMS", period_ms))
+        self.t_mark = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", str(max(50, self.period_ms))], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
 
+    def mark(self):
+        """Start of the timed region."""
+        self.t_mark = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        t0 = self.t_mark if self.t_mark is not None else 0.0
+        inside = [r for t, r in self.rows if t0 <= t <= t_end]
+        note = None
+        if not inside:                       # a timed region shorter than one polling period
+            inside = [r for t, r in self.rows][-2:]
+            note = "timed region shorter than the polling period: last rows of the warm-up (same load)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -98,8 +117,11 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm), "period_ms": self.period_ms}
+        if note:
+            out["note"] = note
+        return out
 
 
 def algorithmic_bytes(stats, ninst):
@@ -374,17 +396,18 @@ def own_arm(args, builder, kw, desc):
                 gathered = sharding.all_gather_blocks(blocks, world, dist)
             return st
 
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()                  # before the warm-up: NVML's start-up stalls the launching thread (see ClockSampler)
         for _ in range(max(args.warmup, 1)):
             st, info, upload_s = step()
             flush.zero_()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        clocks.mark()
         t0 = time.perf_counter()
         ev0.record()
         tot = abi.Stats()

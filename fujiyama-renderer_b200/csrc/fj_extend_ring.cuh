@@ -1,22 +1,27 @@
-// fj_extend_ring.cuh — k_extend_ring: k_extend2 (fj_extend.cuh) with a per-warp ring of PREPARED rays between the queue and
-// the lanes, and a cheaper node loop.  Same contract and results (closest hit of Accelerator::Intersect, src/fj_shading.cc:538-541;
+// fj_extend_ring.cuh — k_extend_ring: the closest-hit kernel that ships.  k_extend2 (fj_extend.cuh) with a cheaper node loop,
+// its rare phases gated by the lanes that wait for them, and — as an option — a per-warp ring of PREPARED rays between the
+// queue and the lanes.  Same contract and results (closest hit of Accelerator::Intersect, src/fj_shading.cc:538-541;
 // bit-identical t / u / v / face / instance), quantised 64-B nodes and warp-cooperative leaves only — trees that cannot be
 // quantised keep k_extend2.
 //
-// Why.  The full-size ncu capture of k_extend2 (profiles/r2_k_extend2_north_star_ncu_full.txt, source view) shows a kernel
-// that is bound by issue slots (71 %), not by memory latency (6 % of the stall samples wait on the node fetch), with 61 % of
-// its warp instructions in the node loop at 24.4 of 32 lanes — and most of the missing 7.6 lanes are IDLE ones: a warp took new
-// rays only when >= 12 lanes had run dry, because preparing a ray (the 112-B record, three FP64 -> FP32 reciprocals, the
-// widened slab constants: ~250 instructions) on a handful of lanes costs as much as on 32.  Here the two halves are decoupled:
-//   produce   when >= `refill` of the warp's 32 ring slots are free, that many rays are taken from the queue head with one
-//             atomic and prepared by as many lanes side by side (box ray, tn / tf, target group) into shared memory;
-//   consume   every outer iteration each idle lane takes the next prepared ray: 11 LDS and a handful of moves.
-// A lane is therefore idle only when the queue has run dry.
-//
-// The node loop sheds the instructions that did no work: the slab constants are kept as (near, far) instead of (lo, hi) —
-// k_extend2 selected near / far from lo / hi with six FSEL per step, and for the quantised form the selection is the identity;
-// the stack is addressed by a running shared-memory address with a DONE / SENTINEL entry at its bottom (a pop is SUB + LDS,
-// no emptiness test; a push is STS + ADD); the re-entry into the instance tree after a BLAS left the loop for phase B2.
+// What the source-level profile of k_extend2 said (DESIGN.md 4.1 "Round 2, second half"): nothing is saturated — 0.65
+// instructions per cycle and scheduler with 1.3 eligible warps of 7 — and on bounce rays every instruction runs on 17.5 of 32
+// lanes: a warp left the node loop after 3 steps, tested 19 (ray, triangle) pairs in rounds of 32 and entered instances
+// — 300 instructions — with 5 lanes.  Hence:
+//   node loop   the slab constants are kept as (near, far) instead of (lo, hi) — k_extend2 selected near / far from lo / hi with
+//               six FSEL per step, and for the quantised form the selection is the identity; the 24 plane distances of a step are
+//               12 packed FMAs (FFMA2: each half an IEEE fma.rn, bit-identical keys); the stack is addressed by a running
+//               shared-memory address with a DONE / SENTINEL entry at its bottom (a pop is SUB + LDS, no emptiness test; a
+//               push is STS + ADD); ray records are read in 16-byte pieces (one L1 tag lookup per lane and instruction
+//               whatever the width); the ray's target group travels in the state word;
+//   transitions the cheap ones (park a leaf, leave a finished BLAS, retire a finished ray: FJ_TRANSIT) run once per outer
+//               iteration and once after the leaf phase;
+//   gates       the two heavy phases — exact triangle tests (B1), instance entry (E) — run when enough lanes wait for them
+//               (RenderArgs::b1_min pairs, b2_min lanes), and whenever lanes are blocked at least one of the two runs;
+//   ring        (RING = true, FJGPU_RING=1; off by default) when >= `refill` of the warp's 32 ring slots are free, that many
+//               rays are taken from the queue head with one atomic and prepared side by side (box ray, tn / tf, state word)
+//               into shared memory; every outer iteration each idle lane takes the next prepared ray.  Measured: the lanes
+//               it fills were not the ones missing (bounce rays are BLOCKED, not idle) and its 6.5 KB per CTA come out of L1.
 #pragma once
 
 #include <type_traits>
@@ -95,9 +100,8 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend_ring(const RenderArgs a)
   const int SENTINEL = (int)0x80000000, DONE = (int)0x80000001, IDLE = (int)0x80000002;
   const int FIXUP = (int)0x80000003;            // back in the instance tree with an inner node on the stack: the world-space box ray has to be rebuilt (phase E)
   const unsigned MISS = 0xffffffffu;
-  // Cheap transitions of a lane whose next reference is not an inner node, done where they arise (at the end of a node step and
-  // after the leaf phase) instead of in a phase of their own: park the first triangle leaf and go on (speculative traversal),
-  // leave a finished BLAS, retire a finished ray.  What stays blocked afterwards waits for a HEAVY phase: a second leaf (or the
+  // Cheap transitions of a lane whose next reference is not an inner node, done once per outer iteration after the node loop and
+  // once after the leaf phase: park a triangle leaf when the slot is free, leave a finished BLAS, retire a finished ray.  What stays blocked afterwards waits for a HEAVY phase: a second leaf (or the
   // end of the walk) behind a parked one -> leaf phase B1; a leaf of the instance tree or FIXUP -> entry phase E.  Inside a
   // BLAS the bottom stack entry is SENTINEL and below it lies the instance tree's DONE, so no pop underflows.
 #define FJ_TRANSIT()                                                                                                              \
@@ -300,9 +304,15 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend_ring(const RenderArgs a)
           }
           node = (w & 2u) ? ((w & 1u) ? ch.w : ch.z) : ((w & 1u) ? ch.y : ch.x);
         } else RPOP(node);
-        FJ_TRANSIT()
+        // speculative traversal: park the first triangle leaf and keep descending (the other transitions wait for FJ_TRANSIT
+        // below: doing them here, at the end of every node step, costs 10 % more instructions at 4-5 lanes — measured 292.6
+        // against 285.4 ms)
+        if (node < 0 && (st & (XS_BLAS | XS_LEAF)) == XS_BLAS && node != SENTINEL) {
+          S.leaf[tid] = node; st |= XS_LEAF | (((unsigned)~node & 7u) << XS_CNT_SHIFT); RPOP(node);
+        }
       }
     }
+    FJ_TRANSIT()                                      // once per outer iteration: leave finished BLASes, retire finished rays, park second leaves
 
     // ---- phase B1: the warp's parked leaves hold W (ray, triangle) pairs on typically 10-12 lanes; the pairs are dealt out 32
     // at a time to ALL lanes (the FP64 ray of any lane is in shared memory), and each owner then folds the hits among its pairs

@@ -570,7 +570,7 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
     a.top_src = nullptr; a.top_count = 0;
     a.shadow_anyhit = ctx->all_opaque && env_int("FJGPU_ANYHIT", 1) != 0 ? 1 : 0;
     if (version >= 3 && coop) {                          // ring of prepared rays (fj_extend_ring.cuh)
-      a.b1_min = std::max(1, env_int("FJGPU_B1_MIN", 24)); a.b2_min = std::max(1, env_int("FJGPU_B2_MIN", 8));
+      a.b1_min = std::max(1, env_int("FJGPU_B1_MIN", 20)); a.b2_min = std::max(1, env_int("FJGPU_B2_MIN", 6));
       const bool ring = env_int("FJGPU_RING", 0) != 0;       // per-warp ring of prepared rays, or the direct refill of k_extend2
       a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", ring ? 32 : 8)));
       const bool f2 = env_int("FJGPU_FMA2", 1) != 0;         // packed FP32 FMAs (FFMA2) in the node step
