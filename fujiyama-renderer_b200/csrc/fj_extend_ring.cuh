@@ -67,6 +67,18 @@ __device__ __forceinline__ void stg256(void *p, const HitRec &h) {
   const float *f = reinterpret_cast<const float *>(&h);
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
 }
+// One triangle of a leaf as load_leaf_triangle (fj_extend.cuh), the 48-B FP32 packet read as three 16-byte pieces: one tag
+// lookup more than the 32 + 16 split of k_extend2, and none of the twelve selects that order the pieces by the packet's parity
+// (measured: k_extend 279.2-280.2 -> 276.2 ms on the north star, 384.3 -> 380.2 on config 4).
+__device__ __forceinline__ void load_leaf_triangle3(const RenderArgs &a, const RayRec *rays, const void *tp_, unsigned fmt, unsigned ridx, int index,
+                                                    D3 *v0, D3 *v1, D3 *v2, int *prim) {
+  if (!(fmt & (XS_TRI64 | XS_VEL))) {
+    const float4 *tb = reinterpret_cast<const float4 *>(tp_) + 3 * (size_t)(unsigned)index;
+    const float4 p0 = __ldg(tb), p1 = __ldg(tb + 1), p2 = __ldg(tb + 2);
+    *v0 = mk(p0.x, p0.y, p0.z); *v1 = mk(p1.x, p1.y, p1.z); *v2 = mk(p2.x, p2.y, p2.z); *prim = __float_as_int(p0.w);
+  } else load_leaf_triangle(a, rays, tp_, fmt, ridx, index, v0, v1, v2, prim);
+}
+
 // Lane state above the XS_* flags: the object group the ray is traced against (RayRec::target), so that phase B2 does not
 // read the record for it
 #define XS_INIT 256u            // S.tmin / S.best_t hold the ray's exact range (set when the first instance is entered)
@@ -350,7 +362,7 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend_ring(const RenderArgs a)
         if (want) {
           const int first = (~S.leaf[otid]) >> 3;
           D3 v0, v1, v2;
-          load_leaf_triangle(a, rays, S.tri[otid], ost, S.ridx[otid], first + k, &v0, &v1, &v2, &prim);
+          load_leaf_triangle3(a, rays, S.tri[otid], ost, S.ridx[otid], first + k, &v0, &v1, &v2, &prim);
           hit = tri_intersect_smem(v0, v1, v2, S, otid, &t, &u, &v);
         }
         // owners fold the hits among their pairs of this round, lowest triangle first
