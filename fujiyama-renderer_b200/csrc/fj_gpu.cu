@@ -552,10 +552,12 @@ void launch_extend2(fjgpu_context *ctx, const fj::RenderArgs &a, int blocks) {
   fj::k_extend2<MINB, true, QUANT, COOP, SD, TOP><<<blocks, FJ_XT, dyn, ctx->stream>>>(a);
 }
 
-// The closest-hit kernel of one wavefront round.  FJGPU_EXTEND=1 selects the register-resident first version (kept as
-// a cross-check), 2 (default) the shared-memory-state version; FJGPU_EXTEND_MINBLOCKS = resident CTAs per SM,
-// FJGPU_STACK_SMEM = stack entries per lane kept in shared memory (8 / 12 / 16), FJGPU_TOP_NODES = nodes of the largest
-// tree staged in shared memory by one bulk copy per CTA (0 = off).
+// The closest-hit kernel of one wavefront round.  FJGPU_EXTEND=3 (default) is k_extend_ring (fj_extend_ring.cuh: quantised trees,
+// cooperative leaves; FJGPU_B1_MIN / FJGPU_B2_MIN gate its leaf-test / instance-entry phases, FJGPU_RING=1 adds the per-warp ring
+// of prepared rays), 2 k_extend2 (also the fallback for trees that cannot be quantised), 1 the register-resident first version
+// (both kept as cross-checks); FJGPU_EXTEND_MINBLOCKS = resident CTAs per SM, FJGPU_STACK_SMEM = stack entries per lane kept in
+// shared memory (8 / 12 / 16), FJGPU_TOP_NODES = nodes of the largest tree staged in shared memory by one bulk copy per CTA
+// (k_extend2 only; 0 = off).
 void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
   a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", 12)));
   a.phase_a_min = std::min(32, std::max(1, env_int("FJGPU_PHASE_A_MIN", 16)));
@@ -569,7 +571,7 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
     const int sd = env_int("FJGPU_STACK_SMEM", 12);
     a.top_src = nullptr; a.top_count = 0;
     a.shadow_anyhit = ctx->all_opaque && env_int("FJGPU_ANYHIT", 1) != 0 ? 1 : 0;
-    if (version >= 3 && coop) {                          // ring of prepared rays (fj_extend_ring.cuh)
+    if (version >= 3 && coop) {                          // k_extend_ring (fj_extend_ring.cuh)
       a.b1_min = std::max(1, env_int("FJGPU_B1_MIN", 20)); a.b2_min = std::max(1, env_int("FJGPU_B2_MIN", 6));
       const bool ring = env_int("FJGPU_RING", 0) != 0;       // per-warp ring of prepared rays, or the direct refill of k_extend2
       a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", ring ? 32 : 8)));
