@@ -571,7 +571,7 @@ void launch_extend(fjgpu_context *ctx, fj::RenderArgs &a, int grid) {
     const int sd = env_int("FJGPU_STACK_SMEM", 12);
     a.top_src = nullptr; a.top_count = 0;
     a.shadow_anyhit = ctx->all_opaque && env_int("FJGPU_ANYHIT", 1) != 0 ? 1 : 0;
-    if (version >= 3 && coop) {                          // k_extend_ring (fj_extend_ring.cuh)
+    if (version >= 3 && coop && ctx->sc.ngroups < (1 << 20)) {      // k_extend_ring (fj_extend_ring.cuh; the target group travels in 20 bits of the lane's state word)
       a.b1_min = std::max(1, env_int("FJGPU_B1_MIN", 20)); a.b2_min = std::max(1, env_int("FJGPU_B2_MIN", 6));
       const bool ring = env_int("FJGPU_RING", 0) != 0;       // per-warp ring of prepared rays, or the direct refill of k_extend2
       a.refill = std::min(32, std::max(1, env_int("FJGPU_REFILL", ring ? 32 : 8)));
