@@ -15,6 +15,7 @@ bounded render_region of the same frame on all host cores.
 """
 import argparse
 import ctypes as C
+import gc
 import json
 import math
 import os
@@ -62,9 +63,12 @@ def workdir():
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
 
-    nvidia-smi is started BEFORE the warm-up steps and polls once per second: measured on a B200 (profiles/
+    nvidia-smi is started during the warm-up and polls about three times per timed region: measured on a B200 (profiles/
     r2b_clock_sampler_period.txt) a sampler started right at the timed region with `-lms 200` cost the 20-step north-star run
-    10-175 ms per 351-ms step (NVML start-up and every poll stall the launching thread), 22 ms at 1000 ms, 0.4 ms at 5000 ms.
+    10-175 ms per 351-ms step (NVML start-up and every poll stall the launching thread), 22 ms at 1000 ms, 0.4 ms at 5000 ms;
+    started before the warm-up with a 1-s period the same run still lost 1-16 ms per step.  (What remains with a single poll
+    per region, 3-17 ms per step, is not the sampler: two or three of the twenty steps take 20-70 ms longer on the host side
+    with identical kernel times — `step_wall_ms` in the JSON line shows them; Python's collector is off in the region.)
     Only the rows that arrive between mark() and stop() are reported; a region shorter than one period falls back to the last
     rows of the warm-up (same load) and says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -83,6 +87,12 @@ class ClockSampler:
             self.t.start()
         except OSError:
             self.proc = None
+
+    def wait_first_row(self, timeout_s=6.0):
+        """Blocks until nvidia-smi has delivered its first row (NVML is up), so that its start-up stays out of the timed region."""
+        t_end = time.perf_counter() + timeout_s
+        while self.proc and not self.rows and time.perf_counter() < t_end and self.proc.poll() is None:
+            time.sleep(0.02)
 
     def mark(self):
         """Start of the timed region."""
@@ -396,26 +406,40 @@ def own_arm(args, builder, kw, desc):
                 gathered = sharding.all_gather_blocks(blocks, world, dist)
             return st
 
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()                  # before the warm-up: NVML's start-up stalls the launching thread (see ClockSampler)
-        for _ in range(max(args.warmup, 1)):
+        # The clock sampler starts after the first warm-up step, with a period of a third of the expected timed region (three
+        # rows per run: every nvidia-smi poll stalls the launching thread for tens of ms, see ClockSampler), and the warm-up
+        # goes on only when its first row has arrived.
+        clocks = None
+        for w in range(max(args.warmup, 1)):
+            tw = time.perf_counter()
             st, info, upload_s = step()
             flush.zero_()
+            if w == 0:
+                torch.cuda.synchronize()
+                step_ms = (time.perf_counter() - tw) * 1e3
+                clocks = ClockSampler(local, period_ms=int(min(5000, max(500, args.steps * step_ms / 3))))
+                if rank == 0:
+                    clocks.start()
+                    clocks.wait_first_row()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        gc.collect()
+        gc.disable()                        # no collector pause between two frames of the timed region (re-enabled below)
         clocks.mark()
         t0 = time.perf_counter()
         ev0.record()
         tot = abi.Stats()
         ms_trace = ms_resolve = ms_shade = 0.0
         launches = trace_launches = 0
+        step_wall = []
         for _ in range(args.steps):
+            tw = time.perf_counter()
             st, info, _ = step()
             flush.zero_()                   # L2 flush between timed iterations (256 MiB > 126 MB L2)
+            step_wall.append((time.perf_counter() - tw) * 1e3)
             for f, _t in abi.Stats._fields_:
                 if f.startswith("rays_") or f in ("camera_samples", "hit_mesh_levels", "node_steps", "tri_tests", "leaf_phases", "leaf_rounds"):
                     setattr(tot, f, getattr(tot, f) + getattr(st, f))
@@ -427,6 +451,7 @@ def own_arm(args, builder, kw, desc):
         ev1.record()
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
+        gc.enable()
         dev_ms = ev0.elapsed_time(ev1)
         if world > 1:
             dist.barrier()
@@ -544,7 +569,8 @@ def own_arm(args, builder, kw, desc):
                          "blas_nodes": int(info.blas_nodes), "blas_max_depth": int(info.blas_max_depth),
                          "node_steps_per_ray": tot.node_steps / max(tot.rays, 1), "tri_tests_per_ray": tot.tri_tests / max(tot.rays, 1),
                          "tri_pairs_per_leaf_phase": tot.tri_tests / max(tot.leaf_phases, 1), "rounds_per_leaf_phase": tot.leaf_rounds / max(tot.leaf_phases, 1)},
-               "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": total_launches, "clocks": clk,
+               "wall_ms_per_step": wall_ms / args.steps, "step_wall_ms": {"min": min(step_wall), "median": sorted(step_wall)[len(step_wall) // 2], "max": max(step_wall)},
+               "gpu_launches": total_launches, "clocks": clk,
                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                "kernel_ms_per_step": {"k_extend": ms_trace / args.steps, "k_generate+k_shade": ms_shade / args.steps,
                                       "k_resolve_tiles": ms_resolve / args.steps}}

@@ -71,3 +71,16 @@ def test_period_comes_from_the_environment(monkeypatch):
     assert _bench().ClockSampler(0).period_ms == 250
     monkeypatch.delenv("FJ_CLOCK_LMS")
     assert _bench().ClockSampler(0).period_ms == 1000
+
+
+def test_wait_first_row_returns_once_nvml_is_up(tmp_path, monkeypatch):
+    monkeypatch.setenv("PATH", _fake_smi(tmp_path, OK_ROW, 0.05) + os.pathsep + os.environ["PATH"])
+    s = _bench().ClockSampler(0, period_ms=700)
+    assert s.period_ms == 700
+    s.start()
+    t0 = time.perf_counter()
+    s.wait_first_row(timeout_s=5.0)
+    assert len(s.rows) >= 1 and time.perf_counter() - t0 < 4.0
+    s.mark()
+    out = s.stop()
+    assert out["period_ms"] == 700

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round 2, thirty-first GPU call: the same with Python's garbage collector disabled inside the timed region.
+set -u
+out=gpurun_out/r2c31; mkdir -p $out
+for lms in default default default; do
+  if [ $lms = default ]; then unset FJ_CLOCK_LMS; else export FJ_CLOCK_LMS=$lms; fi
+  timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-parity 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); k=d['kernel_ms_per_step']
+print('lms $lms: %.1f Mrays/s  step %.1f ms  kernels %.1f ms  gap %.1f ms  per-step wall %s  clocks %s' % (d['value'], d['ms_per_step'], sum(k.values()), d['ms_per_step']-sum(k.values()), {a: round(b,1) for a,b in d['step_wall_ms'].items()}, d['clocks']))" | tee -a $out/gap.log
+done
