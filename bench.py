@@ -67,8 +67,9 @@ class ClockSampler:
     r2b_clock_sampler_period.txt) a sampler started right at the timed region with `-lms 200` cost the 20-step north-star run
     10-175 ms per 351-ms step (NVML start-up and every poll stall the launching thread), 22 ms at 1000 ms, 0.4 ms at 5000 ms;
     started before the warm-up with a 1-s period the same run still lost 1-16 ms per step.  (What remains with a single poll
-    per region, 3-17 ms per step, is not the sampler: two or three of the twenty steps take 20-70 ms longer on the host side
-    with identical kernel times — `step_wall_ms` in the JSON line shows them; Python's collector is off in the region.)
+    per region, 3-17 ms per step, was not the sampler: two or three of the twenty steps took 20-70 ms longer on the host side
+    with identical kernel times — `step_wall_ms` in the JSON line shows them.  It was libfjgpu's cudaMemGetInfo per frame, which
+    queues behind whoever holds the kernel driver's lock; with the batch budget cached the gap is 0.3-0.4 ms.)
     Only the rows that arrive between mark() and stop() are reported; a region shorter than one period falls back to the last
     rows of the warm-up (same load) and says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"

@@ -50,6 +50,7 @@ struct MeshRec {
 
 struct fjgpu_context {
   int device = 0;
+  size_t budget_key = 0, budget_cap_env = 0, budget_cached = 0; int budget_tiles = -1;      // plan_frame: batch budget of the last frame (see there)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
@@ -503,15 +504,23 @@ int plan_frame(fjgpu_context *ctx, const fjgpu_render_params *p, const fjgpu_til
   // budget of the per-batch buffers: FJGPU_SAMPLE_MB (default 16 GiB), never more than 80 % of what the device has free
   // now plus what this context already holds for the purpose
   size_t cap = (size_t)env_int("FJGPU_SAMPLE_MB", 16384) << 20;
+  const size_t per_slot = sizeof(fj::Accum) + (size_t)std::ceil(pl->factor0 * (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec)));
   {
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      const size_t avail = (size_t)(0.8 * (double)(free_b + ctx->d_samples.bytes + ctx->d_queue[0].bytes));
-      cap = std::min(cap, std::max<size_t>(avail, (size_t)64 << 20));
+    // cudaMemGetInfo goes through the kernel driver (and its global lock, which every nvidia-smi / NVML poll on the box takes
+    // too): a frame whose buffers the context already holds reuses the budget of the frame that sized them
+    const size_t want_key = (size_t)pl->wstride * per_slot, held = ctx->d_samples.bytes + ctx->d_queue[0].bytes;
+    if (ctx->budget_key == want_key && ctx->budget_cap_env == cap && ctx->budget_tiles == ntiles && held > 0) cap = ctx->budget_cached;
+    else {
+      size_t free_b = 0, total_b = 0;
+      const size_t cap_env = cap;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const size_t avail = (size_t)(0.8 * (double)(free_b + held));
+        cap = std::min(cap, std::max<size_t>(avail, (size_t)64 << 20));
+      }
+      ctx->budget_key = want_key; ctx->budget_cap_env = cap_env; ctx->budget_tiles = ntiles; ctx->budget_cached = cap;
     }
   }
   pl->budget = cap;
-  const size_t per_slot = sizeof(fj::Accum) + (size_t)std::ceil(pl->factor0 * (2 * sizeof(fj::RayRec) + sizeof(fj::HitRec)));
   long per = (long)(cap / ((size_t)pl->wstride * per_slot));
   per = std::max(1l, std::min<long>(per, std::max(ntiles, 1)));
   const long nbatches = (std::max(ntiles, 1) + per - 1) / per;             // equal batches: no short last batch with long tails
