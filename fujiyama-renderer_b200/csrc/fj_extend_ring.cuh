@@ -79,8 +79,8 @@ __device__ __forceinline__ void load_leaf_triangle3(const RenderArgs &a, const R
   } else load_leaf_triangle(a, rays, tp_, fmt, ridx, index, v0, v1, v2, prim);
 }
 
-// Lane state above the XS_* flags: the object group the ray is traced against (RayRec::target), so that phase B2 does not
-// read the record for it
+// Lane state above the XS_* flags of fj_extend.cuh: the object group the ray is traced against (RayRec::target) from bit 12, so
+// that the transitions and phase E do not read the record for it; bits 9-11 hold the size of the parked leaf
 #define XS_INIT 256u            // S.tmin / S.best_t hold the ray's exact range (set when the first instance is entered)
 #define XS_TARGET_SHIFT 12
 #define XS_CNT_SHIFT 9           // triangles - 1 of the parked leaf (3 bits)
@@ -113,9 +113,10 @@ __global__ void __launch_bounds__(FJ_XT, MINB) k_extend_ring(const RenderArgs a)
   const int FIXUP = (int)0x80000003;            // back in the instance tree with an inner node on the stack: the world-space box ray has to be rebuilt (phase E)
   const unsigned MISS = 0xffffffffu;
   // Cheap transitions of a lane whose next reference is not an inner node, done once per outer iteration after the node loop and
-  // once after the leaf phase: park a triangle leaf when the slot is free, leave a finished BLAS, retire a finished ray.  What stays blocked afterwards waits for a HEAVY phase: a second leaf (or the
-  // end of the walk) behind a parked one -> leaf phase B1; a leaf of the instance tree or FIXUP -> entry phase E.  Inside a
-  // BLAS the bottom stack entry is SENTINEL and below it lies the instance tree's DONE, so no pop underflows.
+  // once after the leaf phase: park a triangle leaf when the slot is free, leave a finished BLAS, retire a finished ray.  What
+  // stays blocked afterwards waits for a HEAVY phase: a second leaf (or the end of the walk) behind a parked one -> leaf phase
+  // B1; a leaf of the instance tree or FIXUP -> entry phase E.  Inside a BLAS the bottom stack entry is SENTINEL and below it
+  // lies the instance tree's DONE, so no pop underflows.
 #define FJ_TRANSIT()                                                                                                              \
   if (node < 0 && node != IDLE) {                                                                                                 \
     if (st & XS_BLAS) {                                                                                                           \
